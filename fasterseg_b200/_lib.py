@@ -1,0 +1,72 @@
+"""ctypes binding of libfsb200.so (C ABI in include/fsb200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, an exception is
+raised (never a silent PyTorch/CPU substitute)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfsb200.so")
+
+FSB_CONV_RELU = 1
+FSB_CONV_AFFINE = 2
+FSB_CONV_FORCE_DIRECT = 4
+FSB_CONV_STATS = 8
+
+
+class FsbError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "Cout", "ksize", "stride", "pad", "dil", "off_h", "off_w",
+                                         "Ho", "Wo", "x_cstride", "y_cstride")] + [("flags", C.c_uint32)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    "fsb_abi_version": (C.c_int, []),
+    "fsb_last_error_string": (C.c_char_p, []),
+    "fsb_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "fsb_conv_packed_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "fsb_pack_conv_weight": (C.c_int, [C.POINTER(ConvDesc), _P, C.c_int64, C.c_int64, _P, _P]),
+    "fsb_bn_fold": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
+    "fsb_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "fsb_stem_conv_nchw": (C.c_int, [C.c_int] * 4 + [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_uint32, _P]),
+    "fsb_bilinear_fwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, C.c_uint32, _P]),
+    "fsb_upsample_logits_nchw": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, _P]),
+    "fsb_upsample_argmax": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, _P]),
+    "fsb_nchw_to_nhwc_f16": (C.c_int, [C.c_int] * 4 + [_P, C.c_int, _P, C.c_int, _P]),
+    "fsb_nhwc_f16_to_nchw": (C.c_int, [C.c_int] * 4 + [_P, C.c_int, _P, C.c_int, _P]),
+    "fsb_copy_channels": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "fsb_bn_stats": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, _P]),
+    "fsb_bn_finalize": (C.c_int, [C.c_int, _P, C.c_double, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "fsb_affine_act": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_uint32, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+def lib():
+    """Load libfsb200.so (once).  Raises FsbError loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FsbError("libfsb200.so not found at %s -- run `python -m fasterseg_b200.build` (needs nvcc); "
+                           "there is no CPU/PyTorch fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.fsb_abi_version() != 1:
+            raise FsbError("libfsb200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().fsb_last_error_string()
+        raise FsbError("%s failed (%d): %s" % (what or "fsb call", rc, msg.decode() if msg else "?"))

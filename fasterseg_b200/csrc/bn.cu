@@ -1,0 +1,171 @@
+// bn.cu -- BatchNorm kernels: eval-mode folding, training statistics (K2), running-stat update (K3), apply.
+// nn.BatchNorm2d semantics of the reference (search/operations.py:79-83 etc., USBatchNorm2d search/slimmable_ops.py:51-70):
+//   eval : y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
+//   train: batch mean, BIASED var for normalisation; running = (1-m)*running + m*{mean, UNBIASED var}
+#include "fsb_common.cuh"
+#include "fsb_internal.h"
+
+namespace fsb {
+
+__global__ void bn_fold_kernel(int C, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               const float* conv_bias, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  const float s = g / sqrtf(var[c] + eps);
+  float sh = b - mean[c] * s;
+  if (conv_bias) sh += conv_bias[c] * s;
+  scale[c] = s;
+  shift[c] = sh;
+}
+int bn_fold_launch(int C, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                   const float* conv_bias, float* scale, float* shift, cudaStream_t stream) {
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, gamma, beta, mean, var, eps, conv_bias, scale, shift);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "bn_fold launch");
+  return FSB_OK;
+}
+
+// per-channel sum / sumsq of an fp16 NHWC tensor.  Block = 256 threads = (256 / cvec_lanes) pixel rows x channel
+// vectors; each thread owns 8 channels (one 16-byte load per pixel), accumulates in fp32 registers, then the block
+// reduces through shared memory and issues one atomicAdd per channel.  Warp-shuffle is not needed for the cross-pixel
+// reduction because a thread's 8 channels never change; the smem tree adds the pixel-row partials.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(int64_t pixels, int C, const __half* __restrict__ x, int xcs, float* __restrict__ stats) {
+  extern __shared__ float red[];  // [rows][C*2]
+  const int cvec = C >> 3;
+  const int rows = blockDim.x / cvec;
+  const int cv = threadIdx.x % cvec;
+  const int row = threadIdx.x / cvec;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (row < rows) {
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * rows + row; p < pixels; p += static_cast<int64_t>(gridDim.x) * rows) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + p * xcs + cv * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x;
+        q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y;
+        q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[(row * C + cv * 8 + j) * 2 + 0] = s[j];
+      red[(row * C + cv * 8 + j) * 2 + 1] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      a += red[(r * C + c) * 2 + 0];
+      b += red[(r * C + c) * 2 + 1];
+    }
+    atomicAdd(&stats[c], a);
+    atomicAdd(&stats[C + c], b);
+  }
+}
+int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, float* stats, cudaStream_t stream) {
+  if (C % 8 || xcs % 8 || C > 2048 || (reinterpret_cast<uintptr_t>(x) & 15))
+    return set_error(FSB_ERR_INVALID, "bn_stats: C and stride must be multiples of 8 (C <= 2048), x 16B aligned");
+  const int cvec = C / 8;
+  const int threads = 256;
+  if (cvec > threads) return set_error(FSB_ERR_INVALID, "bn_stats: C too large");
+  const int rows = threads / cvec;
+  int64_t blocks = (pixels + rows * 8 - 1) / (rows * 8);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  const size_t smem = static_cast<size_t>(rows) * C * 2 * sizeof(float);
+  bn_stats_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(pixels, C, static_cast<const __half*>(x), xcs, stats);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "bn_stats launch");
+  return FSB_OK;
+}
+
+__global__ void bn_finalize_kernel(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                   float* save_mean, float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = static_cast<double>(stats[c]) / count;
+  double var = static_cast<double>(stats[C + c]) / count - mean * mean;
+  if (var < 0) var = 0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  if (scale) scale[c] = g * invstd;
+  if (shift) shift[c] = b - static_cast<float>(mean) * g * invstd;
+  if (save_mean) save_mean[c] = static_cast<float>(mean);
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+int bn_finalize_launch(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
+                       float* save_invstd, cudaStream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, stats, count, gamma, beta, eps, momentum, running_mean,
+                                                         running_var, scale, shift, save_mean, save_invstd);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "bn_finalize launch");
+  return FSB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+affine_act_kernel(int64_t pixels, int cvec, const __half* __restrict__ x, int xcs, const float* __restrict__ scale,
+                  const float* __restrict__ shift, __half* __restrict__ y, int ycs, int relu) {
+  const int64_t total = pixels * cvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvec);
+    const int64_t pix = i / cvec;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + pix * xcs + cv * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + cv * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(scale + cv * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(shift + cv * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(shift + cv * 8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 out;
+    uint32_t* o = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      float r0 = f.x * sc[2 * j] + sf[2 * j];
+      float r1 = f.y * sc[2 * j + 1] + sf[2 * j + 1];
+      if (relu) {
+        r0 = fmaxf(r0, 0.f);
+        r1 = fmaxf(r1, 0.f);
+      }
+      o[j] = pack_half2(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(y + pix * ycs + cv * 8) = out;
+  }
+}
+int affine_act_launch(int64_t pixels, int C, const void* x, int xcs, const float* scale, const float* shift, void* y, int ycs,
+                      uint32_t flags, cudaStream_t stream) {
+  if (C % 8 || xcs % 8 || ycs % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(scale) & 15) || (reinterpret_cast<uintptr_t>(shift) & 15))
+    return set_error(FSB_ERR_INVALID, "affine_act: C/strides multiples of 8, pointers 16B aligned");
+  const int64_t total = pixels * (C / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  affine_act_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pixels, C / 8, static_cast<const __half*>(x), xcs, scale,
+                                                                     shift, static_cast<__half*>(y), ycs,
+                                                                     (flags & FSB_CONV_RELU) ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "affine_act launch");
+  return FSB_OK;
+}
+
+}  // namespace fsb

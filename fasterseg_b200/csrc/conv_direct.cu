@@ -1,0 +1,226 @@
+// conv_direct.cu -- CUDA-core convolution kernels + weight packing.
+//   * pack_conv_weight_kernel : fp32 OIHW (max-width, sliced) -> fp16 [tap][Npad][Kpad] for the tcgen05 kernel
+//   * conv_direct_kernel      : generic NHWC fp16 direct conv on the same packed weights (Cin < 16, odd strides of
+//                               the API, and the device-side cross-check of the tensor-core kernel in tests)
+//   * stem_conv_nchw_kernel   : 3x3 s2 p1 RGB stem reading the caller's NCHW fp32/fp16 tensor directly, so the
+//                               NCHW->NHWC layout change and the fp32->fp16 cast cost no extra HBM round trip
+//                               (ConvNorm at train/model_seg.py:193, search/model_search.py:148)
+#include "fsb_common.cuh"
+#include "fsb_internal.h"
+
+namespace fsb {
+
+// ------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int64_t so, int64_t si, int taps, int Cout, int Cin,
+                                        int npad, int kpad, __half* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(taps) * npad * kpad;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % kpad);
+    const int n = static_cast<int>((i / kpad) % npad);
+    const int tap = static_cast<int>(i / (static_cast<int64_t>(kpad) * npad));
+    float v = 0.f;
+    if (n < Cout && k < Cin) v = w[n * so + k * si + tap];
+    out[i] = __float2half_rn(v);
+  }
+}
+
+int pack_conv_weight(const fsb_conv_desc* d, const float* w, int64_t so, int64_t si, void* packed, cudaStream_t stream) {
+  const ConvGeom g = conv_geom(d);
+  const int64_t total = static_cast<int64_t>(g.taps) * g.npad * g.kpad;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_conv_weight_kernel<<<blocks, 256, 0, stream>>>(w, so, si, g.taps, d->Cout, d->Cin, g.npad, g.kpad,
+                                                      static_cast<__half*>(packed));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "pack_conv_weight");
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic direct conv: one thread = one output pixel x 8 output channels
+// ------------------------------------------------------------------------------------------
+struct DirectParams {
+  fsb_conv_desc d;
+  int npad, kpad, taps;
+  const __half* x;
+  const __half* w;
+  const float* scale;
+  const float* shift;
+  __half* y;
+  float* stats;
+};
+
+__global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) {
+  const fsb_conv_desc& d = p.d;
+  const int64_t npix = static_cast<int64_t>(d.N) * d.Ho * d.Wo;
+  const int cgroups = (d.Cout + 7) / 8;
+  const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (gid >= npix * cgroups) return;
+  const int cg = static_cast<int>(gid % cgroups);
+  const int64_t pix = gid / cgroups;
+  const int wo = static_cast<int>(pix % d.Wo);
+  const int ho = static_cast<int>((pix / d.Wo) % d.Ho);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(d.Wo) * d.Ho));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r = 0; r < d.ksize; ++r) {
+    const int hi = ho * d.stride + r * d.dil - d.pad + d.off_h;
+    if (hi < 0 || hi >= d.H) continue;
+    for (int s = 0; s < d.ksize; ++s) {
+      const int wi = wo * d.stride + s * d.dil - d.pad + d.off_w;
+      if (wi < 0 || wi >= d.W) continue;
+      const __half* xp = p.x + (static_cast<size_t>(n) * d.H * d.W + static_cast<size_t>(hi) * d.W + wi) * d.x_cstride;
+      const __half* wp = p.w + (static_cast<size_t>(r * d.ksize + s) * p.npad + cg * 8) * p.kpad;
+      for (int c = 0; c < d.Cin; ++c) {
+        const float xv = __half2float(xp[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, __half2float(wp[static_cast<size_t>(j) * p.kpad + c]), acc[j]);
+      }
+    }
+  }
+  __half* yp = p.y + static_cast<size_t>(pix) * d.y_cstride + cg * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cg * 8 + j;
+    if (ch >= d.Cout) break;
+    float v = acc[j];
+    if ((d.flags & FSB_CONV_STATS) && p.stats) {
+      atomicAdd(&p.stats[ch], v);
+      atomicAdd(&p.stats[d.Cout + ch], v * v);
+    }
+    if (d.flags & FSB_CONV_AFFINE) v = v * (p.scale ? p.scale[ch] : 1.f) + (p.shift ? p.shift[ch] : 0.f);
+    if (d.flags & FSB_CONV_RELU) v = fmaxf(v, 0.f);
+    yp[j] = __float2half_rn(v);
+  }
+}
+
+int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
+                       void* y, float* stats, cudaStream_t stream) {
+  const ConvGeom g = conv_geom(d);
+  DirectParams p;
+  p.d = *d;
+  p.npad = g.npad;
+  p.kpad = g.kpad;
+  p.taps = g.taps;
+  p.x = static_cast<const __half*>(x);
+  p.w = static_cast<const __half*>(wpacked);
+  p.scale = scale;
+  p.shift = shift;
+  p.y = static_cast<__half*>(y);
+  p.stats = stats;
+  const int64_t total = static_cast<int64_t>(d->N) * d->Ho * d->Wo * ((d->Cout + 7) / 8);
+  const int64_t blocks = (total + 127) / 128;
+  conv_direct_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_direct launch");
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// RGB stem: NCHW in (fp32 or fp16), NHWC fp16 out, 3x3 stride 2 pad 1, fused affine + ReLU.
+// One thread = one output pixel x 16 output channels; weights (27 x Cout fp32) live in shared memory and are
+// read as warp-wide broadcasts.  HBM-bound: 2*3*H*W*4 B in (fp32) + Cout*H*W/4*2 B out.
+// ------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+stem_conv_nchw_kernel(int N, int H, int W, int Cout, const TIn* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ y,
+                      int y_cstride, uint32_t flags) {
+  extern __shared__ float s_w[];  // [27][CoutPad16] then scale[CoutPad16], shift[CoutPad16]
+  const int Ho = H / 2 + (H & 1), Wo = W / 2 + (W & 1);  // floor((H + 2 - 3)/2) + 1
+  const int cpad = (Cout + 15) / 16 * 16;
+  for (int i = threadIdx.x; i < 27 * cpad; i += blockDim.x) {
+    const int co = i % cpad, t = i / cpad;  // t = ci*9 + r*3 + s (OIHW inner order)
+    s_w[i] = (co < Cout) ? w[static_cast<size_t>(co) * 27 + t] : 0.f;
+  }
+  float* s_scale = s_w + 27 * cpad;
+  float* s_shift = s_scale + cpad;
+  for (int i = threadIdx.x; i < cpad; i += blockDim.x) {
+    const bool aff = (flags & FSB_CONV_AFFINE) && i < Cout;
+    s_scale[i] = (aff && scale) ? scale[i] : 1.f;
+    s_shift[i] = (aff && shift) ? shift[i] : 0.f;
+  }
+  __syncthreads();
+  const int groups = cpad / 16;
+  const int wo = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ho = blockIdx.y;
+  const int n = blockIdx.z / groups;
+  const int grp = blockIdx.z % groups;
+  if (wo >= Wo) return;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = ho * 2 + r - 1;
+      const bool hok = hi >= 0 && hi < H;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int wi = wo * 2 + s - 1;
+        float xv = 0.f;
+        if (hok && wi >= 0 && wi < W) xv = static_cast<float>(x[(static_cast<size_t>(n) * 3 + ci) * plane + static_cast<size_t>(hi) * W + wi]);
+        const float4* wp = reinterpret_cast<const float4*>(s_w + (ci * 9 + r * 3 + s) * cpad + grp * 16);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 wv = wp[j4];
+          acc[j4 * 4 + 0] = fmaf(xv, wv.x, acc[j4 * 4 + 0]);
+          acc[j4 * 4 + 1] = fmaf(xv, wv.y, acc[j4 * 4 + 1]);
+          acc[j4 * 4 + 2] = fmaf(xv, wv.z, acc[j4 * 4 + 2]);
+          acc[j4 * 4 + 3] = fmaf(xv, wv.w, acc[j4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  const bool relu = flags & FSB_CONV_RELU;
+  __half* yp = y + (static_cast<size_t>(n) * Ho * Wo + static_cast<size_t>(ho) * Wo + wo) * y_cstride + grp * 16;
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v = acc[j] * s_scale[grp * 16 + j] + s_shift[grp * 16 + j];
+    f[j] = relu ? fmaxf(v, 0.f) : v;
+  }
+  const int remaining = Cout - grp * 16;
+  if (remaining >= 16 && (reinterpret_cast<uintptr_t>(yp) & 15) == 0) {
+    uint4 o0, o1;
+    o0.x = pack_half2(f[0], f[1]);
+    o0.y = pack_half2(f[2], f[3]);
+    o0.z = pack_half2(f[4], f[5]);
+    o0.w = pack_half2(f[6], f[7]);
+    o1.x = pack_half2(f[8], f[9]);
+    o1.y = pack_half2(f[10], f[11]);
+    o1.z = pack_half2(f[12], f[13]);
+    o1.w = pack_half2(f[14], f[15]);
+    reinterpret_cast<uint4*>(yp)[0] = o0;
+    reinterpret_cast<uint4*>(yp)[1] = o1;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < remaining) yp[j] = __float2half_rn(f[j]);
+  }
+}
+
+int stem_conv_nchw_launch(int N, int H, int W, int Cout, const void* x, int x_is_f32, const float* w, const float* scale,
+                          const float* shift, void* y, int y_cstride, uint32_t flags, cudaStream_t stream) {
+  const int Ho = H / 2 + (H & 1), Wo = W / 2 + (W & 1);
+  const int cpad = (Cout + 15) / 16 * 16;
+  const int groups = cpad / 16;
+  const size_t smem = static_cast<size_t>(27 + 2) * cpad * sizeof(float);
+  dim3 block(Wo >= 256 ? 256 : 128);
+  dim3 grid((Wo + block.x - 1) / block.x, Ho, N * groups);
+  if (x_is_f32)
+    stem_conv_nchw_kernel<float><<<grid, block, smem, stream>>>(N, H, W, Cout, static_cast<const float*>(x), w, scale, shift,
+                                                                static_cast<__half*>(y), y_cstride, flags);
+  else
+    stem_conv_nchw_kernel<__half><<<grid, block, smem, stream>>>(N, H, W, Cout, static_cast<const __half*>(x), w, scale,
+                                                                 shift, static_cast<__half*>(y), y_cstride, flags);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "stem_conv_nchw launch");
+  return FSB_OK;
+}
+
+}  // namespace fsb

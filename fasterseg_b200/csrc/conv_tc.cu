@@ -1,0 +1,386 @@
+// conv_tc.cu -- K1: im2col-free implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces F.conv2d (+ BatchNorm eval + ReLU) for every 3x3 / 1x1 conv of the FasterSeg hot path
+// (reference call sites: search/slimmable_ops.py:47, search/operations.py:72-83,146-150,..., search/seg_oprs.py:21-39).
+//
+// GEMM view:  D[M = 128 output pixels (th x tw tile), N = Cout tile] += A[M, K] * B[N, K]^T,
+//             K = taps * Cin, walked as (tap, 64- or 32-channel chunk).
+//   A tile  : for tap (r,s) the 128 x BK slab is ONE TMA box {BK, tw, th, 1} of the NHWC input at the
+//             tap-shifted coordinate; out-of-image rows/cols and channel tails are zero-filled by TMA, so
+//             padding costs nothing and no im2col buffer exists.  Stride-2 convs address one of four
+//             parity planes of the input (each its own tensor map), which keeps every box dense.
+//   B tile  : packed fp16 weights [tap][Npad][Kpad] (K-major), one TMA box {BK, Ntile, 1}.
+//   D       : fp32 accumulator in TMEM (128 lanes x Ntile columns).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2-5 = epilogue (tcgen05.ld -> BN scale/shift -> ReLU -> fp16 -> NHWC store with channel offset/stride,
+// which is how torch.cat(dim=1) call sites become free).
+#include "fsb_common.cuh"
+#include "fsb_internal.h"
+
+namespace fsb {
+
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+
+struct ConvTcParams {
+  CUtensorMap tmap_a[4];
+  CUtensorMap tmap_b;
+  int taps;
+  int tap_map[9];
+  int tap_dh[9];
+  int tap_dw[9];
+  int k_chunks;
+  int Ho, Wo;
+  int tiles_w, tiles_h;
+  int tw, th;
+  int Cout;
+  int n_tile;
+  int stages;
+  int y_cstride;
+  uint32_t flags;
+  uint32_t tmem_cols;
+  const float* scale;
+  const float* shift;
+  __half* y;
+  float* stats;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[256];
+  __shared__ float s_shift[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kABytes = kTileM * BK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * BK * 2;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tile_w = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int tile_h = t % p.tiles_h;
+  const int img = t / p.tiles_h;
+  const int w0 = tile_w * p.tw;
+  const int h0 = tile_h * p.th;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int k_iters = p.taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a[0]);
+    tma_prefetch_desc(&p.tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  // epilogue constants
+  for (int c = threadIdx.x; c < p.n_tile; c += kThreads) {
+    const int ch = n0 + c;
+    const bool ok = ch < p.Cout;
+    s_scale[c] = (ok && (p.flags & FSB_CONV_AFFINE) && p.scale) ? p.scale[ch] : 1.0f;
+    s_shift[c] = (ok && (p.flags & FSB_CONV_AFFINE) && p.shift) ? p.shift[ch] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
+        const int cw = w0 + p.tap_dw[tap];
+        const int chh = h0 + p.tap_dh[tap];
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          const int round = it / p.stages;
+          if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+          uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_4d(sa, ma, &full_bar[s], kc * BK, cw, chh, img);
+          tma_load_3d(sb, &p.tmap_b, &full_bar[s], kc * BK, n0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(p.n_tile));
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % p.stages;
+        const int round = it / p.stages;
+        mbar_wait(&full_bar[s], round & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t sb = sa + kABytes;
+        const uint64_t da = umma_desc_kmajor(sa, BK * 2);
+        const uint64_t db = umma_desc_kmajor(sb, BK * 2);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_f16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+      }
+      umma_commit(&tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ================= epilogue warps 2..5 =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int oh = h0 + m / p.tw;
+    const int ow = w0 + m % p.tw;
+    const bool pix_ok = (oh < p.Ho) && (ow < p.Wo);
+    __half* yrow = p.y + (static_cast<size_t>(img) * p.Ho * p.Wo + static_cast<size_t>(oh) * p.Wo + ow) * p.y_cstride + n0;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0);
+    const bool relu = (p.flags & FSB_CONV_RELU) != 0;
+    const bool do_stats = (p.flags & FSB_CONV_STATS) != 0 && p.stats != nullptr;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < p.n_tile; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (do_stats) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = pix_ok ? f[j] : 0.f;
+          float b = a * a;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (lane == 0 && n0 + c + j < p.Cout) {
+            atomicAdd(&p.stats[n0 + c + j], a);
+            atomicAdd(&p.stats[p.Cout + n0 + c + j], b);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = f[j] * s_scale[c + j] + s_shift[c + j];
+        f[j] = relu ? fmaxf(x, 0.f) : x;
+      }
+      if (pix_ok) {
+        const int remaining = p.Cout - (n0 + c);
+        if (remaining >= 16 && vec_ok) {
+          uint4 o0, o1;
+          o0.x = pack_half2(f[0], f[1]);
+          o0.y = pack_half2(f[2], f[3]);
+          o0.z = pack_half2(f[4], f[5]);
+          o0.w = pack_half2(f[6], f[7]);
+          o1.x = pack_half2(f[8], f[9]);
+          o1.y = pack_half2(f[10], f[11]);
+          o1.z = pack_half2(f[12], f[13]);
+          o1.w = pack_half2(f[14], f[15]);
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+          dst[0] = o0;
+          dst[1] = o1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < remaining) yrow[c + j] = __float2half_rn(f[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int encode_tiled(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return set_error(FSB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                              : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
+                   bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] base %p stride0 %llu",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
+             rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base, (unsigned long long)strides_bytes[0]);
+    return set_error(FSB_ERR_CUDA, buf);
+  }
+  return FSB_OK;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+ConvGeom conv_geom(const fsb_conv_desc* d) {
+  ConvGeom g;
+  g.taps = d->ksize * d->ksize;
+  g.bk = (d->Cin % 64 == 0) ? 64 : 32;
+  g.kpad = (d->Cin + g.bk - 1) / g.bk * g.bk;
+  g.n_tiles = (d->Cout + 255) / 256;
+  int per = (d->Cout + g.n_tiles - 1) / g.n_tiles;
+  g.n_tile = (per + 15) / 16 * 16;
+  g.npad = g.n_tile * g.n_tiles;
+  return g;
+}
+
+int conv_tc_supported(const fsb_conv_desc* d) {
+  if (d->Cin < 16 || (d->x_cstride % 8) != 0) return 0;
+  if (!(d->ksize == 1 || d->ksize == 3) || !(d->stride == 1 || d->stride == 2)) return 0;
+  return 1;
+}
+
+int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
+                   void* y, float* stats, cudaStream_t stream) {
+  const ConvGeom g = conv_geom(d);
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wpacked) & 15))
+    return set_error(FSB_ERR_INVALID, "conv_tc: x / wpacked must be 16-byte aligned");
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.taps = g.taps;
+  p.k_chunks = g.kpad / g.bk;
+  p.Ho = d->Ho;
+  p.Wo = d->Wo;
+  p.tw = d->Wo >= 16 ? 16 : 8;
+  p.th = kTileM / p.tw;
+  p.tiles_w = (d->Wo + p.tw - 1) / p.tw;
+  p.tiles_h = (d->Ho + p.th - 1) / p.th;
+  p.Cout = d->Cout;
+  p.n_tile = g.n_tile;
+  p.y_cstride = d->y_cstride;
+  p.flags = d->flags;
+  p.scale = scale;
+  p.shift = shift;
+  p.y = static_cast<__half*>(y);
+  p.stats = stats;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(g.n_tile)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  const size_t stage_bytes = static_cast<size_t>(kTileM) * g.bk * 2 + static_cast<size_t>(g.n_tile) * g.bk * 2;
+  const int k_iters = p.taps * p.k_chunks;
+  int stages = static_cast<int>((96 * 1024) / stage_bytes);
+  if (stages < 2) stages = 2;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > k_iters) stages = k_iters;
+  p.stages = stages;
+  const size_t smem_bytes = stage_bytes * stages + 1024;
+
+  // ---- A tensor maps ----
+  const __half* xb = static_cast<const __half*>(x);
+  const uint64_t cs = static_cast<uint64_t>(d->x_cstride) * 2;  // bytes per pixel step
+  const uint32_t boxA[4] = {static_cast<uint32_t>(g.bk), static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), 1u};
+  if (d->stride == 1) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(d->N)};
+    const uint64_t str[3] = {cs, cs * d->W, cs * d->W * d->H};
+    int rc = encode_tiled(&p.tmap_a[0], xb, 4, dims, str, boxA, g.bk * 2);
+    if (rc) return rc;
+    for (int r = 0; r < d->ksize; ++r)
+      for (int s = 0; s < d->ksize; ++s) {
+        const int tp = r * d->ksize + s;
+        p.tap_map[tp] = 0;
+        p.tap_dh[tp] = r * d->dil - d->pad + d->off_h;
+        p.tap_dw[tp] = s * d->dil - d->pad + d->off_w;
+      }
+  } else {
+    bool used[4] = {false, false, false, false};
+    for (int r = 0; r < d->ksize; ++r)
+      for (int s = 0; s < d->ksize; ++s) {
+        const int tp = r * d->ksize + s;
+        const int qh = r * d->dil - d->pad + d->off_h;
+        const int qw = s * d->dil - d->pad + d->off_w;
+        const int ph = ((qh % 2) + 2) % 2, pw = ((qw % 2) + 2) % 2;
+        p.tap_map[tp] = ph * 2 + pw;
+        p.tap_dh[tp] = floordiv(qh, 2);
+        p.tap_dw[tp] = floordiv(qw, 2);
+        used[ph * 2 + pw] = true;
+      }
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        if (!used[ph * 2 + pw]) continue;
+        const int Hp = (d->H - ph + 1) / 2, Wp = (d->W - pw + 1) / 2;
+        if (Hp <= 0 || Wp <= 0) return set_error(FSB_ERR_INVALID, "conv_tc: empty parity plane");
+        const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(Wp), static_cast<uint64_t>(Hp),
+                                  static_cast<uint64_t>(d->N)};
+        const uint64_t str[3] = {2 * cs, 2 * cs * d->W, cs * d->W * d->H};
+        const __half* base = xb + (static_cast<size_t>(ph) * d->W + pw) * d->x_cstride;
+        int rc = encode_tiled(&p.tmap_a[ph * 2 + pw], base, 4, dims, str, boxA, g.bk * 2);
+        if (rc) return rc;
+      }
+    // prefetch target must be a valid map
+    if (!used[0]) p.tmap_a[0] = p.tmap_a[p.tap_map[0]];
+  }
+  // ---- B tensor map ----
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(g.kpad), static_cast<uint64_t>(g.npad), static_cast<uint64_t>(g.taps)};
+    const uint64_t str[2] = {static_cast<uint64_t>(g.kpad) * 2, static_cast<uint64_t>(g.kpad) * g.npad * 2};
+    const uint32_t boxB[3] = {static_cast<uint32_t>(g.bk), static_cast<uint32_t>(g.n_tile), 1u};
+    int rc = encode_tiled(&p.tmap_b, wpacked, 3, dims, str, boxB, g.bk * 2);
+    if (rc) return rc;
+  }
+  dim3 grid(static_cast<unsigned>(p.tiles_w * p.tiles_h * d->N), static_cast<unsigned>(g.n_tiles));
+  cudaError_t e;
+  if (g.bk == 64) {
+    static bool attr64 = false;
+    if (!attr64) {
+      e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc<64>)");
+      attr64 = true;
+    }
+    conv_tc_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    static bool attr32 = false;
+    if (!attr32) {
+      e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc<32>)");
+      attr32 = true;
+    }
+    conv_tc_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_tc launch");
+  return FSB_OK;
+}
+
+}  // namespace fsb

@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI (include/fsb200.h).
+
+Activations are torch fp16 tensors with logical shape (N, C, H, W) and channels-last strides
+(N: H*W*cs, C: 1, H: W*cs, W: cs) where the channel stride `cs` may exceed C (a channel slice of a
+wider concat buffer).  PyTorch is plumbing here: it owns the device memory and the stream; every
+arithmetic kernel is ours.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, FSB_CONV_AFFINE, FSB_CONV_FORCE_DIRECT, FSB_CONV_RELU, FSB_CONV_STATS, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def empty_nhwc(N, Cc, H, W, device, dtype=torch.float16) -> torch.Tensor:
+    """(N, C, H, W)-shaped view of a fresh NHWC buffer."""
+    return torch.empty((N, H, W, Cc), device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+def nhwc_info(t: torch.Tensor) -> Tuple[int, int, int, int, int]:
+    """-> (N, C, H, W, channel_stride); raises unless `t` is fp16 channels-last addressable."""
+    if t.dtype != torch.float16 or t.dim() != 4 or not t.is_cuda:
+        raise ValueError("expected a 4-D CUDA fp16 tensor, got %s %s" % (t.dtype, tuple(t.shape)))
+    N, Cc, H, W = t.shape
+    sn, sc, sh, sw = t.stride()
+    cs = sw
+    ok = (Cc == 1 or sc == 1) and cs >= Cc and (H == 1 or sh == W * cs) and (N == 1 or sn == H * W * cs)
+    if W == 1:
+        cs = sh if H > 1 else (sn if N > 1 else max(Cc, 1))
+        ok = (Cc == 1 or sc == 1)
+    if not ok:
+        raise ValueError("tensor is not NHWC-addressable: shape %s strides %s" % (tuple(t.shape), t.stride()))
+    return N, Cc, H, W, cs
+
+
+def is_nhwc_half(t: torch.Tensor) -> bool:
+    try:
+        nhwc_info(t)
+        return True
+    except ValueError:
+        return False
+
+
+def to_nhwc_half(x: torch.Tensor) -> torch.Tensor:
+    """Reference-layout tensor (NCHW fp32/fp16 contiguous) -> NHWC fp16 via our layout kernel."""
+    if is_nhwc_half(x):
+        return x
+    if x.dim() != 4 or not x.is_cuda or x.dtype not in (torch.float32, torch.float16):
+        raise ValueError("expected a CUDA NCHW fp32/fp16 tensor")
+    x = x.contiguous()
+    N, Cc, H, W = x.shape
+    cpad = (Cc + 7) // 8 * 8
+    buf = torch.empty((N, H, W, cpad), device=x.device, dtype=torch.float16)
+    if cpad != Cc:
+        buf.zero_()
+    y = buf.permute(0, 3, 1, 2)[:, :Cc]
+    check(_lib.lib().fsb_nchw_to_nhwc_f16(N, Cc, H, W, _ptr(x), int(x.dtype == torch.float32), _ptr(y), cpad, _stream()),
+          "fsb_nchw_to_nhwc_f16")
+    return y
+
+
+def to_nchw(x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    N, Cc, H, W, cs = nhwc_info(x)
+    y = torch.empty((N, Cc, H, W), device=x.device, dtype=dtype)
+    check(_lib.lib().fsb_nhwc_f16_to_nchw(N, Cc, H, W, _ptr(x), cs, _ptr(y), int(dtype == torch.float32), _stream()),
+          "fsb_nhwc_f16_to_nchw")
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+def conv_out_size(H, W, ksize, stride, pad, dil=1, off_h=0, off_w=0):
+    ext = dil * (ksize - 1) + 1
+    return (H - off_h + 2 * pad - ext) // stride + 1, (W - off_w + 2 * pad - ext) // stride + 1
+
+
+def make_conv_desc(N, H, W, Cin, Cout, ksize, stride, pad, x_cstride, y_cstride, flags=0, dil=1, off_h=0, off_w=0) -> ConvDesc:
+    Ho, Wo = conv_out_size(H, W, ksize, stride, pad, dil, off_h, off_w)
+    return ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, dil, off_h, off_w, Ho, Wo, x_cstride, y_cstride, flags)
+
+
+def pack_conv_weight(w: torch.Tensor, Cin: int, Cout: int, ksize: int) -> torch.Tensor:
+    """fp32 OIHW master weight (possibly max-width; only [:Cout, :Cin] is read) -> packed fp16 buffer."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] == ksize and w.shape[3] == ksize
+    assert w.stride(3) == 1 and w.stride(2) == ksize
+    d = ConvDesc(1, 8, 8, Cin, Cout, ksize, 1, 0, 1, 0, 0, 8, 8, Cin, Cout, 0)
+    nbytes = _lib.lib().fsb_conv_packed_bytes(C.byref(d))
+    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.float16)
+    check(_lib.lib().fsb_pack_conv_weight(C.byref(d), _ptr(w), w.stride(0), w.stride(1), _ptr(out), _stream()),
+          "fsb_pack_conv_weight")
+    return out
+
+
+def bn_fold(gamma, beta, mean, var, eps, conv_bias=None):
+    Cc = mean.numel()
+    out = torch.empty((2, Cc), device=mean.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_fold(Cc, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), float(eps), _ptr(conv_bias),
+                                 _ptr(out[0]), _ptr(out[1]), _stream()), "fsb_bn_fold")
+    return out[0], out[1]
+
+
+def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=False, out=None, off=(0, 0),
+             stats=None, force_direct=False):
+    """y = act(conv(x) * scale + shift); x/out NHWC fp16 views (see module docstring)."""
+    N, Cin, H, W, xcs = nhwc_info(x)
+    Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    if out is None:
+        out = empty_nhwc(N, Cout, Ho, Wo, x.device)
+    No, Co, Hy, Wy, ycs = nhwc_info(out)
+    assert (No, Co, Hy, Wy) == (N, Cout, Ho, Wo), ((No, Co, Hy, Wy), (N, Cout, Ho, Wo))
+    flags = (FSB_CONV_RELU if relu else 0) | (FSB_CONV_AFFINE if (scale is not None or shift is not None) else 0)
+    if stats is not None:
+        flags |= FSB_CONV_STATS
+    if force_direct:
+        flags |= FSB_CONV_FORCE_DIRECT
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, ycs, flags)
+    check(_lib.lib().fsb_conv_fwd(C.byref(d), _ptr(x), _ptr(wpacked), _ptr(scale), _ptr(shift), _ptr(out), _ptr(stats),
+                                  _stream()), "fsb_conv_fwd")
+    return out
+
+
+def stem_conv_nchw(x, w, scale, shift, relu=True, out=None):
+    """3x3 s2 p1 RGB stem on the caller's NCHW fp32/fp16 tensor."""
+    assert x.dim() == 4 and x.shape[1] == 3 and x.is_cuda and x.is_contiguous()
+    assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (3, 3, 3)
+    N, _, H, W = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    if out is None:
+        out = empty_nhwc(N, Cout, Ho, Wo, x.device)
+    _, _, _, _, ycs = nhwc_info(out)
+    flags = (FSB_CONV_RELU if relu else 0) | (FSB_CONV_AFFINE if scale is not None else 0)
+    check(_lib.lib().fsb_stem_conv_nchw(N, H, W, Cout, _ptr(x), int(x.dtype == torch.float32), _ptr(w), _ptr(scale),
+                                        _ptr(shift), _ptr(out), ycs, flags, _stream()), "fsb_stem_conv_nchw")
+    return out
+
+
+def bilinear(x, size, relu=False, out=None):
+    N, Cc, Hi, Wi, xcs = nhwc_info(x)
+    Ho, Wo = int(size[0]), int(size[1])
+    if out is None:
+        out = empty_nhwc(N, Cc, Ho, Wo, x.device)
+    _, Co, Hy, Wy, ycs = nhwc_info(out)
+    assert (Co, Hy, Wy) == (Cc, Ho, Wo)
+    check(_lib.lib().fsb_bilinear_fwd(N, Cc, Hi, Wi, Ho, Wo, _ptr(x), xcs, _ptr(out), ycs, FSB_CONV_RELU if relu else 0,
+                                      _stream()), "fsb_bilinear_fwd")
+    return out
+
+
+def upsample_logits(x, size, dtype=torch.float32, out=None):
+    """NHWC fp16 logits -> NCHW (contiguous) logits at `size`, bilinear align_corners=True."""
+    N, Cc, Hi, Wi, xcs = nhwc_info(x)
+    Ho, Wo = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((N, Cc, Ho, Wo), device=x.device, dtype=dtype)
+    assert out.is_contiguous() and out.dtype in (torch.float16, torch.float32)
+    check(_lib.lib().fsb_upsample_logits_nchw(N, Cc, Hi, Wi, Ho, Wo, _ptr(x), xcs, _ptr(out),
+                                              int(out.dtype == torch.float32), _stream()), "fsb_upsample_logits_nchw")
+    return out
+
+
+def upsample_argmax(x, size, out=None):
+    N, Cc, Hi, Wi, xcs = nhwc_info(x)
+    Ho, Wo = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((N, Ho, Wo), device=x.device, dtype=torch.uint8)
+    check(_lib.lib().fsb_upsample_argmax(N, Cc, Hi, Wi, Ho, Wo, _ptr(x), xcs, _ptr(out), _stream()), "fsb_upsample_argmax")
+    return out
+
+
+def copy_channels(x, out):
+    N, Cc, H, W, xcs = nhwc_info(x)
+    No, Co, Ho, Wo, ycs = nhwc_info(out)
+    assert (N, Cc, H, W) == (No, Co, Ho, Wo)
+    check(_lib.lib().fsb_copy_channels(N * H * W, Cc, _ptr(x), xcs, _ptr(out), ycs, _stream()), "fsb_copy_channels")
+    return out
+
+
+def bn_stats(x, stats=None):
+    N, Cc, H, W, xcs = nhwc_info(x)
+    if stats is None:
+        stats = torch.zeros(2 * Cc, device=x.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_stats(N * H * W, Cc, _ptr(x), xcs, _ptr(stats), _stream()), "fsb_bn_stats")
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, want_save=False):
+    Cc = stats.numel() // 2
+    buf = torch.empty((4, Cc), device=stats.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_finalize(Cc, _ptr(stats), float(count), _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+                                     _ptr(running_mean), _ptr(running_var), _ptr(buf[0]), _ptr(buf[1]),
+                                     _ptr(buf[2]) if want_save else None, _ptr(buf[3]) if want_save else None, _stream()),
+          "fsb_bn_finalize")
+    return buf[0], buf[1], buf[2], buf[3]
+
+
+def affine_act(x, scale, shift, relu=False, out=None):
+    N, Cc, H, W, xcs = nhwc_info(x)
+    if out is None:
+        out = empty_nhwc(N, Cc, H, W, x.device)
+    _, _, _, _, ycs = nhwc_info(out)
+    check(_lib.lib().fsb_affine_act(N * H * W, Cc, _ptr(x), xcs, _ptr(scale), _ptr(shift), _ptr(out), ycs,
+                                    FSB_CONV_RELU if relu else 0, _stream()), "fsb_affine_act")
+    return out

@@ -1,0 +1,138 @@
+/* fsb200.h -- C ABI of libfsb200.so: B200 (sm_100a) kernels for the FasterSeg conv hot path.
+ *
+ * The reference (VITA-Group/FasterSeg) has no FFI of its own: its hot path bottoms out in
+ * torch.nn.functional calls.  Each entry point below therefore cites the
+ * reference call site(s) whose arithmetic it replaces; the Python operator classes in
+ * fasterseg_b200/{operations,slimmable_ops,seg_oprs,model_seg}.py (same names / signatures /
+ * state_dict keys as the reference) bind these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - activations are NHWC fp16 ("channels-last"), addressed as base + pixel * cstride + channel,
+ *     so a channel slice of a wider concat buffer is just (base + offset, cstride) -- this is how
+ *     torch.cat(dim=1) call sites become zero-copy;
+ *   - master weights stay fp32 OIHW in the caller's module (checkpoint format); kernels consume a
+ *     packed fp16 copy produced by fsb_pack_conv_weight;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - return value: 0 on success, negative fsb_status otherwise; fsb_last_error_string() gives the
+ *     text of the last failure on the calling thread.  The library owns no buffers.
+ */
+#ifndef FSB200_H_
+#define FSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSB_ABI_VERSION 1
+
+typedef enum fsb_status {
+  FSB_OK = 0,
+  FSB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  FSB_ERR_CUDA = -2,        /* CUDA runtime or driver error (text in fsb_last_error_string) */
+  FSB_ERR_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+  FSB_ERR_NO_DEVICE = -4
+} fsb_status;
+
+/* epilogue / layout flags for fsb_conv_desc.flags */
+#define FSB_CONV_RELU 1u        /* y = max(y, 0) */
+#define FSB_CONV_AFFINE 2u      /* y = y * scale[c] + shift[c]  (BN eval folded, or conv bias in shift) */
+#define FSB_CONV_FORCE_DIRECT 4u /* use the CUDA-core direct kernel (validation / odd shapes) */
+#define FSB_CONV_STATS 8u       /* also accumulate per-channel sum / sum-of-squares of the (pre-affine) fp32 conv
+                                   output into stats[0..Cout) / stats[Cout..2Cout) (BN train, K2) */
+
+/* One convolution launch.  Replaces F.conv2d at search/slimmable_ops.py:47 and every nn.Conv2d in
+ * search/operations.py:42-534 / search/seg_oprs.py:17-39,228-274, fused with the BatchNorm (eval) +
+ * ReLU that follow it there. */
+typedef struct fsb_conv_desc {
+  int32_t N, H, W;       /* input batch / height / width                      */
+  int32_t Cin, Cout;     /* ACTIVE channels (slimmable slice), not max widths */
+  int32_t ksize;         /* 1 or 3                                            */
+  int32_t stride;        /* 1 or 2                                            */
+  int32_t pad;           /* 0 or 1 (ksize 3 uses dil*1)                       */
+  int32_t dil;           /* 1 (kept for API parity with the reference ctor)   */
+  int32_t off_h, off_w;  /* input origin shift: conv runs on x[:, off_h:, off_w:, :]
+                            (FactorizedReduce's x[:,:,1:,1:], operations.py:523) */
+  int32_t Ho, Wo;        /* output height / width                             */
+  int32_t x_cstride;     /* elements between consecutive pixels of x (>= Cin) */
+  int32_t y_cstride;     /* elements between consecutive pixels of y (>= Cout)*/
+  uint32_t flags;
+} fsb_conv_desc;
+
+int fsb_abi_version(void);
+const char* fsb_last_error_string(void);
+/* number of SMs / compute capability of the current device (host ints, may be NULL) */
+int fsb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* --- weights -------------------------------------------------------------------------------- */
+/* bytes of the packed fp16 weight buffer for `d` */
+size_t fsb_conv_packed_bytes(const fsb_conv_desc* d);
+/* w: fp32 OIHW master weight, possibly a max-width tensor: element (o,i,r,s) at
+ * w[o*w_stride_o + i*w_stride_i + r*ksize + s]; only [0,Cout) x [0,Cin) is read
+ * (USConv2d's weight[:out, :in] slice, search/slimmable_ops.py:42). */
+int fsb_pack_conv_weight(const fsb_conv_desc* d, const float* w, int64_t w_stride_o, int64_t w_stride_i,
+                         void* packed, void* stream);
+/* scale = gamma / sqrt(var + eps), shift = beta - mean * scale (+ scale*conv_bias if conv_bias != NULL).
+ * nn.BatchNorm2d eval forward as used at operations.py:79-83,149,221,... gamma/beta may be NULL (1/0). */
+int fsb_bn_fold(int C, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                const float* conv_bias, float* scale, float* shift, void* stream);
+
+/* --- convolution ---------------------------------------------------------------------------- */
+/* y[n,ho,wo,co] = act( (sum_{r,s,ci} x[n, ho*stride + r*dil - pad + off_h, wo*stride + s*dil - pad + off_w, ci]
+ *                      * w[co,ci,r,s]) * scale[co] + shift[co] )
+ * x, y: fp16 NHWC with the strides in `d`; wpacked from fsb_pack_conv_weight; scale/shift fp32[Cout] or NULL;
+ * stats fp32[2*Cout] (only with FSB_CONV_STATS; caller zeroes it).
+ * Dense 3x3 / 1x1 contractions run as an im2col-free implicit GEMM on tcgen05 tensor cores with TMA-staged
+ * NHWC tiles; Cin < 16 (the RGB stem) and FSB_CONV_FORCE_DIRECT use the CUDA-core direct kernel. */
+int fsb_conv_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
+                 void* y, float* stats, void* stream);
+
+/* Stem conv reading the caller's NCHW tensor directly (fp32 if x_is_f32 else fp16), 3x3 stride 2 pad 1,
+ * Cin = 3, fused BN(eval)+ReLU, fp16 NHWC out.  ConvNorm at train/model_seg.py:193, search/model_search.py:148.
+ * w: fp32 OIHW (read directly, no packing). */
+int fsb_stem_conv_nchw(int N, int H, int W, int Cout, const void* x_nchw, int x_is_f32, const float* w,
+                       const float* scale, const float* shift, void* y, int y_cstride, uint32_t flags, void* stream);
+
+/* --- resize / layout ------------------------------------------------------------------------ */
+/* F.interpolate(mode='bilinear', align_corners=True) on fp16 NHWC; call sites operations.py:271,275,437,444,
+ * model_search.py:339-343, model_seg.py:305,310,317.  flags: FSB_CONV_RELU applies ReLU after the resize
+ * (BasicResidual_downup_*: upsample then ReLU, operations.py:275-276). */
+int fsb_bilinear_fwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x, int x_cstride, void* y,
+                     int y_cstride, uint32_t flags, void* stream);
+/* Final logits upsample (model_seg.py:365, model_search.py:353-357): fp16 NHWC (C classes, cstride) low-res
+ * logits -> NCHW output at (Ho, Wo), bilinear align_corners=True.  out_dtype: 0 = fp16, 1 = fp32. */
+int fsb_upsample_logits_nchw(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x, int x_cstride, void* y,
+                             int out_dtype, void* stream);
+/* Same interpolation fused with argmax over classes -> uint8 label map [N, Ho, Wo] (first max wins, like
+ * torch.argmax / np.argmax at tools/engine/evaluator.py:315-318). */
+int fsb_upsample_argmax(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x, int x_cstride, uint8_t* labels,
+                        void* stream);
+/* NCHW (fp32 or fp16) -> NHWC fp16 and back; plumbing for callers that hand us reference-layout tensors. */
+int fsb_nchw_to_nhwc_f16(int N, int C, int H, int W, const void* x, int x_is_f32, void* y, int y_cstride,
+                         void* stream);
+int fsb_nhwc_f16_to_nchw(int N, int C, int H, int W, const void* x, int x_cstride, void* y, int y_is_f32,
+                         void* stream);
+/* strided channel-slice copy (torch.cat(dim=1) call sites that cannot be made zero-copy) */
+int fsb_copy_channels(int64_t pixels, int C, const void* x, int x_cstride, void* y, int y_cstride, void* stream);
+
+/* --- BatchNorm training path (K2/K3) -------------------------------------------------------- */
+/* per-channel sum and sum of squares over `pixels` of an fp16 NHWC tensor: stats[0..C) += sum, stats[C..2C) += sumsq */
+int fsb_bn_stats(int64_t pixels, int C, const void* x, int x_cstride, float* stats, void* stream);
+/* from stats (summed over `count` elements per channel, possibly all-reduced across ranks by the caller):
+ * mean, biased var -> scale/shift for the apply pass; running stats updated with momentum and UNBIASED var
+ * (nn.BatchNorm2d training semantics; sequential per invocation, model_search.py:326-329). Also writes
+ * save_mean / save_invstd (fp32[C]) for the backward pass when non-NULL. */
+int fsb_bn_finalize(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* save_mean, float* save_invstd, void* stream);
+/* y = act(x * scale[c] + shift[c]) elementwise on fp16 NHWC (in place allowed) */
+int fsb_affine_act(int64_t pixels, int C, const void* x, int x_cstride, const float* scale, const float* shift,
+                   void* y, int y_cstride, uint32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB200_H_ */

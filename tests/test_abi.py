@@ -1,0 +1,55 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads and exports every symbol that
+include/fsb200.h declares; the ctypes binding covers the same set (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "fsb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fasterseg_b200 import _lib, build
+    build.build()
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(dll, s), "libfsb200.so does not export " + s
+    assert sorted(_lib.EXPORTED_SYMBOLS) == syms
+    assert _lib.lib().fsb_abi_version() == 1
+
+
+def test_conv_desc_layout_matches_header():
+    from fasterseg_b200._lib import ConvDesc
+    assert ctypes.sizeof(ConvDesc) == 16 * 4
+    src = open(os.path.join(ROOT, "include", "fsb200.h")).read()
+    body = src[src.index("typedef struct fsb_conv_desc {"):src.index("} fsb_conv_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in re.findall(r"(?:int32_t|uint32_t)\s+([^;]+);", body):
+        names += [n.strip() for n in decl.split(",")]
+    assert names == [f[0] for f in ConvDesc._fields_]
+
+
+def test_packed_bytes_is_pure_host_math():
+    from fasterseg_b200 import _lib
+    d = _lib.ConvDesc(1, 8, 8, 64, 64, 3, 1, 1, 1, 0, 0, 8, 8, 64, 64, 0)
+    assert _lib.lib().fsb_conv_packed_bytes(ctypes.byref(d)) == 9 * 64 * 64 * 2
+    d = _lib.ConvDesc(1, 8, 8, 48, 19, 1, 1, 0, 1, 0, 0, 8, 8, 48, 19, 0)
+    assert _lib.lib().fsb_conv_packed_bytes(ctypes.byref(d)) == 1 * 32 * 64 * 2
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from fasterseg_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.FsbError):
+        _lib.lib()

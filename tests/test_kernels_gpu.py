@@ -1,0 +1,265 @@
+"""GPU parity tests of the individual CUDA kernels (through the C ABI) against the CPU oracle.
+
+Tolerance for the fp16-storage path (north_star: "within 1e-3 relative fp16 tolerance"): inputs and
+weights are rounded to fp16 ONCE, the oracle computes in fp32 on those same rounded values, our kernels
+accumulate in fp32 and round the result to fp16 once -> elementwise |err| <= 1e-3 * |ref| + 1e-3 * rms(ref).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fasterseg_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3
+
+
+def _F():
+    from fasterseg_b200 import functional as F_
+    return F_
+
+
+def _close(got, ref, rel=REL):
+    got = got.double()
+    ref = ref.double()
+    rms = ref.pow(2).mean().sqrt().item() + 1e-12
+    err = (got - ref).abs()
+    bound = rel * ref.abs() + rel * rms
+    bad = (err > bound)
+    assert not bad.any(), "max err %.3e (rms %.3e), %d/%d outside tolerance" % (err.max().item(), rms, int(bad.sum()), bad.numel())
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.from_numpy(np.random.RandomState(seed).standard_normal(shape).astype(np.float32) * scale)
+
+
+def _nhwc(x_nchw_f32):
+    """CPU NCHW fp32 -> CUDA NHWC fp16 view (plain torch plumbing for test inputs)."""
+    return x_nchw_f32.cuda().half().contiguous(memory_format=torch.channels_last)
+
+
+CONV_CASES = [
+    # N, Cin, Cout, k, stride, H, W
+    (1, 32, 32, 3, 1, 16, 32),
+    (2, 64, 64, 3, 1, 24, 40),
+    (1, 64, 128, 3, 2, 32, 48),
+    (1, 96, 64, 3, 1, 16, 16),
+    (1, 128, 64, 1, 1, 16, 32),
+    (1, 256, 128, 1, 1, 8, 16),
+    (1, 128, 19, 1, 1, 16, 32),
+    (2, 48, 80, 3, 1, 9, 13),
+    (2, 384, 384, 3, 1, 8, 16),
+    (1, 32, 128, 3, 1, 20, 36),
+    (2, 32, 64, 3, 2, 9, 13),
+    (1, 64, 64, 3, 2, 18, 30),
+    (1, 160, 320, 3, 1, 5, 7),
+    (1, 192, 128, 3, 1, 32, 64),
+    (3, 80, 48, 1, 1, 6, 10),
+    (1, 16, 16, 3, 1, 8, 8),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("direct", [False, True])
+def test_conv_bn_relu_matches_oracle(case, direct):
+    F_ = _F()
+    N, Cin, Cout, k, stride, Hh, Ww = case
+    seed = hash(case) % 100000
+    x = _rand((N, Cin, Hh, Ww), seed).half().float()
+    w = (_rand((Cout, Cin, k, k), seed + 1) * (2.0 / (Cin * k * k)) ** 0.5).half().float()
+    scale = torch.from_numpy(np.random.RandomState(seed + 2).uniform(0.5, 1.5, Cout).astype(np.float32))
+    shift = _rand((Cout,), seed + 3, 0.2)
+    pad = 1 if k == 3 else 0
+    ref = torch.relu(orc.conv2d(x, w, None, stride, pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    wp = F_.pack_conv_weight(w.cuda(), Cin, Cout, k)
+    y = F_.conv_fwd(_nhwc(x), wp, Cout, k, stride, pad, scale.cuda(), shift.cuda(), relu=True, force_direct=direct)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == tuple(ref.shape)
+    _close(y.float().cpu(), ref)
+
+
+def test_conv_no_epilogue_and_stats():
+    F_ = _F()
+    N, Cin, Cout, Hh, Ww = 2, 64, 96, 12, 20
+    x = _rand((N, Cin, Hh, Ww), 5).half().float()
+    w = (_rand((Cout, Cin, 3, 3), 6) * 0.06).half().float()
+    ref = orc.conv2d(x, w, None, 1, 1)
+    wp = F_.pack_conv_weight(w.cuda(), Cin, Cout, 3)
+    for direct in (False, True):
+        stats = torch.zeros(2 * Cout, device="cuda")
+        y = F_.conv_fwd(_nhwc(x), wp, Cout, 3, 1, 1, stats=stats, force_direct=direct)
+        torch.cuda.synchronize()
+        _close(y.float().cpu(), ref)
+        s = stats.cpu().double()
+        np.testing.assert_allclose(s[:Cout].numpy(), ref.double().sum(dim=(0, 2, 3)).numpy(), rtol=2e-4, atol=2e-2)
+        np.testing.assert_allclose(s[Cout:].numpy(), ref.double().pow(2).sum(dim=(0, 2, 3)).numpy(), rtol=2e-4, atol=2e-2)
+
+
+def test_conv_sliced_weights_and_concat_views():
+    """USConv2d slicing (slimmable_ops.py:42) + torch.cat(dim=1) as channel-offset stores/loads."""
+    F_ = _F()
+    Cmax_o, Cmax_i, co, ci = 96, 64, 48, 32
+    wmax = (_rand((Cmax_o, Cmax_i, 3, 3), 11) * 0.08).half().float()
+    x_full = _rand((2, 64, 10, 14), 12).half().float()  # conv reads channels [16:48) of a 64-channel buffer
+    xs = x_full[:, 16:16 + ci]
+    ref = torch.relu(orc.conv2d(xs, wmax[:co, :ci], None, 1, 1))
+    wp = F_.pack_conv_weight(wmax.cuda(), ci, co, 3)
+    xg = _nhwc(x_full)[:, 16:16 + ci]
+    cat = F_.empty_nhwc(2, 80, 10, 14, "cuda")
+    cat.zero_()
+    F_.conv_fwd(xg, wp, co, 3, 1, 1, relu=True, out=cat[:, 32:32 + co])
+    torch.cuda.synchronize()
+    _close(cat[:, 32:32 + co].float().cpu(), ref)
+    assert float(cat[:, :32].abs().max()) == 0.0
+
+
+def test_factorized_reduce_offset_conv():
+    """1x1 stride-2 conv on x[:, :, 1:, 1:] (operations.py:523) through desc.off_h/off_w."""
+    F_ = _F()
+    x = _rand((2, 64, 12, 16), 21).half().float()
+    w = (_rand((48, 64, 1, 1), 22) * 0.15).half().float()
+    ref0 = orc.conv2d(x, w, None, 2, 0)
+    ref1 = orc.conv2d(x[:, :, 1:, 1:], w, None, 2, 0)
+    wp = F_.pack_conv_weight(w.cuda(), 64, 48, 1)
+    for direct in (False, True):
+        y0 = F_.conv_fwd(_nhwc(x), wp, 48, 1, 2, 0, force_direct=direct)
+        y1 = F_.conv_fwd(_nhwc(x), wp, 48, 1, 2, 0, off=(1, 1), force_direct=direct)
+        torch.cuda.synchronize()
+        _close(y0.float().cpu(), ref0)
+        _close(y1.float().cpu(), ref1)
+
+
+@pytest.mark.parametrize("co", [32, 48])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_stem_conv_nchw(co, dtype):
+    F_ = _F()
+    x = _rand((2, 3, 33, 50), 31)
+    if dtype == torch.float16:
+        x = x.half().float()
+    w = _rand((co, 3, 3, 3), 32) * 0.27
+    scale = torch.from_numpy(np.random.RandomState(33).uniform(0.5, 1.5, co).astype(np.float32))
+    shift = _rand((co,), 34, 0.2)
+    ref = torch.relu(orc.conv2d(x, w, None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    y = F_.stem_conv_nchw(x.cuda().to(dtype), w.cuda(), scale.cuda(), shift.cuda())
+    torch.cuda.synchronize()
+    _close(y.float().cpu(), ref)
+
+
+def test_convnorm_gate_config0():
+    """BASELINE.json configs[0]: ConvNorm(3->32/48, k3, s2) on 1x3x256x512 vs the REFERENCE's golden sample."""
+    F_ = _F()
+    z = H.load_npz("convnorm_gate.npz")
+    x = orc.random_input((1, 3, 256, 512), seed=12345)
+    for co in (32, 48):
+        shapes = {"conv.0.weight": (co, 3, 3, 3), "conv.1.weight": (co,), "conv.1.bias": (co,),
+                  "conv.1.running_mean": (co,), "conv.1.running_var": (co,)}
+        sd = orc.random_state_dict(shapes, seed=12345 + co)
+        sc, sh = F_.bn_fold(sd["conv.1.weight"].cuda(), sd["conv.1.bias"].cuda(), sd["conv.1.running_mean"].cuda(),
+                            sd["conv.1.running_var"].cuda(), orc.BN_EPS)
+        y = F_.stem_conv_nchw(x.cuda(), sd["conv.0.weight"].cuda(), sc, sh).float().cpu()
+        ref_s = torch.from_numpy(z["co%d.eval/sample" % co])
+        _close(y[:, :, ::8, ::8], ref_s)
+        full = orc.conv_norm(x, orc.Params(sd), 3, 2, 1, False)
+        _close(y, full)
+
+
+def test_bilinear_golden_and_random():
+    F_ = _F()
+    z = H.load_npz("bilinear.npz")
+    n = len([k for k in z.files if k.endswith("/x")])
+    for i in range(n):
+        x = torch.from_numpy(z["%d/x" % i])
+        # pad channels 5 -> 8 for the 16-byte vector path
+        xp = torch.zeros(x.shape[0], 8, x.shape[2], x.shape[3])
+        xp[:, :5] = x
+        xh = xp.half().float()
+        ref = orc.bilinear_ac(xh, z["%d/y" % i].shape[2:])
+        y = F_.bilinear(_nhwc(xh), ref.shape[2:])
+        torch.cuda.synchronize()
+        _close(y.float().cpu(), ref)
+        _close(y.float().cpu()[:, :5], torch.from_numpy(z["%d/y" % i]), rel=2e-3)  # vs the reference itself (fp32 input)
+    x = _rand((2, 64, 17, 23), 41).half().float()
+    for size in ((8, 11), (34, 46), (17, 23)):
+        ref = torch.relu(orc.bilinear_ac(x, size))
+        y = F_.bilinear(_nhwc(x), size, relu=True)
+        _close(y.float().cpu(), ref)
+
+
+def test_upsample_logits_and_argmax():
+    F_ = _F()
+    x = _rand((2, 19, 9, 12), 51).half().float()
+    xp = torch.zeros(2, 24, 9, 12)
+    xp[:, :19] = x
+    xg = _nhwc(xp)[:, :19]
+    ref = orc.bilinear_ac(x, (72, 96))
+    for dt in (torch.float32, torch.float16):
+        y = F_.upsample_logits(xg, (72, 96), dtype=dt)
+        torch.cuda.synchronize()
+        assert y.is_contiguous() and tuple(y.shape) == (2, 19, 72, 96)
+        _close(y.float().cpu(), ref, rel=1e-3 if dt == torch.float16 else 1e-5)
+    lab = F_.upsample_argmax(xg, (72, 96)).cpu()
+    ref_lab = ref.argmax(1).to(torch.uint8)
+    mism = lab != ref_lab
+    if mism.any():  # only fp32 rounding-order near-ties may differ
+        top2 = ref.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1])[mism]
+        assert float(margin.max()) < 1e-5, "argmax mismatch with margin %g" % float(margin.max())
+    assert float(mism.float().mean()) < 1e-3
+    # bit-exact against argmax of OUR OWN fp32 upsampled logits
+    own = F_.upsample_logits(xg, (72, 96), dtype=torch.float32).argmax(1).to(torch.uint8).cpu()
+    assert torch.equal(lab, own)
+    # odd output width / non-multiple-of-8 tails
+    ref2 = orc.bilinear_ac(x, (13, 21))
+    y2 = F_.upsample_logits(xg, (13, 21), dtype=torch.float32)
+    _close(y2.cpu(), ref2, rel=1e-5)
+    lab2 = F_.upsample_argmax(xg, (13, 21)).cpu()
+    assert torch.equal(lab2, y2.argmax(1).to(torch.uint8).cpu())
+
+
+def test_layout_roundtrip_and_copy():
+    F_ = _F()
+    x = _rand((2, 19, 7, 11), 61)
+    y = F_.to_nhwc_half(x.cuda())
+    assert tuple(y.shape) == (2, 19, 7, 11)
+    torch.testing.assert_close(y.float().cpu(), x.half().float(), rtol=0, atol=0)
+    back = F_.to_nchw(y, torch.float32)
+    torch.testing.assert_close(back.cpu(), x.half().float(), rtol=0, atol=0)
+    a = _nhwc(_rand((2, 32, 5, 6), 62))
+    cat = F_.empty_nhwc(2, 64, 5, 6, "cuda")
+    cat.zero_()
+    F_.copy_channels(a, cat[:, 16:48])
+    assert torch.equal(cat[:, 16:48].contiguous(), a.contiguous())
+
+
+def test_bn_train_kernels():
+    F_ = _F()
+    Cc = 48
+    x = (_rand((3, Cc, 9, 14), 71) * 1.7 + 0.3).half().float()
+    gamma = torch.from_numpy(np.random.RandomState(72).uniform(0.5, 1.5, Cc).astype(np.float32))
+    beta = _rand((Cc,), 73, 0.2)
+    rm, rv = _rand((Cc,), 74, 0.1), torch.from_numpy(np.random.RandomState(75).uniform(0.5, 1.5, Cc).astype(np.float32))
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = torch.relu(orc.batchnorm(x, gamma, beta, rm_ref, rv_ref, True))
+    xg = _nhwc(x)
+    stats = F_.bn_stats(xg)
+    rm_g, rv_g = rm.cuda(), rv.cuda()
+    scale, shift, mean, invstd = F_.bn_finalize(stats, 3 * 9 * 14, gamma.cuda(), beta.cuda(), orc.BN_EPS, orc.BN_MOMENTUM,
+                                                rm_g, rv_g, want_save=True)
+    y = F_.affine_act(xg, scale, shift, relu=True)
+    torch.cuda.synchronize()
+    _close(y.float().cpu(), ref)
+    np.testing.assert_allclose(rm_g.cpu().numpy(), rm_ref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rv_g.cpu().numpy(), rv_ref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mean.cpu().numpy(), x.mean(dim=(0, 2, 3)).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_errors_are_loud():
+    F_ = _F()
+    from fasterseg_b200._lib import FsbError
+    x = _nhwc(_rand((1, 32, 8, 8), 81))
+    wp = F_.pack_conv_weight(_rand((32, 32, 3, 3), 82).cuda(), 32, 32, 3)
+    bad_out = F_.empty_nhwc(1, 32, 7, 8, "cuda")
+    with pytest.raises((FsbError, AssertionError)):
+        F_.conv_fwd(x, wp, 32, 3, 1, 1, out=bad_out)
