@@ -25,8 +25,11 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def empty_nhwc(N, Cc, H, W, device, dtype=torch.float16) -> torch.Tensor:
-    """(N, C, H, W)-shaped view of a fresh NHWC buffer."""
-    return torch.empty((N, H, W, Cc), device=device, dtype=dtype).permute(0, 3, 1, 2)
+    """(N, C, H, W)-shaped view of a fresh NHWC buffer; the pixel stride is rounded up to 8 channels so that
+    every pixel starts on a 16-byte boundary (vector stores, TMA strides)."""
+    cpad = (Cc + 7) // 8 * 8
+    buf = torch.empty((N, H, W, cpad), device=device, dtype=dtype).permute(0, 3, 1, 2)
+    return buf if cpad == Cc else buf[:, :Cc]
 
 
 def nhwc_info(t: torch.Tensor) -> Tuple[int, int, int, int, int]:

@@ -1,0 +1,80 @@
+"""GPU parity of the reference-facing operator classes (fasterseg_b200.operations / seg_oprs) against golden
+vectors produced by the UNMODIFIED reference classes, and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fasterseg_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+WML = [4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.]
+OPS_META = H.load_json("ops_meta.json")
+
+
+def _build(meta):
+    from fasterseg_b200 import operations as ops
+    from fasterseg_b200 import seg_oprs
+    cls = meta["cls"]
+    if cls == "ConvNorm":
+        return ops.ConvNorm(meta["C_in"], meta["C_out"], kernel_size=meta["kernel_size"], stride=meta["stride"],
+                            slimmable=meta["slimmable"], width_mult_list=WML)
+    if cls == "FactorizedReduce":
+        return ops.FactorizedReduce(meta["C_in"], meta["C_out"], meta["stride"], meta["slimmable"], WML)
+    if cls == "Head":
+        return seg_oprs.Head(meta["C_in"], 19, False)
+    if cls == "FeatureFusion":
+        return seg_oprs.FeatureFusion(meta["C_in"], meta["C_in"])
+    return getattr(ops, cls)(meta["C_in"], meta["C_out"], 3, meta["stride"], 1, 1, meta["slimmable"], WML)
+
+
+def _load(mod, meta):
+    sd = H.case_state_dict(meta)
+    missing, unexpected = mod.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    for m in mod.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eps, m.momentum = orc.BN_EPS, orc.BN_MOMENTUM
+    return sd
+
+
+def _check(got, ref, what, rel_norm=2.5e-3, rel_elem=6e-3):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    rms = np.sqrt((ref ** 2).mean()) + 1e-12
+    nerr = H.rel_err(got, ref)
+    assert nerr < rel_norm, "%s: norm-wise rel err %.3e" % (what, nerr)
+    bad = np.abs(got - ref) > rel_elem * (np.abs(ref) + rms)
+    assert not bad.any(), "%s: %d elements outside elementwise bound, max err %.3e" % (what, bad.sum(), np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("name", sorted(OPS_META))
+def test_operator_class_matches_reference(name):
+    from fasterseg_b200 import functional as F_
+    meta = OPS_META[name]
+    z = H.load_npz("ops.npz")
+    mod = _build(meta).cuda()
+    if meta["shapes"]:
+        _load(mod, meta)
+    if meta.get("slimmable") and meta["ratio"] is not None:
+        mod.set_ratio(tuple(meta["ratio"]))
+    mod.train(meta["training"])
+    x = torch.from_numpy(H.gen_x(meta["seed"], tuple(meta["x_shape"]))).cuda()
+    with torch.no_grad():
+        y = mod(x)
+    torch.cuda.synchronize()
+    ref = z[name + "/y"]
+    y = F_.to_nhwc_half(y) if not F_.is_nhwc_half(y) else y
+    _check(y.float().cpu().numpy(), ref, name)
+    if meta["training"]:
+        sd = mod.state_dict()
+        n = 0
+        for k in z.files:
+            if k.startswith(name + "/after:"):
+                key = k.split("after:")[1]
+                np.testing.assert_allclose(sd[key].cpu().numpy(), z[k], rtol=3e-3, atol=3e-4, err_msg=key)
+                n += 1
+        if meta["shapes"]:
+            assert n > 0
