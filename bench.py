@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- FasterSeg student (arch_1, F12.L16) inference FPS @ 1x3x1024x2048 on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one 1024x2048 frame through the student network (BASELINE.json configs[1]).
+  value : frames/s with the frame already resident in HBM (CUDA-graph replay of the whole forward; full-resolution
+          fp16 NCHW logits are materialised, i.e. the work the reference's `model(input)` does in
+          tools/utils/darts_utils.py:182-223)
+  e2e   : frames/s through the public host API (fasterseg_b200.runtime.InferencePipeline): pinned-host fp32 NCHW
+          frame -> H2D -> network -> fused upsample+argmax -> uint8 label map D2H, 3 frames in flight
+  roofline    : the dominant kernel (tcgen05 implicit-GEMM conv) on its most expensive launch, timed live
+  cpu_baseline: the CPU oracle port of the reference path (same weights) on the host cores (N=1, rank 0 only)
+Multi-GPU: inference has no exchange step -> N independent replicas ("replicas only"), weak scaling.
+`--impl reference` times the reference's CPU path (oracle port; the Python reference tree does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fasterseg_student_fps_1024x2048"
+UNIT = "frames/s"
+H, W = 1024, 2048
+STUDENT_GFLOP = 55.54  # 2*MAC over the 45 convs of arch_1 @1024x2048
+
+
+def synth_weights_(model, seed=12345):
+    """Synthetic parameters per SURVEY 8(d): kaiming_normal(fan_in, relu) convs, BN gamma/beta/running stats randomised
+    so eval-mode BN is not a no-op.  Deterministic (CPU generator) so every rank / impl sees the same network."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in sorted(model.state_dict().items()):
+            if name.endswith("num_batches_tracked"):
+                continue
+            shp = tuple(p.shape)
+            if p.dim() == 4:
+                fan_in = shp[1] * shp[2] * shp[3]
+                v = torch.randn(shp, generator=g) * (2.0 / fan_in) ** 0.5
+            elif name.endswith("running_var"):
+                v = torch.rand(shp, generator=g) + 0.5
+            elif name.endswith("running_mean"):
+                v = torch.randn(shp, generator=g) * 0.1
+            elif name.endswith("conv_1x1.bias"):
+                v = torch.randn(shp, generator=g) * 0.05
+            elif name.endswith(".weight"):
+                v = 1.0 + 0.1 * torch.randn(shp, generator=g)
+            else:
+                v = 0.1 * torch.randn(shp, generator=g)
+            p.copy_(v)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eps, m.momentum = 1e-5, 0.1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def dominant_kernel_roofline(device):
+    """Time the tcgen05 implicit-GEMM conv on its most expensive launch of the student frame: heads8.conv_3x3
+    (3x3, 128 -> 128 channels on the 128x256 1/8-resolution map, 9.66 GFLOP = 17 % of the frame; stem.1.conv2 has the
+    same FLOPs).  Algorithmic work per launch: 2*9*128*128*(128*256) FLOP; bytes = in + out + weights, each once."""
+    from fasterseg_b200 import functional as F_
+    Cin = Cout = 128
+    h, w = 128, 256
+    flops = 2.0 * 9 * Cin * Cout * h * w
+    abytes = 2.0 * (Cin * h * w + Cout * h * w + 9 * Cin * Cout)
+    nbuf = 12  # 12 x (8.4 + 8.4) MB = 201 MB > 126 MB L2: every launch reads its input from HBM
+    xs = [F_.empty_nhwc(1, Cin, h, w, device).normal_() for _ in range(nbuf)]
+    ys = [F_.empty_nhwc(1, Cout, h, w, device) for _ in range(nbuf)]
+    wt = torch.randn(Cout, Cin, 3, 3, device=device) * 0.03
+    wp = F_.pack_conv_weight(wt, Cin, Cout, 3)
+    scale = torch.rand(Cout, device=device) + 0.5
+    shift = torch.randn(Cout, device=device) * 0.1
+    for i in range(nbuf):
+        F_.conv_fwd(xs[i], wp, Cout, 3, 1, 1, scale, shift, relu=True, out=ys[i])
+    torch.cuda.synchronize()
+    reps = 5
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    for _ in range(reps):
+        for i in range(nbuf):
+            F_.conv_fwd(xs[i], wp, Cout, 3, 1, 1, scale, shift, relu=True, out=ys[i])
+    en.record()
+    en.synchronize()
+    us = st.elapsed_time(en) * 1000.0 / (reps * nbuf)
+    pk = measured_peaks()
+    t_tensor = flops / (pk["tflops"] * 1e12)
+    t_hbm = abytes / (pk["hbm_gbs"] * 1e9)
+    if t_tensor >= t_hbm:
+        achieved = flops / (us * 1e-6) / 1e12
+        return {"kernel": "conv_tc_kernel<64> (heads8.conv_3x3: 3x3 128->128 @128x256)", "bound": "tensor",
+                "achieved": round(achieved, 2), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["tflops"], 4),
+                "traffic": None, "us_per_launch": round(us, 2), "peak_source": pk["source"],
+                "algorithmic_flops": flops, "algorithmic_bytes": abytes}
+    achieved = abytes / (us * 1e-6) / 1e9
+    return {"kernel": "conv_tc_kernel<64>", "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "us_per_launch": round(us, 2), "peak_source": pk["source"]}
+
+
+def cpu_port_fps(model_state_cpu, frames, threads):
+    """Time the oracle port (CPU fp32 restatement of train/model_seg.py:337-366) on `frames` 1024x2048 frames."""
+    from oracle import fasterseg_oracle as orc
+    from tests import helpers as Hh
+    torch.set_num_threads(threads)
+    st, _ = Hh.student_structure(1)
+    x = orc.random_input((1, 3, H, W), seed=12345)
+    with torch.no_grad():
+        orc.student_forward(x, model_state_cpu, st, training=False)  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            orc.student_forward(x, model_state_cpu, st, training=False)
+        dt = time.perf_counter() - t0
+    return frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fasterseg_b200 import zoo
+    threads = os.cpu_count() or 1
+    model = zoo.build_network(1)
+    synth_weights_(model)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_port_fps(sd, 1, threads)
+    fps, dt = cpu_port_fps(sd, args.steps, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1000.0 / fps, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FasterSeg student arch_1 F12.L16 inference 1x3x1024x2048 (reference CPU path, oracle port)"},
+            "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d frames of 1x3x1024x2048, torch CPU fp32, %d threads" % (args.steps, threads)},
+            "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 30:
+            args.steps = 30  # bounded CPU sample (a frame costs ~0.2-1 s of CPU time)
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    from fasterseg_b200 import zoo
+    from fasterseg_b200.runtime import GraphedInference, InferencePipeline
+
+    model = zoo.build_network(1)
+    synth_weights_(model)
+    model = model.to(device).eval()
+
+    # ---- device-resident FPS (value) ----
+    g = torch.Generator(device="cpu").manual_seed(12345 + rank)
+    npool = 6  # 6 x 25.2 MB = 151 MB of distinct frames > 126 MB L2
+    pool = [torch.randn(1, 3, H, W, generator=g).to(device) for _ in range(npool)]
+    runner = GraphedInference(model, pool[0], mode="logits", logits_dtype=torch.float16)
+    for i in range(args.warmup):
+        runner(pool[i % npool])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    for i in range(args.steps):
+        runner(pool[i % npool])
+    en.record()
+    torch.cuda.synchronize()
+    ms_total = st.elapsed_time(en)
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * args.steps / (ms_total / 1000.0)
+
+    # ---- end-to-end FPS through the host API ----
+    pipe = InferencePipeline(model, pool[0], mode="labels", depth=3)
+    host_frames = [torch.randn(1, 3, H, W, generator=g).pin_memory() for _ in range(4)]
+    pipe.run(host_frames[i % 4] for i in range(max(3, args.warmup // 2)))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    checksum = [0]
+
+    def consume(lbl):
+        checksum[0] += int(lbl[0, 0, 0])  # touch the result on the host
+
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    pipe.run((host_frames[i % 4] for i in range(e2e_steps)), consume)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * e2e_steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    roof = dominant_kernel_roofline(device)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16", "data": "synthetic",
+        "config": {"workload": "FasterSeg student arch_1 (F12.L16, lasts=[2,1]) inference, 1x3x1024x2048, batch 1 per GPU, "
+                               "fp16 storage / fp32 accumulate, full-res fp16 logits materialised",
+                   "parallelism": "replicas x%d (no exchange step in inference)" % world,
+                   "l2_policy": "inputs rotate through a 6-frame device pool (151 MB > 126 MB L2); activations per frame "
+                                "(~430 MB) exceed L2",
+                   "timing": "CUDA events around %d CUDA-graph replays, max over ranks" % args.steps,
+                   "frame_gflop": STUDENT_GFLOP},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_fps, 1), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                "what": "pinned fp32 NCHW frame -> H2D -> student -> fused upsample+argmax -> uint8 labels D2H; 3 frames in flight",
+                "steps": e2e_steps},
+        "gpu_launches": runner.launches_per_replay * args.steps + pipe.launches_per_frame * e2e_steps,
+        "launches_per_frame": runner.launches_per_replay,
+        "roofline": roof,
+        "frame_tflops": round(STUDENT_GFLOP * value / world / 1000.0, 2),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        frames = 3
+        fps, dt = cpu_port_fps(sd, frames, threads)
+        line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d frames of 1x3x1024x2048 through the CPU oracle port (torch CPU fp32), %.1f s" % (frames, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
