@@ -1,4 +1,6 @@
 // api.cu -- the extern "C" surface of libfsb200.so (declared in include/fsb200.h).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "fsb_internal.h"
@@ -6,6 +8,7 @@
 namespace fsb {
 
 static thread_local char g_err[512] = "";
+thread_local cudaError_t g_launch_err = cudaSuccess;
 
 int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -14,6 +17,24 @@ int set_error(int code, const char* msg) {
 int set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
   return FSB_ERR_CUDA;
+}
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("FSB_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 PFN_encodeTiled get_encode_tiled() {
@@ -72,6 +93,11 @@ extern "C" {
 
 int fsb_abi_version(void) { return FSB_ABI_VERSION; }
 const char* fsb_last_error_string(void) { return g_err; }
+
+int fsb_set_pdl(int enabled) {
+  g_pdl = enabled ? 1 : 0;
+  return FSB_OK;
+}
 
 int fsb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

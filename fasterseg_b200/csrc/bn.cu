@@ -9,6 +9,8 @@ namespace fsb {
 
 __global__ void bn_fold_kernel(int C, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                                const float* conv_bias, float* scale, float* shift) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float g = gamma ? gamma[c] : 1.f;
@@ -21,8 +23,8 @@ __global__ void bn_fold_kernel(int C, const float* gamma, const float* beta, con
 }
 int bn_fold_launch(int C, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                    const float* conv_bias, float* scale, float* shift, cudaStream_t stream) {
-  bn_fold_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, gamma, beta, mean, var, eps, conv_bias, scale, shift);
-  cudaError_t e = cudaGetLastError();
+  FSB_LAUNCH(bn_fold_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, C, gamma, beta, mean, var, eps, conv_bias, scale, shift);
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_fold launch");
   return FSB_OK;
 }
@@ -33,6 +35,8 @@ int bn_fold_launch(int C, const float* gamma, const float* beta, const float* me
 // reduction because a thread's 8 channels never change; the smem tree adds the pixel-row partials.
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(int64_t pixels, int C, const __half* __restrict__ x, int xcs, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [rows][C*2]
   const int cvec = C >> 3;
   const int rows = blockDim.x / cvec;
@@ -82,8 +86,8 @@ int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, float* stats,
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 4) blocks = 148 * 4;
   const size_t smem = static_cast<size_t>(rows) * C * 2 * sizeof(float);
-  bn_stats_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(pixels, C, static_cast<const __half*>(x), xcs, stats);
-  cudaError_t e = cudaGetLastError();
+  FSB_LAUNCH(bn_stats_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, pixels, C, static_cast<const __half*>(x), xcs, stats);
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_stats launch");
   return FSB_OK;
 }
@@ -91,6 +95,8 @@ int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, float* stats,
 __global__ void bn_finalize_kernel(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                                    float* save_mean, float* save_invstd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = static_cast<double>(stats[c]) / count;
@@ -112,9 +118,9 @@ __global__ void bn_finalize_kernel(int C, const float* stats, double count, cons
 int bn_finalize_launch(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
                        float* save_invstd, cudaStream_t stream) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, stats, count, gamma, beta, eps, momentum, running_mean,
+  FSB_LAUNCH(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, C, stats, count, gamma, beta, eps, momentum, running_mean,
                                                          running_var, scale, shift, save_mean, save_invstd);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_finalize launch");
   return FSB_OK;
 }
@@ -122,6 +128,8 @@ int bn_finalize_launch(int C, const float* stats, double count, const float* gam
 __global__ void __launch_bounds__(256)
 affine_act_kernel(int64_t pixels, int cvec, const __half* __restrict__ x, int xcs, const float* __restrict__ scale,
                   const float* __restrict__ shift, __half* __restrict__ y, int ycs, int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = pixels * cvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -160,10 +168,10 @@ int affine_act_launch(int64_t pixels, int C, const void* x, int xcs, const float
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  affine_act_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pixels, C / 8, static_cast<const __half*>(x), xcs, scale,
+  FSB_LAUNCH(affine_act_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8, static_cast<const __half*>(x), xcs, scale,
                                                                      shift, static_cast<__half*>(y), ycs,
                                                                      (flags & FSB_CONV_RELU) ? 1 : 0);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "affine_act launch");
   return FSB_OK;
 }

@@ -13,6 +13,8 @@ namespace fsb {
 // ------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int64_t so, int64_t si, int taps, int Cout, int Cin,
                                         int npad, int kpad, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(taps) * npad * kpad;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -30,9 +32,9 @@ int pack_conv_weight(const fsb_conv_desc* d, const float* w, int64_t so, int64_t
   const int64_t total = static_cast<int64_t>(g.taps) * g.npad * g.kpad;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_conv_weight_kernel<<<blocks, 256, 0, stream>>>(w, so, si, g.taps, d->Cout, d->Cin, g.npad, g.kpad,
+  FSB_LAUNCH(pack_conv_weight_kernel, dim3(blocks), dim3(256), 0, stream, w, so, si, g.taps, d->Cout, d->Cin, g.npad, g.kpad,
                                                       static_cast<__half*>(packed));
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "pack_conv_weight");
   return FSB_OK;
 }
@@ -52,6 +54,8 @@ struct DirectParams {
 };
 
 __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const fsb_conv_desc& d = p.d;
   const int64_t npix = static_cast<int64_t>(d.N) * d.Ho * d.Wo;
   const int cgroups = (d.Cout + 7) / 8;
@@ -112,8 +116,8 @@ int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacke
   p.stats = stats;
   const int64_t total = static_cast<int64_t>(d->N) * d->Ho * d->Wo * ((d->Cout + 7) / 8);
   const int64_t blocks = (total + 127) / 128;
-  conv_direct_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  FSB_LAUNCH(conv_direct_kernel, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream, p);
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "conv_direct launch");
   return FSB_OK;
 }
@@ -128,6 +132,8 @@ __global__ void __launch_bounds__(256)
 stem_conv_nchw_kernel(int N, int H, int W, int Cout, const TIn* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ y,
                       int y_cstride, uint32_t flags) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];  // [27][CoutPad16] then scale[CoutPad16], shift[CoutPad16]
   const int Ho = H / 2 + (H & 1), Wo = W / 2 + (W & 1);  // floor((H + 2 - 3)/2) + 1
   const int cpad = (Cout + 15) / 16 * 16;
@@ -213,12 +219,12 @@ int stem_conv_nchw_launch(int N, int H, int W, int Cout, const void* x, int x_is
   dim3 block(Wo >= 256 ? 256 : 128);
   dim3 grid((Wo + block.x - 1) / block.x, Ho, N * groups);
   if (x_is_f32)
-    stem_conv_nchw_kernel<float><<<grid, block, smem, stream>>>(N, H, W, Cout, static_cast<const float*>(x), w, scale, shift,
+    FSB_LAUNCH(stem_conv_nchw_kernel<float>, dim3(grid), dim3(block), smem, stream, N, H, W, Cout, static_cast<const float*>(x), w, scale, shift,
                                                                 static_cast<__half*>(y), y_cstride, flags);
   else
-    stem_conv_nchw_kernel<__half><<<grid, block, smem, stream>>>(N, H, W, Cout, static_cast<const __half*>(x), w, scale,
+    FSB_LAUNCH(stem_conv_nchw_kernel<__half>, dim3(grid), dim3(block), smem, stream, N, H, W, Cout, static_cast<const __half*>(x), w, scale,
                                                                  shift, static_cast<__half*>(y), y_cstride, flags);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "stem_conv_nchw launch");
   return FSB_OK;
 }

@@ -57,6 +57,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   __shared__ float s_scale[256];
   __shared__ float s_shift[256];
 
+  pdl_launch_dependents();  // let the next kernel's prologue overlap our main loop / tail
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kABytes = kTileM * BK * 2;
@@ -89,6 +90,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     tmem_alloc(&tmem_base_smem, p.tmem_cols);
     tmem_relinquish();
   }
+  pdl_wait();  // predecessor's outputs (our x) and anything it still reads (our y) are safe from here on
   // epilogue constants
   for (int c = threadIdx.x; c < p.n_tile; c += kThreads) {
     const int ch = n0 + c;
@@ -257,10 +259,7 @@ ConvGeom conv_geom(const fsb_conv_desc* d) {
   g.taps = d->ksize * d->ksize;
   g.bk = (d->Cin % 64 == 0) ? 64 : 32;
   g.kpad = (d->Cin + g.bk - 1) / g.bk * g.bk;
-  g.n_tiles = (d->Cout + 255) / 256;
-  int per = (d->Cout + g.n_tiles - 1) / g.n_tiles;
-  g.n_tile = (per + 15) / 16 * 16;
-  g.npad = g.n_tile * g.n_tiles;
+  g.npad = (d->Cout + 15) / 16 * 16;
   return g;
 }
 
@@ -286,7 +285,18 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   p.tiles_w = (d->Wo + p.tw - 1) / p.tw;
   p.tiles_h = (d->Ho + p.th - 1) / p.th;
   p.Cout = d->Cout;
-  p.n_tile = g.n_tile;
+  // Output-channel tiling.  Default: one N tile (<= 256 columns).  When the spatial tiling alone cannot fill the
+  // machine (small maps at 1/16, 1/32 resolution), split N further so that more SMs pull operands from L2 in parallel
+  // (each CTA then streams A 16 KB + a thinner B slab per k-step).  B boxes past npad rows are zero-filled by TMA.
+  const int m_tiles = p.tiles_w * p.tiles_h * d->N;
+  int n_tiles = (g.npad + 255) / 256;
+  int n_tile = ((g.npad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  const int sms = sm_count();
+  while (m_tiles * n_tiles < sms && n_tile > 32) {
+    n_tile = (n_tile / 2 + 15) / 16 * 16;
+    n_tiles = (g.npad + n_tile - 1) / n_tile;
+  }
+  p.n_tile = n_tile;
   p.y_cstride = d->y_cstride;
   p.flags = d->flags;
   p.scale = scale;
@@ -294,12 +304,14 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   p.y = static_cast<__half*>(y);
   p.stats = stats;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(g.n_tile)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(n_tile)) cols <<= 1;
   p.tmem_cols = cols;
 
-  const size_t stage_bytes = static_cast<size_t>(kTileM) * g.bk * 2 + static_cast<size_t>(g.n_tile) * g.bk * 2;
+  const size_t stage_bytes = static_cast<size_t>(kTileM) * g.bk * 2 + static_cast<size_t>(n_tile) * g.bk * 2;
   const int k_iters = p.taps * p.k_chunks;
-  int stages = static_cast<int>((96 * 1024) / stage_bytes);
+  // <= one CTA per SM anyway -> give the pipeline (almost) the whole shared memory; otherwise keep 2 CTAs/SM resident
+  const size_t smem_budget = (m_tiles * n_tiles <= sms) ? 192 * 1024 : 96 * 1024;
+  int stages = static_cast<int>(smem_budget / stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > k_iters) stages = k_iters;
@@ -355,30 +367,29 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(g.kpad), static_cast<uint64_t>(g.npad), static_cast<uint64_t>(g.taps)};
     const uint64_t str[2] = {static_cast<uint64_t>(g.kpad) * 2, static_cast<uint64_t>(g.kpad) * g.npad * 2};
-    const uint32_t boxB[3] = {static_cast<uint32_t>(g.bk), static_cast<uint32_t>(g.n_tile), 1u};
+    const uint32_t boxB[3] = {static_cast<uint32_t>(g.bk), static_cast<uint32_t>(n_tile), 1u};
     int rc = encode_tiled(&p.tmap_b, wpacked, 3, dims, str, boxB, g.bk * 2);
     if (rc) return rc;
   }
-  dim3 grid(static_cast<unsigned>(p.tiles_w * p.tiles_h * d->N), static_cast<unsigned>(g.n_tiles));
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
   cudaError_t e;
   if (g.bk == 64) {
     static bool attr64 = false;
     if (!attr64) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc<64>)");
       attr64 = true;
     }
-    conv_tc_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(p);
+    e = launch_kernel(conv_tc_kernel<64>, grid, dim3(kThreads), smem_bytes, stream, p);
   } else {
     static bool attr32 = false;
     if (!attr32) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc<32>)");
       attr32 = true;
     }
-    conv_tc_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(p);
+    e = launch_kernel(conv_tc_kernel<32>, grid, dim3(kThreads), smem_bytes, stream, p);
   }
-  e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv_tc launch");
   return FSB_OK;
 }

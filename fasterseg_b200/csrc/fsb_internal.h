@@ -23,11 +23,42 @@ struct ConvGeom {
   int taps;     // ksize^2
   int bk;       // K chunk (channels per TMA box / smem row): 64 if Cin % 64 == 0 else 32
   int kpad;     // Cin rounded up to bk
-  int n_tiles;  // output-channel tiles (grid.y)
-  int n_tile;   // UMMA N per tile (multiple of 16, <= 256)
-  int npad;     // n_tile * n_tiles
+  int npad;     // Cout rounded up to 16 (rows of the packed weight matrix per tap)
 };
 ConvGeom conv_geom(const fsb_conv_desc* d);
+
+bool pdl_enabled();
+int sm_count();
+
+// Launch with (optionally) the programmatic-dependent-launch attribute; every kernel of this library calls
+// pdl_launch_dependents() at entry and pdl_wait() before its first dependent global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// launch + remember the error in a thread-local that the following cudaGetLastError()-style check picks up
+extern thread_local cudaError_t g_launch_err;
+#define FSB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (::fsb::g_launch_err = ::fsb::launch_kernel(kernel, grid, block, smem, stream, __VA_ARGS__))
+inline cudaError_t last_launch_error() {
+  cudaError_t e = g_launch_err;
+  g_launch_err = cudaSuccess;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return e;
+}
 
 int conv_tc_supported(const fsb_conv_desc* d);
 int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,

@@ -23,6 +23,8 @@ __host__ __device__ inline float ac_scale(int n_in, int n_out) {
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const __half* __restrict__ x, int xcs,
                      __half* __restrict__ y, int ycs, float sh, float sw, int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvec = C >> 3;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cvec;
   const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -68,10 +70,10 @@ int bilinear_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x,
     return set_error(FSB_ERR_INVALID, "bilinear: C, strides must be multiples of 8 and pointers 16B aligned");
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * (C / 8);
   const int64_t blocks = (total + 255) / 256;
-  bilinear_nhwc_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+  FSB_LAUNCH(bilinear_nhwc_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 
       N, C, Hi, Wi, Ho, Wo, static_cast<const __half*>(x), xcs, static_cast<__half*>(y), ycs, ac_scale(Hi, Ho),
       ac_scale(Wi, Wo), (flags & FSB_CONV_RELU) ? 1 : 0);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bilinear launch");
   return FSB_OK;
 }
@@ -84,6 +86,8 @@ template <typename TOut, int MAXC>
 __global__ void __launch_bounds__(128)
 upsample_logits_nchw_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const __half* __restrict__ x, int xcs,
                             TOut* __restrict__ y, float sh, float sw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int wvec = (Wo + 7) >> 3;
   const int64_t total = static_cast<int64_t>(N) * Ho * wvec;
   const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -148,12 +152,12 @@ int upsample_logits_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const v
   const int64_t total = static_cast<int64_t>(N) * Ho * ((Wo + 7) / 8);
   const int64_t blocks = (total + 127) / 128;
   if (out_dtype == 0)
-    upsample_logits_nchw_kernel<__half, 32><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
+    FSB_LAUNCH(upsample_logits_nchw_kernel<__half, 32>, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream, 
         N, C, Hi, Wi, Ho, Wo, static_cast<const __half*>(x), xcs, static_cast<__half*>(y), ac_scale(Hi, Ho), ac_scale(Wi, Wo));
   else
-    upsample_logits_nchw_kernel<float, 32><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
+    FSB_LAUNCH(upsample_logits_nchw_kernel<float, 32>, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream, 
         N, C, Hi, Wi, Ho, Wo, static_cast<const __half*>(x), xcs, static_cast<float*>(y), ac_scale(Hi, Ho), ac_scale(Wi, Wo));
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "upsample_logits launch");
   return FSB_OK;
 }
@@ -164,6 +168,8 @@ int upsample_logits_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const v
 __global__ void __launch_bounds__(128)
 upsample_argmax_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const __half* __restrict__ x, int xcs,
                        uint8_t* __restrict__ labels, float sh, float sw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int wvec = (Wo + 3) >> 2;
   const int64_t total = static_cast<int64_t>(N) * Ho * wvec;
   const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -218,9 +224,9 @@ int upsample_argmax_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const v
                            cudaStream_t stream) {
   const int64_t total = static_cast<int64_t>(N) * Ho * ((Wo + 3) / 4);
   const int64_t blocks = (total + 127) / 128;
-  upsample_argmax_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(N, C, Hi, Wi, Ho, Wo, static_cast<const __half*>(x),
+  FSB_LAUNCH(upsample_argmax_kernel, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream, N, C, Hi, Wi, Ho, Wo, static_cast<const __half*>(x),
                                                                          xcs, labels, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "upsample_argmax launch");
   return FSB_OK;
 }
@@ -230,6 +236,8 @@ int upsample_argmax_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const v
 // ------------------------------------------------------------------------------------------
 template <typename TIn>
 __global__ void nchw_to_nhwc_kernel(int N, int C, int H, int W, const TIn* __restrict__ x, __half* __restrict__ y, int ycs) {
+  pdl_launch_dependents();
+  pdl_wait();
   // tile transpose through shared memory: 32 pixels x 32 channels
   __shared__ float tile[32][33];
   const int64_t HW = static_cast<int64_t>(H) * W;
@@ -250,6 +258,8 @@ __global__ void nchw_to_nhwc_kernel(int N, int C, int H, int W, const TIn* __res
 }
 template <typename TOut>
 __global__ void nhwc_to_nchw_kernel(int N, int C, int H, int W, const __half* __restrict__ x, int xcs, TOut* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int64_t HW = static_cast<int64_t>(H) * W;
   const int n = blockIdx.z;
@@ -272,10 +282,10 @@ int nchw_to_nhwc_launch(int N, int C, int H, int W, const void* x, int x_is_f32,
   const int64_t HW = static_cast<int64_t>(H) * W;
   dim3 block(32, 8), grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N);
   if (x_is_f32)
-    nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(N, C, H, W, static_cast<const float*>(x), static_cast<__half*>(y), ycs);
+    FSB_LAUNCH(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(block), 0, stream, N, C, H, W, static_cast<const float*>(x), static_cast<__half*>(y), ycs);
   else
-    nchw_to_nhwc_kernel<__half><<<grid, block, 0, stream>>>(N, C, H, W, static_cast<const __half*>(x), static_cast<__half*>(y), ycs);
-  cudaError_t e = cudaGetLastError();
+    FSB_LAUNCH(nchw_to_nhwc_kernel<__half>, dim3(grid), dim3(block), 0, stream, N, C, H, W, static_cast<const __half*>(x), static_cast<__half*>(y), ycs);
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "nchw_to_nhwc launch");
   return FSB_OK;
 }
@@ -283,16 +293,18 @@ int nhwc_to_nchw_launch(int N, int C, int H, int W, const void* x, int xcs, void
   const int64_t HW = static_cast<int64_t>(H) * W;
   dim3 block(32, 8), grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N);
   if (y_is_f32)
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>(N, C, H, W, static_cast<const __half*>(x), xcs, static_cast<float*>(y));
+    FSB_LAUNCH(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(block), 0, stream, N, C, H, W, static_cast<const __half*>(x), xcs, static_cast<float*>(y));
   else
-    nhwc_to_nchw_kernel<__half><<<grid, block, 0, stream>>>(N, C, H, W, static_cast<const __half*>(x), xcs, static_cast<__half*>(y));
-  cudaError_t e = cudaGetLastError();
+    FSB_LAUNCH(nhwc_to_nchw_kernel<__half>, dim3(grid), dim3(block), 0, stream, N, C, H, W, static_cast<const __half*>(x), xcs, static_cast<__half*>(y));
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "nhwc_to_nchw launch");
   return FSB_OK;
 }
 
 __global__ void copy_channels_kernel(int64_t pixels, int cvec, const __half* __restrict__ x, int xcs, __half* __restrict__ y,
                                      int ycs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = pixels * cvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -307,9 +319,9 @@ int copy_channels_launch(int64_t pixels, int C, const void* x, int xcs, void* y,
   const int64_t total = pixels * (C / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  copy_channels_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pixels, C / 8, static_cast<const __half*>(x), xcs,
+  FSB_LAUNCH(copy_channels_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8, static_cast<const __half*>(x), xcs,
                                                                         static_cast<__half*>(y), ycs);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "copy_channels launch");
   return FSB_OK;
 }

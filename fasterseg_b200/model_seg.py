@@ -184,6 +184,10 @@ class Network_Multi_Path_Infer(nn.Module):
         self._stem_head_width = stem_head_width
         self.latency = 0
         self.logits_dtype = torch.float32  # dtype of the upsampled logits returned by forward (fp16 halves the HBM write)
+        # Branches are independent dependency chains of small, latency-bound kernels once their cells stop being shared
+        # (model_seg.py:347-355): run each on its own CUDA stream (captured as parallel arms of the CUDA graph) and join
+        # before the feature-fusion module.
+        self.parallel_branches = True
 
         w0 = stem_head_width[0]
         self.stem = nn.Sequential(
@@ -302,25 +306,40 @@ class Network_Multi_Path_Infer(nn.Module):
         F_.copy_channels(F_.to_nhwc_half(skip), cat[:, c_up:])
         return refine(cat, out=out)
 
-    def agg_ffm(self, outputs8, outputs16, outputs32):
+    # ---- multi-stream plumbing (inference only) ----------------------------------------------------------
+    def _side_streams(self, device):
+        if not self.parallel_branches or self._branch < 2 or self.training or device.type != "cuda":
+            return None
+        streams = self.__dict__.get("_fsb_streams")
+        if streams is None or streams[0].device != device:
+            streams = [torch.cuda.Stream(device) for _ in range(self._branch - 1)]
+            self.__dict__["_fsb_streams"] = streams
+        return streams
+
+    def agg_ffm(self, outputs8, outputs16, outputs32, ctx=None):
         training = self.training
+        ctx = ctx if ctx is not None else _BranchCtx(None)
         pred32, pred16 = [], []
         f8 = self.num_filters(8, self._stem_head_width[1])
         ref = outputs8[0]
-        fused_in = F_.empty_nhwc(ref.shape[0], f8 * self._branch, ref.shape[2], ref.shape[3], ref.device)  # cat(pred8)
+        fused_in = getattr(ctx, "fused_in", None)  # allocated before the fork (see _trunk)
+        if fused_in is None:
+            fused_in = F_.empty_nhwc(ref.shape[0], f8 * self._branch, ref.shape[2], ref.shape[3], ref.device)  # cat(pred8)
         for branch in range(self._branch):
             last = self.lasts[branch]
             slot = fused_in[:, branch * f8:(branch + 1) * f8]
-            if last == 2:
-                if training: pred32.append(outputs32[branch])
-                out = self._arm_refine(self.arms32[0], self.refines32[0], outputs32[branch], outputs16[branch])
-                if training: pred16.append(outputs16[branch])
-                self._arm_refine(self.arms32[1], self.refines32[1], out, outputs8[branch], out=slot)
-            elif last == 1:
-                if training: pred16.append(outputs16[branch])
-                self._arm_refine(self.arms16, self.refines16, outputs16[branch], outputs8[branch], out=slot)
-            elif last == 0:
-                F_.copy_channels(F_.to_nhwc_half(outputs8[branch]), slot)
+            with ctx.on(branch):
+                if last == 2:
+                    if training: pred32.append(outputs32[branch])
+                    out = self._arm_refine(self.arms32[0], self.refines32[0], outputs32[branch], outputs16[branch])
+                    if training: pred16.append(outputs16[branch])
+                    self._arm_refine(self.arms32[1], self.refines32[1], out, outputs8[branch], out=slot)
+                elif last == 1:
+                    if training: pred16.append(outputs16[branch])
+                    self._arm_refine(self.arms16, self.refines16, outputs16[branch], outputs8[branch], out=slot)
+                elif last == 0:
+                    F_.copy_channels(F_.to_nhwc_half(outputs8[branch]), slot)
+        ctx.join()
         pred8 = self.heads8(self.ffm(fused_in))
         if not training:
             return pred8
@@ -328,17 +347,26 @@ class Network_Multi_Path_Infer(nn.Module):
         pred16 = self.heads16(_cat_channels(pred16)) if len(pred16) > 0 else None
         return pred8, pred16, pred32
 
-    def _trunk(self, input):
+    def _trunk(self, input, ctx=None):
         H = input.size(2)
+        ctx = ctx if ctx is not None else _BranchCtx(None)
         stem = self.stem(input)
+        # The concat buffer that the side streams will write into is allocated on the main stream BEFORE the fork, so the
+        # block the caching allocator hands out cannot still be in use by main-stream work the side streams do not wait for.
+        f8 = self.num_filters(8, self._stem_head_width[1])
+        ctx.fused_in = F_.empty_nhwc(stem.shape[0], f8 * self._branch, stem.shape[2], stem.shape[3], stem.device)
         # last feature map of each branch at each scale
         outputs8 = [stem] * self._branch
         outputs16 = [stem] * self._branch
         outputs32 = [stem] * self._branch
         outputs = [stem] * self._branch
         for layer in range(len(self.branch_groups)):
-            for group in self.branch_groups[layer]:
-                output = self.cells[str(layer) + "-" + str(group[0])](outputs[group[0]])
+            groups = self.branch_groups[layer]
+            if len(groups) > 1:
+                ctx.fork()
+            for group in groups:
+                with ctx.on(group[0]):
+                    output = self.cells[str(layer) + "-" + str(group[0])](outputs[group[0]])
                 scale = int(H // output.size(2))
                 for branch in group:
                     outputs[branch] = output
@@ -348,16 +376,17 @@ class Network_Multi_Path_Infer(nn.Module):
         return outputs8, outputs16, outputs32
 
     def forward(self, input):
-        outputs8, outputs16, outputs32 = self._trunk(input)
+        ctx = _BranchCtx(self._side_streams(input.device))
+        outputs8, outputs16, outputs32 = self._trunk(input, ctx)
         if self.training:
-            pred8, pred16, pred32 = self.agg_ffm(outputs8, outputs16, outputs32)
+            pred8, pred16, pred32 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
             pred8 = F_.upsample_logits(pred8, (pred8.size(2) * 8, pred8.size(3) * 8), dtype=self.logits_dtype)
             if pred16 is not None:
                 pred16 = F_.upsample_logits(pred16, (pred16.size(2) * 16, pred16.size(3) * 16), dtype=self.logits_dtype)
             if pred32 is not None:
                 pred32 = F_.upsample_logits(pred32, (pred32.size(2) * 32, pred32.size(3) * 32), dtype=self.logits_dtype)
             return pred8, pred16, pred32
-        pred8 = self.agg_ffm(outputs8, outputs16, outputs32)
+        pred8 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
         return F_.upsample_logits(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), dtype=self.logits_dtype)
 
     @torch.no_grad()
@@ -365,7 +394,9 @@ class Network_Multi_Path_Infer(nn.Module):
         """argmax(forward(input), dim=1) as uint8, fused into the x8 upsample: the evaluator's
         `exp -> cpu -> argmax` (tools/engine/evaluator.py:315-318) without materialising full-resolution logits."""
         assert not self.training
-        pred8 = self.agg_ffm(*self._trunk(input))
+        ctx = _BranchCtx(self._side_streams(input.device))
+        outputs8, outputs16, outputs32 = self._trunk(input, ctx)
+        pred8 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
         return F_.upsample_argmax(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), out=out)
 
     def forward_latency(self, size):
@@ -406,6 +437,44 @@ class Network_Multi_Path_Infer(nn.Module):
         latency, size = self.ffm.forward_latency((out_size[0] * self._branch, out_size[1], out_size[2])); latency_total += latency
         latency, size = self.heads8.forward_latency(size); latency_total += latency
         return latency_total, size
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class _BranchCtx:
+    """Routes the work of branch b to its own stream after `fork()`; `join()` makes the main stream wait for all.
+    Cross-stream tensors stay alive in the caller's `outputs*` lists until the forward returns, and every forward starts
+    with a fork-wait / ends with a join, so the caching allocator never hands a block to another stream while it is in use."""
+
+    def __init__(self, streams):
+        self.streams, self.forked = streams, False
+        self.main = torch.cuda.current_stream() if streams else None
+        self.fused_in = None
+
+    def fork(self):
+        if self.streams and not self.forked:
+            for s in self.streams:
+                s.wait_stream(self.main)
+            self.forked = True
+
+    def on(self, branch):
+        if not self.streams:
+            return _NullCtx()
+        if not self.forked or branch == 0:
+            return torch.cuda.stream(self.main)
+        return torch.cuda.stream(self.streams[branch - 1])
+
+    def join(self):
+        if self.forked:
+            for s in self.streams:
+                self.main.wait_stream(s)
+            self.forked = False
 
 
 def _cat_channels(tensors):

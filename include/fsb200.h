@@ -67,6 +67,10 @@ const char* fsb_last_error_string(void);
 /* number of SMs / compute capability of the current device (host ints, may be NULL) */
 int fsb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Programmatic dependent launch between consecutive kernels of this library (default on; env FSB_PDL=0 disables).
+ * With it a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps its predecessor's tail. */
+int fsb_set_pdl(int enabled);
+
 /* --- weights -------------------------------------------------------------------------------- */
 /* bytes of the packed fp16 weight buffer for `d` */
 size_t fsb_conv_packed_bytes(const fsb_conv_desc* d);
