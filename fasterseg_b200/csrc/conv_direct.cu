@@ -210,10 +210,153 @@ stem_conv_nchw_kernel(int N, int H, int W, int Cout, const TIn* __restrict__ x, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// RGB stem on the tensor cores: a CTA (128 threads) owns 128 consecutive output pixels of one output row.  Thread t
+// gathers the 27 inputs of its pixel straight from the NCHW tensor (warp-coalesced per (channel,row)), converts to
+// fp16 and writes row t of a 128 x 32 K-major A tile in the SWIZZLE_64B canonical layout (K = 27 padded to 32); the
+// OIHW weights are laid out the same way as the B tile.  Two tcgen05.mma (K = 16 each) produce the 128 x Cout fp32
+// tile in TMEM; the epilogue applies BN scale/shift + ReLU and each thread stores its pixel's Cout fp16 values
+// contiguously (a warp writes 32 x 2*Cout contiguous bytes).  No im2col buffer, no fp16 NHWC copy of the image.
+// ------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(128)
+stem_conv_tc_kernel(int N, int H, int W, int Cout, int npad, const TIn* __restrict__ x, const float* __restrict__ w,
+                    const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ y,
+                    int y_cstride, uint32_t flags, uint32_t tmem_cols) {
+  __shared__ __align__(1024) uint8_t s_a[128 * 64];
+  __shared__ __align__(1024) uint8_t s_b[64 * 64];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_scale[64];
+  __shared__ float s_shift[64];
+  pdl_launch_dependents();
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const int Ho = H / 2 + (H & 1), Wo = W / 2 + (W & 1);
+  const int wo = blockIdx.x * 128 + t;
+  const int ho = blockIdx.y;
+  const int n = blockIdx.z;
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, tmem_cols);
+    tmem_relinquish();
+  }
+  pdl_wait();  // weights / scale / shift may have been produced by the immediately preceding kernel
+  // weights -> B tile rows (one thread per output channel), fp32 OIHW is already [co][27]
+  if (t < npad) {
+    __half hv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) hv[k] = __float2half_rn((t < Cout && k < 27) ? w[t * 27 + k] : 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(s_b + t * 64 + ((j ^ ((t >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(&hv[j * 8]);
+    const bool aff = (flags & FSB_CONV_AFFINE) && t < Cout;
+    s_scale[t] = (aff && scale) ? scale[t] : 1.f;
+    s_shift[t] = (aff && shift) ? shift[t] : 0.f;
+  }
+  // im2col row of this thread's pixel
+  {
+    __half hv[32];
+    const size_t plane = static_cast<size_t>(H) * W;
+    const bool pix = wo < Wo;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hi = ho * 2 + r - 1;
+        const bool hok = pix && hi >= 0 && hi < H;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int wi = wo * 2 + s - 1;
+          float v = 0.f;
+          if (hok && wi >= 0 && wi < W) v = static_cast<float>(x[(static_cast<size_t>(n) * 3 + ci) * plane + static_cast<size_t>(hi) * W + wi]);
+          hv[ci * 9 + r * 3 + s] = __float2half_rn(v);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) hv[k] = __float2half_rn(0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(s_a + t * 64 + ((j ^ ((t >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(&hv[j * 8]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (t == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(npad));
+    const uint64_t da = umma_desc_kmajor(smem_u32(s_a), 64);
+    const uint64_t db = umma_desc_kmajor(smem_u32(s_b), 64);
+    umma_f16_ss(tmem, da, db, idesc, 0u);
+    umma_f16_ss(tmem, da + 2, db + 2, idesc, 1u);
+    umma_commit(&s_bar);
+  }
+  mbar_wait(&s_bar, 0);
+  tc_fence_after();
+  const bool relu = flags & FSB_CONV_RELU;
+  __half* yp = y + (static_cast<size_t>(n) * Ho * Wo + static_cast<size_t>(ho) * Wo + wo) * y_cstride;
+  const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < npad; c += 16) {
+    uint32_t v[16];
+    tmem_ld16(taddr + c, v);
+    tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = __uint_as_float(v[j]) * s_scale[c + j] + s_shift[c + j];
+      f[j] = relu ? fmaxf(a, 0.f) : a;
+    }
+    if (wo < Wo) {
+      const int remaining = Cout - c;
+      if (remaining >= 16 && (reinterpret_cast<uintptr_t>(yp + c) & 15) == 0) {
+        uint4 o0, o1;
+        o0.x = pack_half2(f[0], f[1]);
+        o0.y = pack_half2(f[2], f[3]);
+        o0.z = pack_half2(f[4], f[5]);
+        o0.w = pack_half2(f[6], f[7]);
+        o1.x = pack_half2(f[8], f[9]);
+        o1.y = pack_half2(f[10], f[11]);
+        o1.z = pack_half2(f[12], f[13]);
+        o1.w = pack_half2(f[14], f[15]);
+        reinterpret_cast<uint4*>(yp + c)[0] = o0;
+        reinterpret_cast<uint4*>(yp + c)[1] = o1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < remaining) yp[c + j] = __float2half_rn(f[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, tmem_cols);
+  }
+}
+
 int stem_conv_nchw_launch(int N, int H, int W, int Cout, const void* x, int x_is_f32, const float* w, const float* scale,
                           const float* shift, void* y, int y_cstride, uint32_t flags, cudaStream_t stream) {
   const int Ho = H / 2 + (H & 1), Wo = W / 2 + (W & 1);
   const int cpad = (Cout + 15) / 16 * 16;
+  if (cpad <= 64 && !(flags & FSB_CONV_FORCE_DIRECT)) {
+    dim3 grid_tc((Wo + 127) / 128, Ho, N);
+    const uint32_t cols = cpad <= 32 ? 32u : 64u;
+    if (x_is_f32)
+      FSB_LAUNCH(stem_conv_tc_kernel<float>, grid_tc, dim3(128), 0, stream, N, H, W, Cout, cpad, static_cast<const float*>(x), w,
+                 scale, shift, static_cast<__half*>(y), y_cstride, flags, cols);
+    else
+      FSB_LAUNCH(stem_conv_tc_kernel<__half>, grid_tc, dim3(128), 0, stream, N, H, W, Cout, cpad, static_cast<const __half*>(x), w,
+                 scale, shift, static_cast<__half*>(y), y_cstride, flags, cols);
+    cudaError_t e2 = last_launch_error();
+    if (e2 != cudaSuccess) return set_cuda_error(e2, "stem_conv_tc launch");
+    return FSB_OK;
+  }
   const int groups = cpad / 16;
   const size_t smem = static_cast<size_t>(27 + 2) * cpad * sizeof(float);
   dim3 block(Wo >= 256 ? 256 : 128);

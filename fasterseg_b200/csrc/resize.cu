@@ -147,8 +147,139 @@ upsample_logits_nchw_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// tiled variant (the x8 / x16 / x32 logits upsample of model_seg.py:359-365): a block owns kRows output rows x kCols
+// output columns.  The (few) source rows/columns it touches are staged in shared memory as fp32 [row][class][col];
+// per output row the vertical lerp is done once into a [class][col] line, and each thread then produces 8 consecutive
+// output columns of one class from <= 3 line entries -> one 16-byte store; a warp writes 512 contiguous bytes.
+// HBM traffic = output bytes (+ the tiny source), i.e. the kernel is a pure streaming write.
+// ------------------------------------------------------------------------------------------
+constexpr int kUpRows = 4;
+constexpr int kUpCols = 512;
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+upsample_logits_tiled_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const __half* __restrict__ x, int xcs,
+                             TOut* __restrict__ y, float sh, float sw, int max_rows, int max_cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_up[];  // [max_rows][C][max_cols] window, then [C][max_cols] line
+  const int n = blockIdx.z;
+  const int ho0 = blockIdx.y * kUpRows;
+  const int wo0 = blockIdx.x * kUpCols;
+  const int ho_last = min(ho0 + kUpRows, Ho) - 1;
+  const int wo_last = min(wo0 + kUpCols, Wo) - 1;
+  int hs0, hs1, ws0, ws1, tmp;
+  float ftmp;
+  src_index(ho0, sh, Hi, hs0, tmp, ftmp);
+  src_index(ho_last, sh, Hi, tmp, hs1, ftmp);
+  src_index(wo0, sw, Wi, ws0, tmp, ftmp);
+  src_index(wo_last, sw, Wi, tmp, ws1, ftmp);
+  const int nrows = hs1 - hs0 + 1;  // <= max_rows by construction on the host
+  const int ncols = ws1 - ws0 + 1;  // <= max_cols
+  float* win = s_up;
+  float* line = s_up + static_cast<size_t>(max_rows) * C * max_cols;
+  // ---- stage the source window (NHWC fp16 -> [row][class][col] fp32) ----
+  const int cvec = (C + 7) >> 3;
+  const int items = nrows * ncols * cvec;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int cv = i % cvec;
+    const int col = (i / cvec) % ncols;
+    const int row = i / (cvec * ncols);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * Hi + hs0 + row) * Wi + ws0 + col) * xcs + cv * 8);
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cv * 8 + j;
+      if (c < C) win[(static_cast<size_t>(row) * C + c) * max_cols + col] = __half2float(hv[j]);
+    }
+  }
+  __syncthreads();
+  const size_t plane = static_cast<size_t>(Ho) * Wo;
+  // thread -> (column vector v, class group cg): the 8 horizontal taps of a thread are the same for every class and
+  // every output row, so they are computed once and kept in registers
+  constexpr int kVecs = kUpCols / 8;            // 64
+  const int v = threadIdx.x % kVecs;
+  const int cg = threadIdx.x / kVecs;           // 0..3
+  const int cgs = blockDim.x / kVecs;
+  const int wo = wo0 + v * 8;
+  int wofs[8];
+  float lwj[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int w0, w1;
+    src_index(min(wo + j, Wo - 1), sw, Wi, w0, w1, lwj[j]);
+    wofs[j] = (w0 - ws0) | ((w1 - w0) << 16);
+  }
+  const bool active = wo <= wo_last;
+  for (int r = 0; r <= ho_last - ho0; ++r) {
+    const int ho = ho0 + r;
+    int h0, h1;
+    float lh;
+    src_index(ho, sh, Hi, h0, h1, lh);
+    const float* r0 = win + static_cast<size_t>(h0 - hs0) * C * max_cols;
+    const float* r1 = win + static_cast<size_t>(h1 - hs0) * C * max_cols;
+    for (int i = threadIdx.x; i < C * ncols; i += blockDim.x) {
+      const int c = i / ncols, col = i % ncols;
+      line[c * max_cols + col] = (1.f - lh) * r0[c * max_cols + col] + lh * r1[c * max_cols + col];
+    }
+    __syncthreads();
+    if (active) {
+      for (int c = cg; c < C; c += cgs) {
+        const float* ln = line + c * max_cols;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int a = wofs[j] & 0xffff;
+          const float x0 = ln[a], x1 = ln[a + (wofs[j] >> 16)];
+          o[j] = x0 + lwj[j] * (x1 - x0);
+        }
+        TOut* dst = y + (static_cast<size_t>(n) * C + c) * plane + static_cast<size_t>(ho) * Wo + wo;
+        if (wo + 8 <= Wo && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          if (sizeof(TOut) == 2) {
+            uint4 pk;
+            pk.x = pack_half2(o[0], o[1]);
+            pk.y = pack_half2(o[2], o[3]);
+            pk.z = pack_half2(o[4], o[5]);
+            pk.w = pack_half2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(dst) = pk;
+          } else {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            d4[0] = make_float4(o[0], o[1], o[2], o[3]);
+            d4[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (wo + j < Wo) dst[j] = static_cast<TOut>(o[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int upsample_logits_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x, int xcs, void* y, int out_dtype,
                            cudaStream_t stream) {
+  // tiled path: upsampling only, source window must fit in shared memory, 16-byte addressable source pixels
+  const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  if (sh <= 1.f && sw <= 1.f && xcs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && xcs >= (C + 7) / 8 * 8) {
+    const int max_rows = static_cast<int>(sh * (kUpRows - 1)) + 3;
+    const int max_cols = static_cast<int>(sw * (kUpCols - 1)) + 3;
+    const size_t smem = (static_cast<size_t>(max_rows) * C * max_cols + static_cast<size_t>(C) * max_cols) * sizeof(float);
+    if (smem <= 48 * 1024) {
+      dim3 grid((Wo + kUpCols - 1) / kUpCols, (Ho + kUpRows - 1) / kUpRows, N);
+      if (out_dtype == 0)
+        FSB_LAUNCH(upsample_logits_tiled_kernel<__half>, grid, dim3(256), smem, stream, N, C, Hi, Wi, Ho, Wo,
+                   static_cast<const __half*>(x), xcs, static_cast<__half*>(y), sh, sw, max_rows, max_cols);
+      else
+        FSB_LAUNCH(upsample_logits_tiled_kernel<float>, grid, dim3(256), smem, stream, N, C, Hi, Wi, Ho, Wo,
+                   static_cast<const __half*>(x), xcs, static_cast<float*>(y), sh, sw, max_rows, max_cols);
+      cudaError_t e2 = last_launch_error();
+      if (e2 != cudaSuccess) return set_cuda_error(e2, "upsample_logits_tiled launch");
+      return FSB_OK;
+    }
+  }
   const int64_t total = static_cast<int64_t>(N) * Ho * ((Wo + 7) / 8);
   const int64_t blocks = (total + 127) / 128;
   if (out_dtype == 0)

@@ -141,10 +141,13 @@ def test_stem_conv_nchw(co, dtype):
     w = _rand((co, 3, 3, 3), 32) * 0.27
     scale = torch.from_numpy(np.random.RandomState(33).uniform(0.5, 1.5, co).astype(np.float32))
     shift = _rand((co,), 34, 0.2)
-    ref = torch.relu(orc.conv2d(x, w, None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    # declared semantics: image and weights are rounded to fp16 once, products accumulate in fp32 (tensor cores)
+    ref = torch.relu(orc.conv2d(x.half().float(), w.half().float(), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     y = F_.stem_conv_nchw(x.cuda().to(dtype), w.cuda(), scale.cuda(), shift.cuda())
     torch.cuda.synchronize()
     _close(y.float().cpu(), ref)
+    ref32 = torch.relu(orc.conv2d(x, w, None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert H.rel_err(y.float().cpu().numpy(), ref32.numpy()) < 1e-3  # vs un-rounded fp32 operands: norm-wise
 
 
 def test_convnorm_gate_config0():
@@ -160,9 +163,12 @@ def test_convnorm_gate_config0():
                             sd["conv.1.running_var"].cuda(), orc.BN_EPS)
         y = F_.stem_conv_nchw(x.cuda(), sd["conv.0.weight"].cuda(), sc, sh).float().cpu()
         ref_s = torch.from_numpy(z["co%d.eval/sample" % co])
-        _close(y[:, :, ::8, ::8], ref_s)
+        # vs the REFERENCE (fp32 operands): norm-wise 1e-3 (north_star) + elementwise 2e-3 * (|ref| + rms)
+        assert H.rel_err(y[:, :, ::8, ::8].numpy(), ref_s.numpy()) < 1e-3
+        _close(y[:, :, ::8, ::8], ref_s, rel=4e-3)  # tails of 27-term sums of fp16-rounded operands
         full = orc.conv_norm(x, orc.Params(sd), 3, 2, 1, False)
-        _close(y, full)
+        assert H.rel_err(y.numpy(), full.numpy()) < 1e-3
+        _close(y, full, rel=4e-3)
 
 
 def test_bilinear_golden_and_random():
