@@ -12,6 +12,8 @@ FSB_CONV_RELU = 1
 FSB_CONV_AFFINE = 2
 FSB_CONV_FORCE_DIRECT = 4
 FSB_CONV_STATS = 8
+FSB_CONV_OUT_F32 = 16
+FSB_ACT_IN_F32 = 32
 
 
 class FsbError(RuntimeError):
@@ -43,6 +45,20 @@ _SIGS = {
     "fsb_bn_stats": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, _P]),
     "fsb_bn_finalize": (C.c_int, [C.c_int, _P, C.c_double, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "fsb_affine_act": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_uint32, _P]),
+    "fsb_bn_bwd_reduce": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "fsb_bn_bwd_apply": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_double,
+                                   C.c_int, _P, C.c_int, _P, _P, C.c_float, _P]),
+    "fsb_relu_bwd": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "fsb_conv_packed_dgrad_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "fsb_pack_conv_weight_dgrad": (C.c_int, [C.POINTER(ConvDesc), _P, C.c_int64, C.c_int64, _P, _P]),
+    "fsb_conv_dgrad": (C.c_int, [C.POINTER(ConvDesc), _P, C.c_int, _P, _P, C.c_int64, C.c_int64, _P, C.c_int, _P]),
+    "fsb_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _P, _P, C.c_int, _P, C.c_int64, C.c_int64, C.c_int, C.c_float, _P]),
+    "fsb_bilinear_bwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "fsb_upsample_logits_bwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, C.c_float, _P]),
+    "fsb_nchw_grad_to_nhwc": (C.c_int, [C.c_int] * 4 + [_P, C.c_int, _P, C.c_int, C.c_float, _P]),
+    "fsb_wsum_fwd": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
+    "fsb_wsum_bwd": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_float, _P]),
+    "fsb_add_inplace": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -1,0 +1,292 @@
+"""torch.autograd.Function wrappers: the training-mode forward/backward of the hot path on the sm_100a kernels.
+
+The reference gets its backward from autograd over F.conv2d / BatchNorm2d / ReLU / F.interpolate / torch.cat and the
+`result + op(x) * w` python arithmetic (search/operations.py, search/model_search.py:60-78,318-333).  Here each fused unit
+is one autograd node whose backward calls the kernels in csrc/train.cu, so `loss.backward()`, `torch.autograd.grad`,
+`clip_grad_norm_` and the stock optimizers work unchanged on the fp32 master parameters.
+
+Gradient precision: activation gradients are fp16 NHWC; to keep small mean-reduced-loss gradients out of the fp16
+subnormal range they carry a static loss scale GRAD_SCALE, applied where fp32 NCHW logits gradients enter
+(`UpsampleLogitsFn`, `ToNCHWFn`) and divided out of every fp32 parameter / scalar gradient by the kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine
+from . import functional as F_
+
+GRAD_SCALE = 1024.0
+
+
+def set_grad_scale(v: float):
+    global GRAD_SCALE
+    GRAD_SCALE = float(v)
+
+
+def _dy(t):
+    """Incoming gradient as an NHWC fp16 view (autograd may hand us a differently-strided tensor after accumulation)."""
+    if F_.is_nhwc_half(t):
+        return t
+    return t.contiguous(memory_format=torch.channels_last) if t.dtype == torch.float16 else F_.to_nhwc_half(t)
+
+
+def _dgrad_pack(conv, ci, co):
+    cache = conv.__dict__.setdefault("_fsb_wtcache", {})
+    ver = engine._versions(conv.weight)
+    hit = cache.get((ci, co))
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    packed = F_.pack_conv_weight_dgrad(conv.weight.detach(), ci, co, conv.kernel_size[0])
+    cache[(ci, co)] = (ver, packed)
+    return packed
+
+
+def _conv_backward(ctx_conv, x, draw, ci, co, off, need_dx, need_dw):
+    k, s, p = ctx_conv.kernel_size[0], ctx_conv.stride[0], ctx_conv.padding[0]
+    w = ctx_conv.weight.detach()
+    dx = dw = None
+    if need_dx:
+        wt = _dgrad_pack(ctx_conv, ci, co) if (s == 1 and off == (0, 0)) else None
+        dx = F_.conv_dgrad(draw, w, tuple(x.shape), ci, co, k, s, p, off=off, wpacked_t=wt)
+    if need_dw:
+        dw = F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off)
+    return dx, dw
+
+
+class ConvBnActFn(torch.autograd.Function):
+    """act(BN_train(conv(x))): conv with fused per-channel statistics -> finalize (running-stat update) -> apply."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, conv, bn, relu, ci, co, off):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        wp = engine.packed_weight(conv, ci, co)
+        stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
+        raw = F_.conv_fwd(x, wp, co, k, s, p, relu=False, off=off, stats=stats, out_f32=True)
+        N, _, Ho, Wo = raw.shape
+        stats = engine.dp_allreduce_stats(stats)
+        count = N * Ho * Wo * engine.dp_world_size()
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        scale, shift, mean, invstd = F_.bn_finalize(stats, count, gamma, beta, bn.eps, momentum,
+                                                    bn.running_mean if bn.track_running_stats else None,
+                                                    bn.running_var if bn.track_running_stats else None, want_save=True)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        y = F_.affine_act(raw, scale, shift, relu=relu)
+        ctx.conv, ctx.relu, ctx.ci, ctx.co, ctx.off, ctx.count = conv, relu, ci, co, off, count
+        ctx.save_for_backward(x, raw, y, mean, invstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, y, mean, invstd, gamma = ctx.saved_tensors
+        dy = _dy(dy)
+        need = ctx.needs_input_grad
+        sync = engine.dp_allreduce_stats if engine.dp_world_size() > 1 else None
+        draw, dgamma, dbeta = F_.bn_bwd(dy, y, raw, mean, invstd, gamma, ctx.count, ctx.relu, GRAD_SCALE,
+                                        want_param_grads=bool(need[2] or need[3]), allreduce=sync)
+        dx, dw = _conv_backward(ctx.conv, x, draw, ctx.ci, ctx.co, ctx.off, need[0], need[1])
+        return dx, dw, dgamma if need[2] else None, dbeta if need[3] else None, None, None, None, None, None, None
+
+
+class ConvBiasFn(torch.autograd.Function):
+    """conv(x) + bias, optional ReLU, no BN (Head.conv_1x1, seg_oprs.py:246,273)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, conv, relu, ci, co):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        wp = engine.packed_weight(conv, ci, co)
+        shift = None if bias is None else bias.detach()[:co].float().contiguous()
+        y = F_.conv_fwd(x, wp, co, k, s, p, None, shift, relu=relu)
+        ctx.conv, ctx.relu, ctx.ci, ctx.co = conv, relu, ci, co
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dy = _dy(dy)
+        if ctx.relu:
+            dy = F_.relu_bwd(dy, y)
+        need = ctx.needs_input_grad
+        dx, dw = _conv_backward(ctx.conv, x, dy, ctx.ci, ctx.co, (0, 0), need[0], need[1])
+        db = None
+        if need[2]:
+            # bias gradient = per-channel sum of dy: reuse the statistics kernel (first half of its output)
+            full = torch.zeros(ctx.conv.bias.shape, device=dy.device, dtype=torch.float32)
+            full[:ctx.co] = F_.bn_stats(dy)[:ctx.co] / GRAD_SCALE
+            db = full
+        return dx, dw, db, None, None, None, None
+
+
+class FactorizedReduceFn(torch.autograd.Function):
+    """cat[conv1(x), conv2(x[:, :, 1:, 1:])] -> BN(train) -> ReLU (operations.py:521-526) as one node."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, gamma, beta, op, bn, ci, co_half):
+        co = 2 * co_half
+        N, _, H, W = x.shape
+        p1 = engine.packed_weight(op.conv1, ci, co_half)
+        p2 = engine.packed_weight(op.conv2, ci, co_half)
+        raw = F_.empty_nhwc(N, co, H // 2, W // 2, x.device, dtype=torch.float32)
+        s1 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
+        s2 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
+        F_.conv_fwd(x, p1, co_half, 1, 2, 0, out=raw[:, :co_half], stats=s1, out_f32=True)
+        F_.conv_fwd(x, p2, co_half, 1, 2, 0, out=raw[:, co_half:], off=(1, 1), stats=s2, out_f32=True)
+        stats = torch.cat([s1[:co_half], s2[:co_half], s1[co_half:], s2[co_half:]])
+        stats = engine.dp_allreduce_stats(stats)
+        count = N * (H // 2) * (W // 2) * engine.dp_world_size()
+        scale, shift, mean, invstd = F_.bn_finalize(stats, count, gamma, beta, bn.eps, 0.1 if bn.momentum is None else bn.momentum,
+                                                    bn.running_mean, bn.running_var, want_save=True)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        y = F_.affine_act(raw, scale, shift, relu=True)
+        ctx.op, ctx.ci, ctx.co_half, ctx.count = op, ci, co_half, count
+        ctx.save_for_backward(x, raw, y, mean, invstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, y, mean, invstd, gamma = ctx.saved_tensors
+        dy = _dy(dy)
+        need = ctx.needs_input_grad
+        sync = engine.dp_allreduce_stats if engine.dp_world_size() > 1 else None
+        draw, dgamma, dbeta = F_.bn_bwd(dy, y, raw, mean, invstd, gamma, ctx.count, True, GRAD_SCALE,
+                                        want_param_grads=bool(need[3] or need[4]), allreduce=sync)
+        ch = ctx.co_half
+        dx1, dw1 = _conv_backward(ctx.op.conv1, x, draw[:, :ch], ctx.ci, ch, (0, 0), need[0], need[1])
+        dx2, dw2 = _conv_backward(ctx.op.conv2, x, draw[:, ch:], ctx.ci, ch, (1, 1), need[0], need[2])
+        dx = None
+        if need[0]:
+            dx = F_.add_inplace(dx2, dx1)
+        return dx, dw1, dw2, dgamma if need[3] else None, dbeta if need[4] else None, None, None, None, None
+
+
+class BilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, relu):
+        y = F_.bilinear(x, size, relu=relu)
+        ctx.in_hw, ctx.relu = (x.shape[2], x.shape[3]), relu
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mask = ctx.saved_tensors[0] if ctx.relu else None
+        return F_.bilinear_bwd(_dy(dy), ctx.in_hw, relu_mask_y=mask), None, None
+
+
+class UpsampleLogitsFn(torch.autograd.Function):
+    """NHWC fp16 logits -> upsampled NCHW logits (model_seg.py:359-361); backward re-enters the fp16 domain (x GRAD_SCALE)."""
+
+    @staticmethod
+    def forward(ctx, x, size, dtype):
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        return F_.upsample_logits(x, size, dtype=dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return F_.upsample_logits_bwd(dy, ctx.in_hw, GRAD_SCALE), None, None
+
+
+class ToNCHWFn(torch.autograd.Function):
+    """NHWC fp16 -> NCHW fp32 (logits handed to the caller's criterion at 1/8 resolution, model_search.py:346-358)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return F_.to_nchw(x, dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return F_.nchw_grad_to_nhwc(dy, GRAD_SCALE), None
+
+
+class WsumFn(torch.autograd.Function):
+    """out = sum_k wts[k] * xs[k] (MixedOp / beta aggregation, model_search.py:75-78,330-333) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, wts, *xs):
+        wts32 = wts.detach().float().contiguous()
+        out = F_.wsum_fwd(list(xs), wts32)
+        ctx.save_for_backward(wts32, *xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        wts32, *xs = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dxs, dw = F_.wsum_bwd(_dy(dout), list(xs), wts32, [bool(n) for n in need[1:]], bool(need[0]), GRAD_SCALE)
+        return (dw, *dxs)
+
+
+class CatFn(torch.autograd.Function):
+    """torch.cat(dim=1) (operations.py:523, model_search.py:340-350, model_seg.py:307-331): strided copies forward,
+    channel-slice views backward."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        N, _, H, W = xs[0].shape
+        ctx.sizes = [t.shape[1] for t in xs]
+        out = F_.empty_nhwc(N, sum(ctx.sizes), H, W, xs[0].device)
+        at = 0
+        for t in xs:
+            F_.copy_channels(t, out[:, at:at + t.shape[1]])
+            at += t.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _dy(dy)
+        outs, at = [], 0
+        for c in ctx.sizes:
+            outs.append(dy[:, at:at + c])
+            at += c
+        return tuple(outs)
+
+
+# ----------------------------------------------------------------------------------------------
+# entry points used by engine / operations / models
+# ----------------------------------------------------------------------------------------------
+def conv_bn_act_train(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
+    assert conv.bias is None, "conv bias followed by train-mode BN is not on the hot path"
+    y = ConvBnActFn.apply(x, conv.weight, bn.weight, bn.bias, conv, bn, relu, ci, co, off)
+    if out is not None:  # autograd-visible copy into a caller-provided slot (training path does not use zero-copy concat)
+        raise RuntimeError("out= is an inference-only fast path")
+    return y
+
+
+def conv_bias_act(x, conv, relu, ci, co):
+    return ConvBiasFn.apply(x, conv.weight, conv.bias, conv, relu, ci, co)
+
+
+def factorized_reduce_train(op, x, bn, ci, co_half, out=None):
+    if out is not None:
+        raise RuntimeError("out= is an inference-only fast path")
+    return FactorizedReduceFn.apply(x, op.conv1.weight, op.conv2.weight, bn.weight, bn.bias, op, bn, ci, co_half)
+
+
+def bilinear(x, size, relu=False):
+    return BilinearFn.apply(x, (int(size[0]), int(size[1])), relu)
+
+
+def upsample_logits(x, size, dtype=torch.float32):
+    return UpsampleLogitsFn.apply(x, (int(size[0]), int(size[1])), dtype)
+
+
+def to_nchw(x, dtype=torch.float32):
+    return ToNCHWFn.apply(x, dtype)
+
+
+def weighted_sum(wts, xs):
+    return WsumFn.apply(wts, *xs)
+
+
+def cat_channels(xs):
+    xs = [F_.to_nhwc_half(t) for t in xs]
+    return xs[0] if len(xs) == 1 else CatFn.apply(*xs)
+
+
+def grad_mode(*tensors):
+    """True when an autograd graph must be recorded for these inputs."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)

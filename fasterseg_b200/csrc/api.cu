@@ -61,10 +61,27 @@ int nchw_to_nhwc_launch(int, int, int, int, const void*, int, void*, int, cudaSt
 int nhwc_to_nchw_launch(int, int, int, int, const void*, int, void*, int, cudaStream_t);
 int copy_channels_launch(int64_t, int, const void*, int, void*, int, cudaStream_t);
 int bn_fold_launch(int, const float*, const float*, const float*, const float*, float, const float*, float*, float*, cudaStream_t);
-int bn_stats_launch(int64_t, int, const void*, int, float*, cudaStream_t);
+int bn_stats_launch(int64_t, int, const void*, int, int, float*, cudaStream_t);
 int bn_finalize_launch(int, const float*, double, const float*, const float*, float, float, float*, float*, float*, float*,
                        float*, float*, cudaStream_t);
 int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t);
+
+int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*, int,
+                         float*, cudaStream_t);
+int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
+                        const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t);
+int relu_bwd_launch(int64_t, int, const void*, int, const void*, int, void*, int, cudaStream_t);
+fsb_conv_desc dgrad_as_fwd_desc(const fsb_conv_desc*, int, int);
+int pack_dgrad_launch(const fsb_conv_desc*, const float*, int64_t, int64_t, void*, cudaStream_t);
+int conv_dgrad_launch(const fsb_conv_desc*, const void*, int, const void*, const float*, int64_t, int64_t, void*, int, cudaStream_t);
+int conv_wgrad_launch(const fsb_conv_desc*, const void*, const void*, int, float*, int64_t, int64_t, int, float, cudaStream_t);
+int bilinear_bwd_launch(int, int, int, int, int, int, const void*, int, const void*, int, void*, int, cudaStream_t);
+int upsample_logits_bwd_launch(int, int, int, int, int, int, const void*, int, void*, int, float, cudaStream_t);
+int nchw_grad_to_nhwc_launch(int, int, int, int, const void*, int, void*, int, float, cudaStream_t);
+int wsum_fwd_launch(int, int64_t, int, const void* const*, const int*, const float*, void*, int, cudaStream_t);
+int wsum_bwd_launch(int, int64_t, int, const void*, int, const void* const*, const int*, const float*, void* const*, const int*,
+                    float*, float, cudaStream_t);
+int add_inplace_launch(int64_t, int, const void*, int, void*, int, cudaStream_t);
 
 static int check_desc(const fsb_conv_desc* d) {
   if (!d) return set_error(FSB_ERR_INVALID, "null conv desc");
@@ -178,7 +195,7 @@ int fsb_copy_channels(int64_t pixels, int C, const void* x, int xcs, void* y, in
 
 int fsb_bn_stats(int64_t pixels, int C, const void* x, int xcs, float* stats, void* stream) {
   if (pixels <= 0 || C <= 0 || !x || !stats) return set_error(FSB_ERR_INVALID, "bn_stats: bad argument");
-  return bn_stats_launch(pixels, C, x, xcs, stats, static_cast<cudaStream_t>(stream));
+  return bn_stats_launch(pixels, C, x, xcs, 0, stats, static_cast<cudaStream_t>(stream));
 }
 int fsb_bn_finalize(int C, const float* stats, double count, const float* gamma, const float* beta, float eps, float momentum,
                     float* running_mean, float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
@@ -191,6 +208,79 @@ int fsb_affine_act(int64_t pixels, int C, const void* x, int xcs, const float* s
                    uint32_t flags, void* stream) {
   if (pixels <= 0 || C <= 0 || !x || !y || !scale || !shift) return set_error(FSB_ERR_INVALID, "affine_act: bad argument");
   return affine_act_launch(pixels, C, x, xcs, scale, shift, y, ycs, flags, static_cast<cudaStream_t>(stream));
+}
+
+
+int fsb_bn_bwd_reduce(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
+                      int raw_is_f32, const float* mean, const float* invstd, int relu, float* sums, void* stream) {
+  if (pixels <= 0 || C <= 0 || !dy || !raw || !mean || !invstd || !sums || (relu && !y))
+    return set_error(FSB_ERR_INVALID, "bn_bwd_reduce: bad argument");
+  return bn_bwd_reduce_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, relu, sums,
+                              static_cast<cudaStream_t>(stream));
+}
+int fsb_bn_bwd_apply(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
+                     int raw_is_f32, const float* mean, const float* invstd, const float* gamma, const float* sums, double count, int relu,
+                     void* draw, int ocs, float* dgamma, float* dbeta, float gscale, void* stream) {
+  if (pixels <= 0 || C <= 0 || !dy || !raw || !mean || !invstd || !sums || !draw || count <= 0 || gscale <= 0 || (relu && !y))
+    return set_error(FSB_ERR_INVALID, "bn_bwd_apply: bad argument");
+  return bn_bwd_apply_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, gamma, sums, count, relu, draw, ocs,
+                             dgamma, dbeta, gscale, static_cast<cudaStream_t>(stream));
+}
+int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, void* dx, int xcs, void* stream) {
+  if (pixels <= 0 || C <= 0 || !dy || !y || !dx) return set_error(FSB_ERR_INVALID, "relu_bwd: bad argument");
+  return relu_bwd_launch(pixels, C, dy, dcs, y, ycs, dx, xcs, static_cast<cudaStream_t>(stream));
+}
+size_t fsb_conv_packed_dgrad_bytes(const fsb_conv_desc* d) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
+  const fsb_conv_desc t = dgrad_as_fwd_desc(d, d->Cout, d->Cin);
+  const ConvGeom g = conv_geom(&t);
+  return static_cast<size_t>(g.taps) * g.npad * g.kpad * 2;
+}
+int fsb_pack_conv_weight_dgrad(const fsb_conv_desc* d, const float* w, int64_t so, int64_t si, void* packed_t, void* stream) {
+  if (!d || !w || !packed_t) return set_error(FSB_ERR_INVALID, "pack_conv_weight_dgrad: null argument");
+  return pack_dgrad_launch(d, w, so, si, packed_t, static_cast<cudaStream_t>(stream));
+}
+int fsb_conv_dgrad(const fsb_conv_desc* d, const void* dy, int dcs, const void* wpacked_t, const float* w, int64_t so, int64_t si,
+                   void* dx, int xcs, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!dy || !dx || dcs < d->Cout || xcs < d->Cin) return set_error(FSB_ERR_INVALID, "conv_dgrad: bad argument");
+  return conv_dgrad_launch(d, dy, dcs, wpacked_t, w, so, si, dx, xcs, static_cast<cudaStream_t>(stream));
+}
+int fsb_conv_wgrad(const fsb_conv_desc* d, const void* x, const void* dy, int dcs, float* dw, int64_t so, int64_t si,
+                   int accumulate, float gscale, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!x || !dy || !dw || dcs < d->Cout || gscale <= 0) return set_error(FSB_ERR_INVALID, "conv_wgrad: bad argument");
+  return conv_wgrad_launch(d, x, dy, dcs, dw, so, si, accumulate, gscale, static_cast<cudaStream_t>(stream));
+}
+int fsb_bilinear_bwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* dy, int dcs, const void* ymask, int ycs, void* dx,
+                     int xcs, void* stream) {
+  if (N <= 0 || C <= 0 || !dy || !dx) return set_error(FSB_ERR_INVALID, "bilinear_bwd: bad argument");
+  return bilinear_bwd_launch(N, C, Hi, Wi, Ho, Wo, dy, dcs, ymask, ycs, dx, xcs, static_cast<cudaStream_t>(stream));
+}
+int fsb_upsample_logits_bwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* dy, int dy_is_f32, void* dx, int xcs,
+                            float gscale, void* stream) {
+  if (N <= 0 || C <= 0 || !dy || !dx || xcs < C) return set_error(FSB_ERR_INVALID, "upsample_logits_bwd: bad argument");
+  return upsample_logits_bwd_launch(N, C, Hi, Wi, Ho, Wo, dy, dy_is_f32, dx, xcs, gscale, static_cast<cudaStream_t>(stream));
+}
+int fsb_nchw_grad_to_nhwc(int N, int C, int H, int W, const void* dy, int dy_is_f32, void* dx, int xcs, float gscale, void* stream) {
+  if (N <= 0 || C <= 0 || !dy || !dx || xcs < C) return set_error(FSB_ERR_INVALID, "nchw_grad_to_nhwc: bad argument");
+  return nchw_grad_to_nhwc_launch(N, C, H, W, dy, dy_is_f32, dx, xcs, gscale, static_cast<cudaStream_t>(stream));
+}
+int fsb_wsum_fwd(int K, int64_t pixels, int C, const void* const* xs, const int* xcs, const float* wts, void* out, int ocs,
+                 void* stream) {
+  if (pixels <= 0 || C <= 0 || !xs || !xcs || !wts || !out) return set_error(FSB_ERR_INVALID, "wsum_fwd: bad argument");
+  return wsum_fwd_launch(K, pixels, C, xs, xcs, wts, out, ocs, static_cast<cudaStream_t>(stream));
+}
+int fsb_wsum_bwd(int K, int64_t pixels, int C, const void* dout, int docs, const void* const* xs, const int* xcs, const float* wts,
+                 void* const* dxs, const int* dxcs, float* dwts, float gscale, void* stream) {
+  if (pixels <= 0 || C <= 0 || !dout || !wts || gscale <= 0) return set_error(FSB_ERR_INVALID, "wsum_bwd: bad argument");
+  return wsum_bwd_launch(K, pixels, C, dout, docs, xs, xcs, wts, dxs, dxcs, dwts, gscale, static_cast<cudaStream_t>(stream));
+}
+int fsb_add_inplace(int64_t pixels, int C, const void* x, int xcs, void* y, int ycs, void* stream) {
+  if (pixels <= 0 || C <= 0 || !x || !y) return set_error(FSB_ERR_INVALID, "add_inplace: bad argument");
+  return add_inplace_launch(pixels, C, x, xcs, y, ycs, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

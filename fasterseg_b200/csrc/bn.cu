@@ -75,9 +75,50 @@ bn_stats_kernel(int64_t pixels, int C, const __half* __restrict__ x, int xcs, fl
     atomicAdd(&stats[C + c], b);
   }
 }
-int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, float* stats, cudaStream_t stream) {
-  if (C % 8 || xcs % 8 || C > 2048 || (reinterpret_cast<uintptr_t>(x) & 15))
-    return set_error(FSB_ERR_INVALID, "bn_stats: C and stride must be multiples of 8 (C <= 2048), x 16B aligned");
+// generic (any C / stride) fallback: block = 32 channels x 8 pixel rows
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_generic_kernel(int64_t pixels, int C, const T* __restrict__ x, int xcs, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8][32][2];
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int row = threadIdx.x >> 5;
+  float s = 0.f, q = 0.f;
+  if (c < C)
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * 8 + row; p < pixels; p += static_cast<int64_t>(gridDim.x) * 8) {
+      const float v = static_cast<float>(x[p * xcs + c]);
+      s += v;
+      q += v * v;
+    }
+  red[row][threadIdx.x & 31][0] = s;
+  red[row][threadIdx.x & 31][1] = q;
+  __syncthreads();
+  if (row == 0 && c < C) {
+    for (int r = 1; r < 8; ++r) {
+      s += red[r][threadIdx.x][0];
+      q += red[r][threadIdx.x][1];
+    }
+    atomicAdd(&stats[c], s);
+    atomicAdd(&stats[C + c], q);
+  }
+}
+
+int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* stats, cudaStream_t stream) {
+  if (x_is_f32 || C % 8 || xcs % 8 || C > 2048 || (reinterpret_cast<uintptr_t>(x) & 15)) {
+    int64_t gx = (pixels + 63) / 64;
+    if (gx > 148 * 2) gx = 148 * 2;
+    if (gx < 1) gx = 1;
+    if (x_is_f32)
+      FSB_LAUNCH(bn_stats_generic_kernel<float>, dim3(static_cast<unsigned>(gx), (C + 31) / 32), dim3(256), 0, stream, pixels, C,
+                 static_cast<const float*>(x), xcs, stats);
+    else
+      FSB_LAUNCH(bn_stats_generic_kernel<__half>, dim3(static_cast<unsigned>(gx), (C + 31) / 32), dim3(256), 0, stream, pixels, C,
+                 static_cast<const __half*>(x), xcs, stats);
+    cudaError_t e0 = last_launch_error();
+    if (e0 != cudaSuccess) return set_cuda_error(e0, "bn_stats_generic launch");
+    return FSB_OK;
+  }
   const int cvec = C / 8;
   const int threads = 256;
   if (cvec > threads) return set_error(FSB_ERR_INVALID, "bn_stats: C too large");
@@ -125,8 +166,30 @@ int bn_finalize_launch(int C, const float* stats, double count, const float* gam
   return FSB_OK;
 }
 
+template <typename T>
+__device__ __forceinline__ void load8f(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8f<__half>(const __half* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8f<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-affine_act_kernel(int64_t pixels, int cvec, const __half* __restrict__ x, int xcs, const float* __restrict__ scale,
+affine_act_kernel(int64_t pixels, int cvec, const T* __restrict__ x, int xcs, const float* __restrict__ scale,
                   const float* __restrict__ shift, __half* __restrict__ y, int ycs, int relu) {
   pdl_launch_dependents();
   pdl_wait();
@@ -135,8 +198,8 @@ affine_act_kernel(int64_t pixels, int cvec, const __half* __restrict__ x, int xc
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % cvec);
     const int64_t pix = i / cvec;
-    const uint4 v = *reinterpret_cast<const uint4*>(x + pix * xcs + cv * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    float xin[8];
+    load8f<T>(x + pix * xcs + cv * 8, xin);
     const float4 s0 = *reinterpret_cast<const float4*>(scale + cv * 8);
     const float4 s1 = *reinterpret_cast<const float4*>(scale + cv * 8 + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(shift + cv * 8);
@@ -147,9 +210,8 @@ affine_act_kernel(int64_t pixels, int cvec, const __half* __restrict__ x, int xc
     uint32_t* o = reinterpret_cast<uint32_t*>(&out);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      float r0 = f.x * sc[2 * j] + sf[2 * j];
-      float r1 = f.y * sc[2 * j + 1] + sf[2 * j + 1];
+      float r0 = xin[2 * j] * sc[2 * j] + sf[2 * j];
+      float r1 = xin[2 * j + 1] * sc[2 * j + 1] + sf[2 * j + 1];
       if (relu) {
         r0 = fmaxf(r0, 0.f);
         r1 = fmaxf(r1, 0.f);
@@ -168,9 +230,12 @@ int affine_act_launch(int64_t pixels, int C, const void* x, int xcs, const float
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  FSB_LAUNCH(affine_act_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8, static_cast<const __half*>(x), xcs, scale,
-                                                                     shift, static_cast<__half*>(y), ycs,
-                                                                     (flags & FSB_CONV_RELU) ? 1 : 0);
+  if (flags & FSB_ACT_IN_F32)
+    FSB_LAUNCH(affine_act_kernel<float>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8,
+               static_cast<const float*>(x), xcs, scale, shift, static_cast<__half*>(y), ycs, (flags & FSB_CONV_RELU) ? 1 : 0);
+  else
+    FSB_LAUNCH(affine_act_kernel<__half>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8,
+               static_cast<const __half*>(x), xcs, scale, shift, static_cast<__half*>(y), ycs, (flags & FSB_CONV_RELU) ? 1 : 0);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "affine_act launch");
   return FSB_OK;

@@ -10,6 +10,8 @@
 
 namespace fsb {
 
+int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* stats, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int64_t so, int64_t si, int taps, int Cout, int Cin,
                                         int npad, int kpad, __half* __restrict__ out) {
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
     }
   }
   __half* yp = p.y + static_cast<size_t>(pix) * d.y_cstride + cg * 8;
+  float* yp32 = reinterpret_cast<float*>(p.y) + static_cast<size_t>(pix) * d.y_cstride + cg * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = cg * 8 + j;
@@ -96,7 +99,10 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
     }
     if (d.flags & FSB_CONV_AFFINE) v = v * (p.scale ? p.scale[ch] : 1.f) + (p.shift ? p.shift[ch] : 0.f);
     if (d.flags & FSB_CONV_RELU) v = fmaxf(v, 0.f);
-    yp[j] = __float2half_rn(v);
+    if (d.flags & FSB_CONV_OUT_F32)
+      yp32[j] = v;
+    else
+      yp[j] = __float2half_rn(v);
   }
 }
 
@@ -113,12 +119,20 @@ int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacke
   p.scale = scale;
   p.shift = shift;
   p.y = static_cast<__half*>(y);
-  p.stats = stats;
+  // per-element atomics would serialise on Cout addresses: take the statistics in a second pass over the (fp16) output
+  const bool want_stats = (d->flags & FSB_CONV_STATS) && stats;
+  p.stats = nullptr;
+  p.d.flags &= ~FSB_CONV_STATS;
   const int64_t total = static_cast<int64_t>(d->N) * d->Ho * d->Wo * ((d->Cout + 7) / 8);
   const int64_t blocks = (total + 127) / 128;
   FSB_LAUNCH(conv_direct_kernel, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream, p);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "conv_direct launch");
+  if (want_stats) {
+    if (d->flags & (FSB_CONV_AFFINE | FSB_CONV_RELU)) return set_error(FSB_ERR_INVALID, "conv_direct: STATS needs a raw (no epilogue) output");
+    return bn_stats_launch(static_cast<int64_t>(d->N) * d->Ho * d->Wo, d->Cout, y, d->y_cstride,
+                           (d->flags & FSB_CONV_OUT_F32) ? 1 : 0, stats, stream);
+  }
   return FSB_OK;
 }
 

@@ -154,7 +154,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     const int ow = w0 + m % p.tw;
     const bool pix_ok = (oh < p.Ho) && (ow < p.Wo);
     __half* yrow = p.y + (static_cast<size_t>(img) * p.Ho * p.Wo + static_cast<size_t>(oh) * p.Wo + ow) * p.y_cstride + n0;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0);
+    const bool out_f32 = (p.flags & FSB_CONV_OUT_F32) != 0;
+    float* yrow32 = reinterpret_cast<float*>(p.y) +
+                    (static_cast<size_t>(img) * p.Ho * p.Wo + static_cast<size_t>(oh) * p.Wo + ow) * p.y_cstride + n0;
+    const bool vec_ok = out_f32 ? ((reinterpret_cast<uintptr_t>(yrow32) & 15) == 0) : ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0);
     const bool relu = (p.flags & FSB_CONV_RELU) != 0;
     const bool do_stats = (p.flags & FSB_CONV_STATS) != 0 && p.stats != nullptr;
     mbar_wait(&tmem_full_bar, 0);
@@ -188,7 +191,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         float x = f[j] * s_scale[c + j] + s_shift[c + j];
         f[j] = relu ? fmaxf(x, 0.f) : x;
       }
-      if (pix_ok) {
+      if (pix_ok && out_f32) {
+        const int remaining = p.Cout - (n0 + c);
+        if (remaining >= 16 && vec_ok) {
+          float4* dst = reinterpret_cast<float4*>(yrow32 + c);
+          dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+          dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+          dst[2] = make_float4(f[8], f[9], f[10], f[11]);
+          dst[3] = make_float4(f[12], f[13], f[14], f[15]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < remaining) yrow32[c + j] = f[j];
+        }
+      } else if (pix_ok) {
         const int remaining = p.Cout - (n0 + c);
         if (remaining >= 16 && vec_ok) {
           uint4 o0, o1;

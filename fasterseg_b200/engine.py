@@ -82,10 +82,16 @@ def conv_bn_act(x: torch.Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], 
     wp = packed_weight(conv, ci, co)
     bn = active_bn(bn) if bn is not None else None
     training = bn is not None and (bn.training or bn.running_mean is None)
+    want_grad = torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)
     if not training:
+        if want_grad and bn is None:
+            from .autograd import conv_bias_act  # conv (+bias) with backward, e.g. Head.conv_1x1
+            assert out is None and off == (0, 0)
+            return conv_bias_act(x, conv, relu, ci, co)
+        # eval-mode BN: inference only (the teacher runs under no_grad, train/train.py:249-252)
         scale, shift = folded_bn(bn, co, conv.bias)
         return F_.conv_fwd(x, wp, co, k, s, p, scale, shift, relu=relu, out=out, off=off)
-    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+    if want_grad:
         from .autograd import conv_bn_act_train  # training path with backward
         return conv_bn_act_train(x, conv, bn, relu, ci, co, out=out, off=off)
     return conv_bn_act_train_nograd(x, conv, bn, relu, ci, co, out=out, off=off)
@@ -97,7 +103,7 @@ def conv_bn_act_train_nograd(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
     k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
     wp = packed_weight(conv, ci, co)
     stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
-    raw = F_.conv_fwd(x, wp, co, k, s, p, relu=False, off=off, stats=stats)
+    raw = F_.conv_fwd(x, wp, co, k, s, p, relu=False, off=off, stats=stats, out_f32=True)
     N, _, Ho, Wo = raw.shape
     stats = dp_allreduce_stats(stats)
     count = N * Ho * Wo * dp_world_size()
@@ -107,7 +113,7 @@ def conv_bn_act_train_nograd(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
                                         bn.running_var if bn.track_running_stats else None)
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
-    return F_.affine_act(raw, scale, shift, relu=relu, out=out if out is not None else raw)
+    return F_.affine_act(raw, scale, shift, relu=relu, out=out)
 
 
 # ----------------------------------------------------------------------------------------------

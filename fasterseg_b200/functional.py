@@ -13,7 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, FSB_CONV_AFFINE, FSB_CONV_FORCE_DIRECT, FSB_CONV_RELU, FSB_CONV_STATS, check
+from ._lib import (ConvDesc, FSB_ACT_IN_F32, FSB_CONV_AFFINE, FSB_CONV_FORCE_DIRECT, FSB_CONV_OUT_F32, FSB_CONV_RELU,
+                   FSB_CONV_STATS, check)
 
 
 def _stream() -> int:
@@ -32,10 +33,10 @@ def empty_nhwc(N, Cc, H, W, device, dtype=torch.float16) -> torch.Tensor:
     return buf if cpad == Cc else buf[:, :Cc]
 
 
-def nhwc_info(t: torch.Tensor) -> Tuple[int, int, int, int, int]:
-    """-> (N, C, H, W, channel_stride); raises unless `t` is fp16 channels-last addressable."""
-    if t.dtype != torch.float16 or t.dim() != 4 or not t.is_cuda:
-        raise ValueError("expected a 4-D CUDA fp16 tensor, got %s %s" % (t.dtype, tuple(t.shape)))
+def nhwc_info(t: torch.Tensor, dtype=torch.float16) -> Tuple[int, int, int, int, int]:
+    """-> (N, C, H, W, channel_stride); raises unless `t` is a channels-last addressable CUDA tensor of `dtype`."""
+    if t.dtype != dtype or t.dim() != 4 or not t.is_cuda:
+        raise ValueError("expected a 4-D CUDA %s tensor, got %s %s" % (dtype, t.dtype, tuple(t.shape)))
     N, Cc, H, W = t.shape
     sn, sc, sh, sw = t.stride()
     cs = sw
@@ -114,19 +115,23 @@ def bn_fold(gamma, beta, mean, var, eps, conv_bias=None):
 
 
 def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=False, out=None, off=(0, 0),
-             stats=None, force_direct=False):
-    """y = act(conv(x) * scale + shift); x/out NHWC fp16 views (see module docstring)."""
+             stats=None, force_direct=False, out_f32=False):
+    """y = act(conv(x) * scale + shift); x/out NHWC fp16 views (see module docstring).  out_f32: fp32 NHWC output (the
+    training path's raw conv result, normalised by BatchNorm from un-rounded values)."""
     N, Cin, H, W, xcs = nhwc_info(x)
     Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    odt = torch.float32 if out_f32 else torch.float16
     if out is None:
-        out = empty_nhwc(N, Cout, Ho, Wo, x.device)
-    No, Co, Hy, Wy, ycs = nhwc_info(out)
+        out = empty_nhwc(N, Cout, Ho, Wo, x.device, dtype=odt)
+    No, Co, Hy, Wy, ycs = nhwc_info(out, odt)
     assert (No, Co, Hy, Wy) == (N, Cout, Ho, Wo), ((No, Co, Hy, Wy), (N, Cout, Ho, Wo))
     flags = (FSB_CONV_RELU if relu else 0) | (FSB_CONV_AFFINE if (scale is not None or shift is not None) else 0)
     if stats is not None:
         flags |= FSB_CONV_STATS
     if force_direct:
         flags |= FSB_CONV_FORCE_DIRECT
+    if out_f32:
+        flags |= FSB_CONV_OUT_F32
     d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, ycs, flags)
     check(_lib.lib().fsb_conv_fwd(C.byref(d), _ptr(x), _ptr(wpacked), _ptr(scale), _ptr(shift), _ptr(out), _ptr(stats),
                                   _stream()), "fsb_conv_fwd")
@@ -209,10 +214,141 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
 
 
 def affine_act(x, scale, shift, relu=False, out=None):
-    N, Cc, H, W, xcs = nhwc_info(x)
+    N, Cc, H, W, xcs = nhwc_info(x, x.dtype)
     if out is None:
         out = empty_nhwc(N, Cc, H, W, x.device)
     _, _, _, _, ycs = nhwc_info(out)
-    check(_lib.lib().fsb_affine_act(N * H * W, Cc, _ptr(x), xcs, _ptr(scale), _ptr(shift), _ptr(out), ycs,
-                                    FSB_CONV_RELU if relu else 0, _stream()), "fsb_affine_act")
+    flags = (FSB_CONV_RELU if relu else 0) | (FSB_ACT_IN_F32 if x.dtype == torch.float32 else 0)
+    check(_lib.lib().fsb_affine_act(N * H * W, Cc, _ptr(x), xcs, _ptr(scale), _ptr(shift), _ptr(out), ycs, flags, _stream()),
+          "fsb_affine_act")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# backward / training wrappers (kernels in csrc/train.cu)
+# ----------------------------------------------------------------------------------------------
+def bn_bwd(dy, y, raw, mean, invstd, gamma, count, relu, gscale, want_param_grads=True, allreduce=None):
+    """BatchNorm(+ReLU) backward -> (draw, dgamma, dbeta).  `allreduce(sums)` hook = SyncBN backward."""
+    N, Cc, H, W, dcs = nhwc_info(dy)
+    _, _, _, _, rcs = nhwc_info(raw, raw.dtype)
+    rf32 = int(raw.dtype == torch.float32)
+    ycs = nhwc_info(y)[4] if relu else 0
+    pixels = N * H * W
+    sums = torch.zeros(2 * Cc, device=dy.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_bwd_reduce(pixels, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
+                                       _ptr(invstd), int(relu), _ptr(sums), _stream()), "fsb_bn_bwd_reduce")
+    if allreduce is not None:
+        sums = allreduce(sums)
+    draw = empty_nhwc(N, Cc, H, W, dy.device)
+    dg = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    db = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    check(_lib.lib().fsb_bn_bwd_apply(pixels, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
+                                      _ptr(invstd), _ptr(gamma), _ptr(sums), float(count), int(relu), _ptr(draw),
+                                      nhwc_info(draw)[4], _ptr(dg), _ptr(db), float(gscale), _stream()), "fsb_bn_bwd_apply")
+    return draw, dg, db
+
+
+def relu_bwd(dy, y):
+    N, Cc, H, W, dcs = nhwc_info(dy)
+    ycs = nhwc_info(y)[4]
+    dx = empty_nhwc(N, Cc, H, W, dy.device)
+    check(_lib.lib().fsb_relu_bwd(N * H * W, Cc, _ptr(dy), dcs, _ptr(y), ycs, _ptr(dx), nhwc_info(dx)[4], _stream()), "fsb_relu_bwd")
+    return dx
+
+
+def pack_conv_weight_dgrad(w, Cin, Cout, ksize):
+    d = ConvDesc(1, 8, 8, Cin, Cout, ksize, 1, (ksize - 1) // 2, 1, 0, 0, 8, 8, Cin, Cout, 0)
+    nbytes = _lib.lib().fsb_conv_packed_dgrad_bytes(C.byref(d))
+    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.float16)
+    check(_lib.lib().fsb_pack_conv_weight_dgrad(C.byref(d), _ptr(w), w.stride(0), w.stride(1), _ptr(out), _stream()),
+          "fsb_pack_conv_weight_dgrad")
+    return out
+
+
+def conv_dgrad(dy, w, x_shape, Cin, Cout, ksize, stride, pad, off=(0, 0), wpacked_t=None, force_direct=False):
+    """dx of conv(x, w[:Cout, :Cin]); x_shape = (N, Cin, H, W) of the forward input."""
+    N, _, H, W = x_shape
+    Nd, Cd, Ho, Wo, dcs = nhwc_info(dy)
+    assert Cd == Cout and Nd == N
+    dx = empty_nhwc(N, Cin, H, W, dy.device)
+    flags = FSB_CONV_FORCE_DIRECT if force_direct else 0
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, Cin, Cout, flags)
+    check(_lib.lib().fsb_conv_dgrad(C.byref(d), _ptr(dy), dcs, _ptr(wpacked_t), _ptr(w), w.stride(0), w.stride(1), _ptr(dx),
+                                    nhwc_info(dx)[4], _stream()), "fsb_conv_dgrad")
+    return dx
+
+
+def conv_wgrad(x, dy, w_like, Cin, Cout, ksize, stride, pad, gscale, off=(0, 0)):
+    """fp32 gradient with the shape/strides of the master weight `w_like` (zero outside the active corner)."""
+    N, Cx, H, W, xcs = nhwc_info(x)
+    _, Cd, Ho, Wo, dcs = nhwc_info(dy)
+    assert Cx == Cin and Cd == Cout
+    full = (w_like.shape[0] == Cout and w_like.shape[1] == Cin)
+    dw = torch.empty_like(w_like, dtype=torch.float32, memory_format=torch.contiguous_format) if full else \
+        torch.zeros_like(w_like, dtype=torch.float32, memory_format=torch.contiguous_format)
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, Cout, 0)
+    check(_lib.lib().fsb_conv_wgrad(C.byref(d), _ptr(x), _ptr(dy), dcs, _ptr(dw), dw.stride(0), dw.stride(1), 0, float(gscale),
+                                    _stream()), "fsb_conv_wgrad")
+    return dw
+
+
+def bilinear_bwd(dy, in_hw, relu_mask_y=None):
+    N, Cc, Ho, Wo, dcs = nhwc_info(dy)
+    Hi, Wi = in_hw
+    dx = empty_nhwc(N, Cc, Hi, Wi, dy.device)
+    ycs = nhwc_info(relu_mask_y)[4] if relu_mask_y is not None else 0
+    check(_lib.lib().fsb_bilinear_bwd(N, Cc, Hi, Wi, Ho, Wo, _ptr(dy), dcs, _ptr(relu_mask_y), ycs, _ptr(dx), nhwc_info(dx)[4],
+                                      _stream()), "fsb_bilinear_bwd")
+    return dx
+
+
+def upsample_logits_bwd(dy_nchw, in_hw, gscale):
+    dy_nchw = dy_nchw.contiguous()
+    N, Cc, Ho, Wo = dy_nchw.shape
+    Hi, Wi = in_hw
+    dx = empty_nhwc(N, Cc, Hi, Wi, dy_nchw.device)
+    check(_lib.lib().fsb_upsample_logits_bwd(N, Cc, Hi, Wi, Ho, Wo, _ptr(dy_nchw), int(dy_nchw.dtype == torch.float32), _ptr(dx),
+                                             nhwc_info(dx)[4], float(gscale), _stream()), "fsb_upsample_logits_bwd")
+    return dx
+
+
+def nchw_grad_to_nhwc(dy_nchw, gscale):
+    dy_nchw = dy_nchw.contiguous()
+    N, Cc, H, W = dy_nchw.shape
+    dx = empty_nhwc(N, Cc, H, W, dy_nchw.device)
+    check(_lib.lib().fsb_nchw_grad_to_nhwc(N, Cc, H, W, _ptr(dy_nchw), int(dy_nchw.dtype == torch.float32), _ptr(dx),
+                                           nhwc_info(dx)[4], float(gscale), _stream()), "fsb_nchw_grad_to_nhwc")
+    return dx
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+    return arr
+
+
+def wsum_fwd(xs, wts, out=None):
+    N, Cc, H, W, _ = nhwc_info(xs[0])
+    if out is None:
+        out = empty_nhwc(N, Cc, H, W, xs[0].device)
+    strides = (C.c_int * len(xs))(*[nhwc_info(t)[4] for t in xs])
+    check(_lib.lib().fsb_wsum_fwd(len(xs), N * H * W, Cc, _ptr_array(xs), strides, _ptr(wts), _ptr(out), nhwc_info(out)[4],
+                                  _stream()), "fsb_wsum_fwd")
+    return out
+
+
+def wsum_bwd(dout, xs, wts, need_dx, need_dw, gscale):
+    N, Cc, H, W, docs = nhwc_info(dout)
+    K = len(xs)
+    dxs = [empty_nhwc(N, Cc, H, W, dout.device) if need_dx[k] else None for k in range(K)]
+    dw = torch.zeros(K, device=dout.device, dtype=torch.float32) if need_dw else None
+    xstr = (C.c_int * K)(*[nhwc_info(t)[4] for t in xs])
+    dxstr = (C.c_int * K)(*[0 if t is None else nhwc_info(t)[4] for t in dxs])
+    check(_lib.lib().fsb_wsum_bwd(K, N * H * W, Cc, _ptr(dout), docs, _ptr_array(xs), xstr, _ptr(wts), _ptr_array(dxs), dxstr,
+                                  _ptr(dw), float(gscale), _stream()), "fsb_wsum_bwd")
+    return dxs, dw
+
+
+def add_inplace(x, y):
+    N, Cc, H, W, xcs = nhwc_info(x)
+    check(_lib.lib().fsb_add_inplace(N * H * W, Cc, _ptr(x), xcs, _ptr(y), nhwc_info(y)[4], _stream()), "fsb_add_inplace")
+    return y

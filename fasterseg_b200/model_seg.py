@@ -299,6 +299,10 @@ class Network_Multi_Path_Infer(nn.Module):
         """arm 1x1 -> bilinear to skip's size -> cat([up, skip]) -> refine 3x3, with the concat done by writing both
         producers into one buffer (model_seg.py:304-307, 309-312, 316-319)."""
         a = arm(coarse)
+        if torch.is_grad_enabled() and a.requires_grad:
+            from . import autograd as AG
+            up = AG.bilinear(a, (skip.shape[2], skip.shape[3]))
+            return refine(AG.cat_channels([up, skip]))
         N, c_up = a.shape[0], a.shape[1]
         c_skip, Hs, Ws = skip.shape[1], skip.shape[2], skip.shape[3]
         cat = F_.empty_nhwc(N, c_up + c_skip, Hs, Ws, a.device)
@@ -325,21 +329,27 @@ class Network_Multi_Path_Infer(nn.Module):
         fused_in = getattr(ctx, "fused_in", None)  # allocated before the fork (see _trunk)
         if fused_in is None:
             fused_in = F_.empty_nhwc(ref.shape[0], f8 * self._branch, ref.shape[2], ref.shape[3], ref.device)  # cat(pred8)
+        grad = torch.is_grad_enabled() and any(t.requires_grad for t in outputs8 + outputs16 + outputs32)
+        pred8_list = []
         for branch in range(self._branch):
             last = self.lasts[branch]
-            slot = fused_in[:, branch * f8:(branch + 1) * f8]
+            slot = None if grad else fused_in[:, branch * f8:(branch + 1) * f8]
             with ctx.on(branch):
                 if last == 2:
                     if training: pred32.append(outputs32[branch])
                     out = self._arm_refine(self.arms32[0], self.refines32[0], outputs32[branch], outputs16[branch])
                     if training: pred16.append(outputs16[branch])
-                    self._arm_refine(self.arms32[1], self.refines32[1], out, outputs8[branch], out=slot)
+                    pred8_list.append(self._arm_refine(self.arms32[1], self.refines32[1], out, outputs8[branch], out=slot))
                 elif last == 1:
                     if training: pred16.append(outputs16[branch])
-                    self._arm_refine(self.arms16, self.refines16, outputs16[branch], outputs8[branch], out=slot)
+                    pred8_list.append(self._arm_refine(self.arms16, self.refines16, outputs16[branch], outputs8[branch], out=slot))
                 elif last == 0:
-                    F_.copy_channels(F_.to_nhwc_half(outputs8[branch]), slot)
+                    pred8_list.append(outputs8[branch])
+                    if not grad:
+                        F_.copy_channels(F_.to_nhwc_half(outputs8[branch]), slot)
         ctx.join()
+        if grad:
+            fused_in = _cat_channels(pred8_list)
         pred8 = self.heads8(self.ffm(fused_in))
         if not training:
             return pred8
@@ -380,11 +390,12 @@ class Network_Multi_Path_Infer(nn.Module):
         outputs8, outputs16, outputs32 = self._trunk(input, ctx)
         if self.training:
             pred8, pred16, pred32 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
-            pred8 = F_.upsample_logits(pred8, (pred8.size(2) * 8, pred8.size(3) * 8), dtype=self.logits_dtype)
+            up = _upsample_logits
+            pred8 = up(pred8, (pred8.size(2) * 8, pred8.size(3) * 8), self.logits_dtype)
             if pred16 is not None:
-                pred16 = F_.upsample_logits(pred16, (pred16.size(2) * 16, pred16.size(3) * 16), dtype=self.logits_dtype)
+                pred16 = up(pred16, (pred16.size(2) * 16, pred16.size(3) * 16), self.logits_dtype)
             if pred32 is not None:
-                pred32 = F_.upsample_logits(pred32, (pred32.size(2) * 32, pred32.size(3) * 32), dtype=self.logits_dtype)
+                pred32 = up(pred32, (pred32.size(2) * 32, pred32.size(3) * 32), self.logits_dtype)
             return pred8, pred16, pred32
         pred8 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
         return F_.upsample_logits(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), dtype=self.logits_dtype)
@@ -477,11 +488,21 @@ class _BranchCtx:
             self.forked = False
 
 
+def _upsample_logits(x, size, dtype):
+    if torch.is_grad_enabled() and x.requires_grad:
+        from . import autograd as AG
+        return AG.upsample_logits(x, size, dtype)
+    return F_.upsample_logits(x, size, dtype=dtype)
+
+
 def _cat_channels(tensors):
     """torch.cat(dim=1) of NHWC fp16 views through the strided copy kernel."""
     tensors = [F_.to_nhwc_half(t) for t in tensors]
     if len(tensors) == 1:
         return tensors[0]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        from . import autograd as AG
+        return AG.cat_channels(tensors)
     N, _, H, W = tensors[0].shape
     total = sum(t.shape[1] for t in tensors)
     out = F_.empty_nhwc(N, total, H, W, tensors[0].device)

@@ -229,6 +229,14 @@ class _Residual(_Primitive):
             return x
         x = F_.to_nhwc_half(x)
         H, W = int(x.size(2)), int(x.size(3))
+        grad = torch.is_grad_enabled() and (x.requires_grad or self.conv1.weight.requires_grad)
+        if grad:
+            from . import autograd as AG
+            y = AG.bilinear(x, (H // 2, W // 2))
+            for i, (conv, bn) in enumerate(stages):
+                last = i == len(stages) - 1
+                y = engine.conv_bn_act(y, conv, bn, relu=(not last) or self.stride == 2)
+            return AG.bilinear(y, (H, W), relu=True) if self.stride == 1 else y
         y = F_.bilinear(x, (H // 2, W // 2))
         for i, (conv, bn) in enumerate(stages):
             last = i == len(stages) - 1
@@ -337,6 +345,9 @@ def _factorized_reduce_s2(op, x, out):
     N, _, H, W = x.shape
     assert H % 2 == 0 and W % 2 == 0, "FactorizedReduce needs even H, W (the reference's cat fails otherwise)"
     co = 2 * co_half
+    if bn.training and torch.is_grad_enabled() and (x.requires_grad or op.conv1.weight.requires_grad):
+        from .autograd import factorized_reduce_train
+        return factorized_reduce_train(op, x, bn, ci, co_half, out)
     if out is None:
         out = F_.empty_nhwc(N, co, H // 2, W // 2, x.device)
     w1 = engine.packed_weight(op.conv1, ci, co_half)
@@ -346,15 +357,13 @@ def _factorized_reduce_s2(op, x, out):
         F_.conv_fwd(x, w1, co_half, 1, 2, 0, scale[:co_half], shift[:co_half], relu=True, out=out[:, :co_half])
         F_.conv_fwd(x, w2, co_half, 1, 2, 0, scale[co_half:], shift[co_half:], relu=True, out=out[:, co_half:], off=(1, 1))
         return out
-    if torch.is_grad_enabled() and (x.requires_grad or op.conv1.weight.requires_grad):
-        from .autograd import factorized_reduce_train
-        return factorized_reduce_train(op, x, bn, ci, co_half, out)
     stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
     # stats layout is [sum(co) | sumsq(co)]: run each half with its own view of a 2 x co_half scratch, then merge
     s1 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
     s2 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
-    F_.conv_fwd(x, w1, co_half, 1, 2, 0, out=out[:, :co_half], stats=s1)
-    F_.conv_fwd(x, w2, co_half, 1, 2, 0, out=out[:, co_half:], off=(1, 1), stats=s2)
+    raw = F_.empty_nhwc(N, co, H // 2, W // 2, x.device, dtype=torch.float32)
+    F_.conv_fwd(x, w1, co_half, 1, 2, 0, out=raw[:, :co_half], stats=s1, out_f32=True)
+    F_.conv_fwd(x, w2, co_half, 1, 2, 0, out=raw[:, co_half:], off=(1, 1), stats=s2, out_f32=True)
     stats[:co_half], stats[co_half:co] = s1[:co_half], s2[:co_half]
     stats[co:co + co_half], stats[co + co_half:] = s1[co_half:], s2[co_half:]
     stats = engine.dp_allreduce_stats(stats)
@@ -363,7 +372,7 @@ def _factorized_reduce_s2(op, x, out):
                                         bn.running_mean, bn.running_var)
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
-    return F_.affine_act(out, scale, shift, relu=True, out=out)
+    return F_.affine_act(raw, scale, shift, relu=True, out=out)
 
 
 OPS = {

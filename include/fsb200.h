@@ -41,6 +41,9 @@ typedef enum fsb_status {
 #define FSB_CONV_RELU 1u        /* y = max(y, 0) */
 #define FSB_CONV_AFFINE 2u      /* y = y * scale[c] + shift[c]  (BN eval folded, or conv bias in shift) */
 #define FSB_CONV_FORCE_DIRECT 4u /* use the CUDA-core direct kernel (validation / odd shapes) */
+#define FSB_CONV_OUT_F32 16u    /* y is fp32 NHWC (y_cstride in fp32 elements): the training path keeps the raw conv output in
+                                   fp32 so that BatchNorm normalises un-rounded values, like the fp32 reference */
+#define FSB_ACT_IN_F32 32u      /* fsb_affine_act: x is fp32 NHWC */
 #define FSB_CONV_STATS 8u       /* also accumulate per-channel sum / sum-of-squares of the (pre-affine) fp32 conv
                                    output into stats[0..Cout) / stats[Cout..2Cout) (BN train, K2) */
 
@@ -135,6 +138,65 @@ int fsb_bn_finalize(int C, const float* stats, double count, const float* gamma,
 /* y = act(x * scale[c] + shift[c]) elementwise on fp16 NHWC (in place allowed) */
 int fsb_affine_act(int64_t pixels, int C, const void* x, int x_cstride, const float* scale, const float* shift,
                    void* y, int y_cstride, uint32_t flags, void* stream);
+
+/* --- backward / training kernels (K5, K7, K8 + resize backward) ------------------------------ */
+/* All gradient tensors are fp16 NHWC like activations unless stated; `gscale` is the static loss scale the caller
+ * applied to the incoming gradients: parameter / scalar gradients written in fp32 are divided by it. */
+
+/* BatchNorm(+ReLU) backward, pass 1: per-channel sums over `pixels` of dz and dz * xhat, with
+ *   dz = dy * (relu ? y > 0 : 1),  xhat = (raw - mean[c]) * invstd[c]   (raw = conv output saved by the forward)
+ * sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat  (fp32, caller zeroes; all-reduce across ranks for SyncBN). */
+int fsb_bn_bwd_reduce(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
+                      int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, int relu, float* sums,
+                      void* stream);
+/* pass 2: draw = gamma*invstd * (dz - sum_dz/count - xhat * sum_dzxhat/count); also dgamma = sum_dzxhat/gscale,
+ * dbeta = sum_dz/gscale accumulated (+=) into fp32 dgamma/dbeta when non-NULL. */
+int fsb_bn_bwd_apply(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
+                     int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, const float* gamma, const float* sums,
+                     double count, int relu, void* draw, int draw_cstride, float* dgamma, float* dbeta, float gscale,
+                     void* stream);
+/* dy_in = dy * (y > 0)  (ReLU backward for affine-free paths) */
+int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, void* dx, int dx_cstride,
+                 void* stream);
+
+/* conv data gradient (autograd of F.conv2d wrt input): dx[n,hi,wi,ci] = sum_{r,s,co} dy[n,ho,wo,co] * w[co,ci,r,s] over the
+ * (ho,wo,r,s) with ho*stride + r - pad + off_h == hi (same for w).  `d` describes the FORWARD conv (x: N,H,W,Cin ...);
+ * dy has d->Ho x d->Wo x Cout with pixel stride dy_cstride; dx has H x W x Cin with pixel stride dx_cstride.
+ * w: fp32 OIHW master weight with strides like fsb_pack_conv_weight.  Stride-1 convs run on the tcgen05 kernel with
+ * a transposed/rotated weight pack (wpacked_t from fsb_pack_conv_weight_dgrad); others use the direct kernel. */
+size_t fsb_conv_packed_dgrad_bytes(const fsb_conv_desc* d);
+int fsb_pack_conv_weight_dgrad(const fsb_conv_desc* d, const float* w, int64_t w_stride_o, int64_t w_stride_i, void* packed_t,
+                               void* stream);
+int fsb_conv_dgrad(const fsb_conv_desc* d, const void* dy, int dy_cstride, const void* wpacked_t, const float* w,
+                   int64_t w_stride_o, int64_t w_stride_i, void* dx, int dx_cstride, void* stream);
+/* conv weight gradient: dw[co,ci,r,s] (+)= (1/gscale) * sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*stride+r-pad+off_h, ..., ci]
+ * written into the fp32 OIHW gradient tensor with the master weight's strides (only the [0,Cout) x [0,Cin) corner).
+ * accumulate != 0 adds to the existing contents (a cell invoked twice, model_search.py:326-329). */
+int fsb_conv_wgrad(const fsb_conv_desc* d, const void* x, const void* dy, int dy_cstride, float* dw, int64_t w_stride_o,
+                   int64_t w_stride_i, int accumulate, float gscale, void* stream);
+
+/* bilinear (align_corners=True) backward: dx (Hi x Wi) = transpose of the forward interpolation applied to dy (Ho x Wo);
+ * relu_mask_y != NULL fuses the ReLU-after-upsample backward (dy * (y > 0)). */
+int fsb_bilinear_bwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* dy, int dy_cstride, const void* relu_mask_y,
+                     int y_cstride, void* dx, int dx_cstride, void* stream);
+/* backward of fsb_upsample_logits_nchw: dlogits NCHW (fp32 if dy_is_f32 else fp16) at (Ho, Wo) -> NHWC fp16 (Hi, Wi),
+ * multiplied by gscale. */
+int fsb_upsample_logits_bwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* dy_nchw, int dy_is_f32, void* dx,
+                            int dx_cstride, float gscale, void* stream);
+/* NCHW (fp32/fp16) gradient -> NHWC fp16 scaled by gscale (backward of fsb_nhwc_f16_to_nchw) */
+int fsb_nchw_grad_to_nhwc(int N, int C, int H, int W, const void* dy, int dy_is_f32, void* dx, int dx_cstride, float gscale,
+                          void* stream);
+
+/* K5: weighted multi-tensor sum (MixedOp / beta aggregation, model_search.py:75-78,326-333):
+ *   out = sum_k wts[k] * xs[k]   (K <= 8 tensors of identical shape; wts fp32[K] on the device)
+ * backward: dxs[k] = wts[k] * dout (fp16), dwts[k] += <dout, xs[k]> / gscale (fp32). */
+int fsb_wsum_fwd(int K, int64_t pixels, int C, const void* const* xs, const int* x_cstrides, const float* wts, void* out,
+                 int out_cstride, void* stream);
+int fsb_wsum_bwd(int K, int64_t pixels, int C, const void* dout, int dout_cstride, const void* const* xs,
+                 const int* x_cstrides, const float* wts, void* const* dxs, const int* dx_cstrides, float* dwts, float gscale,
+                 void* stream);
+/* y (+)= x elementwise over a channel-slice view (gradient accumulation when a tensor feeds several consumers) */
+int fsb_add_inplace(int64_t pixels, int C, const void* x, int x_cstride, void* y, int y_cstride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,11 +54,38 @@ def conv_padding(kernel_size, stride, dilation=1):
 
 
 # --------------------------------------------------------------------------------------
+# optional fp16-storage emulation: with EMULATE_FP16["on"] every activation an fp16-storage implementation would write to
+# memory (unit outputs, resize outputs, the image, the weights) is rounded to fp16 in the forward pass, and the matching
+# activation gradients are rounded (at loss scale EMULATE_FP16["gscale"]) in the backward pass.  Arithmetic stays fp32.
+# Used by the tests to separate "implementation error" from the conditioning of train-mode BatchNorm chains: the CUDA path
+# must be as close to the fp32 oracle as this emulation is.
+# --------------------------------------------------------------------------------------
+EMULATE_FP16 = {"on": False, "gscale": 1024.0}
+
+
+def _q(t):
+    """Round an activation to fp16 storage (straight-through) + round its gradient, when emulation is on."""
+    if not EMULATE_FP16["on"]:
+        return t
+    out = t + (t.detach().half().float() - t.detach())
+    if out.requires_grad:
+        s = EMULATE_FP16["gscale"]
+        out.register_hook(lambda g: (g * s).half().float() / s)
+    return out
+
+
+def _qw(w):
+    if not EMULATE_FP16["on"]:
+        return w
+    return w + (w.detach().half().float() - w.detach())
+
+
+# --------------------------------------------------------------------------------------
 # tensor primitives (what L0 = torch.nn.functional does for the reference)
 # --------------------------------------------------------------------------------------
 def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1):
     """F.conv2d call site search/slimmable_ops.py:47 and every nn.Conv2d in operations.py."""
-    return F.conv2d(x, w, bias, stride, padding, dilation, 1)
+    return F.conv2d(_q(x) if x.shape[1] == 3 else x, _qw(w), bias, stride, padding, dilation, 1)
 
 
 def batchnorm(x, weight, bias, running_mean, running_var, training, momentum=BN_MOMENTUM, eps=BN_EPS):
@@ -182,7 +209,7 @@ def conv_norm(x, p: Params, kernel_size=3, stride=1, padding=None, training=Fals
         w = _us_w(w, ratio.ci(w.shape[1]), ratio.co(w.shape[0]))
     y = conv2d(x, w, None, stride, padding)
     y = _us_bn(y, p.sub("conv.1"), None if ratio is None else ratio.idx_out(), training)
-    return F.relu(y)
+    return _q(F.relu(y))
 
 
 def basic_residual_1x(x, p: Params, stride=1, training=False, ratio: Optional[Ratio] = None):
@@ -192,21 +219,21 @@ def basic_residual_1x(x, p: Params, stride=1, training=False, ratio: Optional[Ra
         w = _us_w(w, ratio.ci(w.shape[1]), ratio.co(w.shape[0]))
     y = conv2d(x, w, None, stride, 1)
     y = _us_bn(y, p.sub("bn1"), None if ratio is None else ratio.idx_out(), training)
-    return F.relu(y)
+    return _q(F.relu(y))
 
 
 def basic_residual_downup_1x(x, p: Params, stride=1, training=False, ratio: Optional[Ratio] = None):
     """BasicResidual_downup_1x.forward, search/operations.py:270-277."""
     H, W = x.shape[2], x.shape[3]
-    y = bilinear_ac(x, (H // 2, W // 2))
+    y = _q(bilinear_ac(x, (H // 2, W // 2)))
     w = p["conv1.weight"]
     if ratio is not None:
         w = _us_w(w, ratio.ci(w.shape[1]), ratio.co(w.shape[0]))
     y = conv2d(y, w, None, 1, 1)
     y = _us_bn(y, p.sub("bn1"), None if ratio is None else ratio.idx_out(), training)
     if stride == 1:
-        y = bilinear_ac(y, (H, W))
-    return F.relu(y)
+        y = bilinear_ac(_q(y), (H, W))
+    return _q(F.relu(y))
 
 
 def basic_residual_2x(x, p: Params, stride=1, training=False, ratio: Optional[Ratio] = None):
@@ -218,8 +245,8 @@ def basic_residual_2x(x, p: Params, stride=1, training=False, ratio: Optional[Ra
         w1 = _us_w(w1, ratio.ci(w1.shape[1]), co)
         w2 = _us_w(w2, co, co)  # set_ratio((ratio[1], ratio[1])), operations.py:314
         idx = ratio.idx_out()
-    y = F.relu(_us_bn(conv2d(x, w1, None, stride, 1), p.sub("bn1"), idx, training))
-    y = F.relu(_us_bn(conv2d(y, w2, None, 1, 1), p.sub("bn2"), idx, training))
+    y = _q(F.relu(_us_bn(conv2d(x, w1, None, stride, 1), p.sub("bn1"), idx, training)))
+    y = _q(F.relu(_us_bn(conv2d(y, w2, None, 1, 1), p.sub("bn2"), idx, training)))
     return y
 
 
@@ -233,12 +260,12 @@ def basic_residual_downup_2x(x, p: Params, stride=1, training=False, ratio: Opti
         w1 = _us_w(w1, ratio.ci(w1.shape[1]), co)
         w2 = _us_w(w2, co, co)
         idx = ratio.idx_out()
-    y = bilinear_ac(x, (H // 2, W // 2))
-    y = F.relu(_us_bn(conv2d(y, w1, None, 1, 1), p.sub("bn1"), idx, training))
+    y = _q(bilinear_ac(x, (H // 2, W // 2)))
+    y = _q(F.relu(_us_bn(conv2d(y, w1, None, 1, 1), p.sub("bn1"), idx, training)))
     y = _us_bn(conv2d(y, w2, None, 1, 1), p.sub("bn2"), idx, training)
     if stride == 1:
-        y = bilinear_ac(y, (H, W))
-    return F.relu(y)
+        y = bilinear_ac(_q(y), (H, W))
+    return _q(F.relu(y))
 
 
 def factorized_reduce(x, p: Params, stride=1, training=False, ratio: Optional[Ratio] = None, slimmable=None):
@@ -260,12 +287,12 @@ def factorized_reduce(x, p: Params, stride=1, training=False, ratio: Optional[Ra
             w2 = _us_w(w2, ci, co_half)
             idx = ratio.idx_out()
         y = torch.cat([conv2d(x, w1, None, 2, 0), conv2d(x[:, :, 1:, 1:], w2, None, 2, 0)], dim=1)
-        return F.relu(_us_bn(y, p.sub("bn"), idx, training))
+        return _q(F.relu(_us_bn(y, p.sub("bn"), idx, training)))
     if not slimmable:
         return x
     w = p["conv1.weight"]
     w = _us_w(w, ratio.ci(w.shape[1]), ratio.co(w.shape[0]))
-    return F.relu(_us_bn(conv2d(x, w, None, 1, 0), p.sub("bn"), ratio.idx_out(), training))
+    return _q(F.relu(_us_bn(conv2d(x, w, None, 1, 0), p.sub("bn"), ratio.idx_out(), training)))
 
 
 OP_FUNCS = [factorized_reduce, basic_residual_1x, basic_residual_downup_1x, basic_residual_2x,
@@ -277,7 +304,7 @@ def conv_bn_relu(x, p: Params, stride=1, pad=0, has_bn=True, has_relu=True, trai
     y = conv2d(x, p["conv.weight"], p["conv.bias"] if p.has("conv.bias") else None, stride, pad)
     if has_bn:
         y = _bn(y, p.sub("bn"), training)
-    return F.relu(y) if has_relu else y
+    return _q(F.relu(y) if has_relu else y)
 
 
 def feature_fusion(x, p: Params, training=False):
@@ -288,7 +315,7 @@ def feature_fusion(x, p: Params, training=False):
 def head(x, p: Params, training=False):
     """Head.forward: 3x3 ConvBnRelu -> 1x1 conv with bias, search/seg_oprs.py:271-274."""
     y = conv_bn_relu(x, p.sub("conv_3x3"), 1, 1, training=training)
-    return conv2d(y, p["conv_1x1.weight"], p["conv_1x1.bias"], 1, 0)
+    return _q(conv2d(y, p["conv_1x1.weight"], p["conv_1x1.bias"], 1, 0))
 
 
 # --------------------------------------------------------------------------------------
@@ -543,19 +570,19 @@ def student_forward(x, sd: Dict[str, torch.Tensor], st: StudentStructure, traini
             if training:
                 pred32.append(out32[b])
             o = conv_norm(out32[b], P.sub("arms32.0"), 1, 1, 0, training)
-            o = bilinear_ac(o, out16[b].shape[2:])
+            o = _q(bilinear_ac(o, out16[b].shape[2:]))
             o = conv_norm(torch.cat([o, out16[b]], 1), P.sub("refines32.0"), 3, 1, 1, training)
             if training:
                 pred16.append(out16[b])
             o = conv_norm(o, P.sub("arms32.1"), 1, 1, 0, training)
-            o = bilinear_ac(o, out8[b].shape[2:])
+            o = _q(bilinear_ac(o, out8[b].shape[2:]))
             o = conv_norm(torch.cat([o, out8[b]], 1), P.sub("refines32.1"), 3, 1, 1, training)
             pred8.append(o)
         elif last == 1:
             if training:
                 pred16.append(out16[b])
             o = conv_norm(out16[b], P.sub("arms16"), 1, 1, 0, training)
-            o = bilinear_ac(o, out8[b].shape[2:])
+            o = _q(bilinear_ac(o, out8[b].shape[2:]))
             o = conv_norm(torch.cat([o, out8[b]], 1), P.sub("refines16"), 3, 1, 1, training)
             pred8.append(o)
         else:

@@ -270,8 +270,13 @@ def golden_convnorm_gate(ns):
 def golden_student(ns_train):
     """Full derived-network forward (eval + train mode) of arch_1 (student) and arch_0 (teacher)."""
     rec = {}
-    for arch_idx, hw in ((1, (64, 128)), (0, (64, 128)), (1, (96, 160))):
+    # train-mode vectors use 192x384 as well: BatchNorm over the handful of samples that a 64x128 input leaves at 1/32
+    # resolution (4 per channel inside the zoomed ops) is numerically chaotic and not representative of the reference's
+    # own training resolutions (>= 224x448, config_search.py:92-101)
+    for arch_idx, hw in ((1, (64, 128)), (0, (64, 128)), (1, (96, 160)), (1, (192, 384))):
         for training in (False, True):
+            if hw == (192, 384) and not training:
+                continue
             model, state, lasts = rh.build_reference_student(ns_train, arch_idx, train_mode=training)
             fill_module_from_seed(model, 2024 + arch_idx)
             model.train(training)

@@ -121,15 +121,16 @@ def test_student_eval_matches_reference(arch_idx, hw):
     assert agree > 0.9995, agree
 
 
-def test_student_train_matches_reference():
+@pytest.mark.parametrize("hw", [(64, 128), (192, 384)])
+def test_student_train_matches_reference(hw):
     z = H.load_npz("student.npz")
     st, g = H.student_structure(1)
     full = {k: tuple(v) for k, v in g["state_dict_shapes_train"].items() if not k.endswith("num_batches_tracked")}
     sd = orc.random_state_dict(full, seed=2025)
-    x = orc.random_input((2, 3, 64, 128), seed=100)
+    x = orc.random_input((2, 3) + hw, seed=100)
     with torch.no_grad():
         p8, p16, p32 = orc.student_forward(x, sd, st, training=True)
-    tag = "arch1.64x128.train"
+    tag = "arch1.%dx%d.train" % hw
     for name, o in (("pred8", p8), ("pred16", p16), ("pred32", p32)):
         assert H.rel_err(o.numpy()[:, :, ::4, ::4], z[tag + "/" + name + ".s4"]) < 1e-4, name
     for k in ("stem.0.conv.1.running_mean", "stem.0.conv.1.running_var", "heads8.conv_3x3.bn.running_var"):

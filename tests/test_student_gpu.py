@@ -78,3 +78,81 @@ def test_student_eval_vs_oracle_256x512():
     agree = (y.argmax(1) == ref.argmax(1)).mean()
     print("argmax agreement %.5f" % agree)
     assert agree > 0.995
+
+
+def test_student_train_forward_vs_reference_golden():
+    """Train-mode forward (BN batch statistics, 3 full-resolution logits, running-stat updates), model_seg.py:357-362."""
+    z = H.load_npz("student.npz")
+    model, g = _build_student(1, training=True)
+    model = model.cuda().train()
+    _load_seeded(model, g, 2025, key="state_dict_shapes_train")
+    x = orc.random_input((2, 3, 192, 384), seed=100).cuda()
+    with torch.no_grad():
+        p8, p16, p32 = model(x)
+    tag = "arch1.192x384.train"
+    for name, o in (("pred8", p8), ("pred16", p16), ("pred32", p32)):
+        nerr, maxerr = _report(tag + " " + name, o.float().cpu().numpy()[:, :, ::4, ::4], z[tag + "/" + name + ".s4"])
+        # train-mode BN chains with random weights amplify fp16 STORAGE rounding layer by layer (the fp16-emulating CPU oracle
+        # shows the same 1.4-2.8e-2, see test_student_train_step_gradients_vs_oracle); eval-mode parity is the 1e-3 gate
+        assert nerr < 4e-2, name
+    sd = model.state_dict()
+    for k in ("stem.0.conv.1.running_mean", "stem.0.conv.1.running_var", "heads8.conv_3x3.bn.running_var"):
+        np.testing.assert_allclose(sd[k].cpu().numpy(), z[tag + "/after:" + k], rtol=3e-3, atol=3e-4)
+
+
+def test_student_train_step_gradients_vs_oracle():
+    """One forward+backward of a student loss surrogate on 2x3x192x384: every parameter gradient vs CPU autograd through the
+    oracle (same weights, same batch).
+
+    Train-mode BatchNorm chains with random weights are ill-conditioned: merely rounding the stored activations to fp16 (the
+    oracle's EMULATE_FP16 mode, arithmetic still fp32 on the CPU) moves the fp32 gradients by up to ~30 % at the stem.  The
+    CUDA path implements exactly those storage semantics, so the gate is two-sided:
+      (a) err(ours, fp32 oracle) <= 1.5 x err(fp16-emulating oracle, fp32 oracle) + 2e-2   for every parameter
+      (b) the forward outputs deviate from fp32 no more than 1.5 x the emulation does."""
+    model, g = _build_student(1, training=True)
+    model = model.cuda().train()
+    sd = _load_seeded(model, g, 31, key="state_dict_shapes_train")
+    st, _ = H.student_structure(1)
+    x = orc.random_input((2, 3, 192, 384), seed=32)
+    tgt = [orc.random_input((2, 19, 192, 384), seed=33 + i) for i in range(3)]
+
+    def run_oracle(emulate):
+        orc.EMULATE_FP16["on"] = emulate
+        try:
+            sd_ref = {k: v.clone().requires_grad_(not ("running" in k)) for k, v in sd.items()}
+            outs = orc.student_forward(x, sd_ref, st, training=True)
+            sum((o * t).mean() for o, t in zip(outs, tgt)).backward()
+        finally:
+            orc.EMULATE_FP16["on"] = False
+        return [o.detach().numpy() for o in outs], {k: v.grad.numpy() for k, v in sd_ref.items() if v.grad is not None}
+
+    o32, g32 = run_oracle(False)
+    o16, g16 = run_oracle(True)
+    outs_g = model(x.cuda())
+    loss = sum((o * t.cuda()).mean() for o, t in zip(outs_g, tgt))
+    loss.backward()
+    torch.cuda.synchronize()
+    for name, a, b, c in zip(("pred8", "pred16", "pred32"), outs_g, o32, o16):
+        e_ours, e_emu = H.rel_err(a.detach().float().cpu().numpy(), b), H.rel_err(c, b)
+        print("%s: ours vs fp32 %.3e | fp16-emulation vs fp32 %.3e | ours vs emulation %.3e" % (
+            name, e_ours, e_emu, H.rel_err(a.detach().float().cpu().numpy(), c)))
+        assert e_ours <= 1.5 * e_emu + 2e-3
+    checked, worst_ratio = 0, 0.0
+    for k, p in model.named_parameters():
+        if k not in g32 or np.linalg.norm(g32[k]) < 1e-12:
+            continue
+        assert p.grad is not None, k
+        ours = p.grad.float().cpu().numpy()
+        e_ours, e_emu = H.rel_err(ours, g32[k]), H.rel_err(g16[k], g32[k])
+        checked += 1
+        worst_ratio = max(worst_ratio, e_ours / (e_emu + 1e-9))
+        if checked % 12 == 1:
+            print("   grad %-42s ours vs fp32 %.2e | emulation vs fp32 %.2e | ours vs emulation %.2e" % (
+                k, e_ours, e_emu, H.rel_err(ours, g16[k])))
+        assert e_ours <= 1.5 * e_emu + 2e-2, "%s: ours %.3e vs emulation %.3e" % (k, e_ours, e_emu)
+    print("checked %d parameter gradients; worst err(ours)/err(emulation) = %.2f" % (checked, worst_ratio))
+    assert checked > 100
+    # the set of parameters without gradient must match autograd on the oracle
+    no_grad_ours = {k for k, p in model.named_parameters() if p.grad is None}
+    no_grad_ref = {k for k in dict(model.named_parameters()) if k not in g32}
+    assert no_grad_ours == no_grad_ref, sorted(no_grad_ours ^ no_grad_ref)
