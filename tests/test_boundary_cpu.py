@@ -97,3 +97,23 @@ def test_op_classes_state_dict_and_api():
     import torch.nn as nn
     from fasterseg_b200.slimmable_ops import USBatchNorm2d, USConv2d
     assert issubclass(USConv2d, nn.Conv2d) and issubclass(USBatchNorm2d, nn.BatchNorm2d)
+
+
+def _build_supernet(layers):
+    import torch.nn as nn
+    from fasterseg_b200.model_search import Network_Multi_Path
+    return Network_Multi_Path(19, layers, nn.CrossEntropyLoss(ignore_index=255), Fch=12,
+                              width_mult_list=[4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.], prun_modes=['max', 'arch_ratio'],
+                              stem_head_width=[(1, 1), (8. / 12, 8. / 12)])
+
+
+def test_supernet_state_dict_and_parameter_order_match_reference():
+    meta = H.load_json("supernet_meta.json")
+    m = _build_supernet(meta["case"]["layers"])
+    got = {k: list(v.shape) for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    assert got == meta["shapes"]
+    assert [k for k, _ in m.named_parameters()] == meta["param_order"]
+    assert len(m._arch_parameters) == 2 and len(m._arch_parameters[0]) == 8
+    assert m._arch_names[1]["ratios"] == ["ratio_1_0", "ratio_1_1", "ratio_1_2"]
+    # teacher ('max') has a single width choice, the student ('arch_ratio') five (model_search.py:522-529)
+    assert tuple(m.ratio_0_0.shape) == (meta["case"]["layers"] - 1, 1) and tuple(m.ratio_1_2.shape) == (meta["case"]["layers"] - 2, 5)

@@ -1,0 +1,110 @@
+"""GPU parity of the search supernet (fasterseg_b200.model_search.Network_Multi_Path): forward in every width-sampling
+mode against golden vectors from the UNMODIFIED reference, and `_loss` + backward (the search / pretrain step of
+search/train_search.py:240-250) against the CPU oracle with the two-sided fp16-storage gate."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import fasterseg_oracle as orc
+from oracle import supernet_oracle as sno
+from tests import helpers as H
+from tests.test_boundary_cpu import _build_supernet
+from tests.test_supernet_oracle import CASE, FWD, META, cfg, inputs, make_sd
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(model):
+    sd = make_sd()
+    own = model.state_dict()
+    for k, v in sd.items():
+        own[k].copy_(v)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.eps, m.momentum = orc.BN_EPS, orc.BN_MOMENTUM
+    return sd
+
+
+@pytest.mark.parametrize("tag,arch_idx,mode,train,np_seed,torch_seed", FWD)
+def test_supernet_forward_vs_reference_golden(tag, arch_idx, mode, train, np_seed, torch_seed):
+    z = H.load_npz("supernet.npz")
+    model = _build_supernet(CASE["layers"]).cuda()
+    _load(model)
+    model.train(train)
+    x, _ = inputs()
+    if np_seed is not None:
+        np.random.seed(np_seed)
+    if torch_seed is not None:
+        torch.manual_seed(torch_seed)
+    model.arch_idx, model.prun_mode = arch_idx, mode
+    with torch.no_grad():
+        preds = model(x.cuda())
+    torch.cuda.synchronize()
+    worst = 0.0
+    for i, p in enumerate(preds):
+        assert p.dtype == torch.float32 and p.is_contiguous()
+        ref = z["%s/pred%d" % (tag, i)]
+        got = p.cpu().numpy() if train else p.cpu().numpy()[:, :, ::8, ::8]
+        worst = max(worst, H.rel_err(got, ref))
+    print("%s: worst norm-wise rel err over the 5 logits %.3e" % (tag, worst))
+    # eval mode: running statistics, well-conditioned -> fp16 tolerance; train mode: ill-conditioned BN chains (see
+    # tests/test_student_gpu.py::test_student_train_step_gradients_vs_oracle for the tolerance model)
+    assert worst < (5e-3 if not train else 5e-2)
+    if train:
+        sd = model.state_dict()
+        for k in z.files:
+            if k.startswith(tag + "/after:"):
+                np.testing.assert_allclose(sd[k.split("after:")[1]].cpu().numpy(), z[k], rtol=2e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("tag,pretrain,np_seed,torch_seed", [("loss.pretrain", True, 11, 12), ("loss.search", "some-dir", 13, 14)])
+def test_supernet_loss_backward(tag, pretrain, np_seed, torch_seed):
+    z = H.load_npz("supernet.npz")
+    x, tgt = inputs()
+    crit = nn.CrossEntropyLoss(ignore_index=255)
+
+    def run_oracle(emulate):
+        sd = make_sd(requires_grad=True)
+        np.random.seed(np_seed)
+        torch.manual_seed(torch_seed)
+        orc.EMULATE_FP16["on"] = emulate
+        try:
+            loss = sno.supernet_loss(x, tgt, sd, cfg(), crit, pretrain)
+            loss.backward()
+        finally:
+            orc.EMULATE_FP16["on"] = False
+        return float(loss.detach()), {k: v.grad.numpy() for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+    l32, g32 = run_oracle(False)
+    l16, g16 = run_oracle(True)
+    model = _build_supernet(CASE["layers"]).cuda()
+    _load(model)
+    model.train(True)
+    np.random.seed(np_seed)
+    torch.manual_seed(torch_seed)
+    loss = model._loss(x.cuda(), tgt.cuda(), pretrain)
+    loss.backward()
+    torch.cuda.synchronize()
+    lo = float(loss.detach())
+    print("%s: loss ours %.5f | fp32 oracle %.5f | fp16-emulating oracle %.5f | reference %.5f" % (tag, lo, l32, l16, float(z[tag + "/loss"][0])))
+    assert abs(lo - l32) <= 1.5 * abs(l16 - l32) + 2e-3 * abs(l32)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert sorted(k for k, g in grads.items() if g is None) == sorted(k for k in grads if k not in g32)
+    checked, worst = 0, 0.0
+    # typical deviation that fp16 storage alone causes in this (ill-conditioned, randomly initialised) supernet
+    typical = float(np.median([H.rel_err(g16[k], g32[k]) for k in g32 if np.linalg.norm(g32[k]) >= 1e-10]))
+    print("%s: median err(fp16-emulating oracle, fp32 oracle) over all gradients = %.3e" % (tag, typical))
+    for k, g in grads.items():
+        if g is None or np.linalg.norm(g32[k]) < 1e-10:
+            continue
+        e_ours, e_emu = H.rel_err(g.float().cpu().numpy(), g32[k]), H.rel_err(g16[k], g32[k])
+        e_emu = max(e_emu, typical)  # tiny tensors (a 4x2 beta) can be lucky in one realisation
+        worst = max(worst, e_ours / (e_emu + 1e-9))
+        checked += 1
+        if k.startswith(("alpha_", "beta_", "ratio_")) or checked % 80 == 0:
+            print("   grad %-40s ours vs fp32 %.2e | emulation vs fp32 %.2e" % (k, e_ours, e_emu))
+        assert e_ours <= 2.0 * e_emu + 3e-2, "%s: ours %.3e vs emulation %.3e" % (k, e_ours, e_emu)
+    print("%s: checked %d gradients, worst err(ours)/err(emulation) %.2f" % (tag, checked, worst))
+    assert checked > 300
+    assert len([k for k, g in grads.items() if g is None]) == META[tag + ".no_grad_count"]

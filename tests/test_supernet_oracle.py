@@ -1,0 +1,91 @@
+"""Pin the CPU supernet oracle (oracle/supernet_oracle.py) to golden vectors from the UNMODIFIED reference
+(search/model_search.py): forward in all four width-sampling modes, eval mode, and `_loss` value + gradients for the
+pretrain and search configurations.  CPU only."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import fasterseg_oracle as orc
+from oracle import supernet_oracle as sno
+from tests import helpers as H
+
+META = H.load_json("supernet_meta.json")
+CASE = META["case"]
+
+
+def make_sd(requires_grad=False):
+    shapes = {k: tuple(v) for k, v in META["shapes"].items()}
+    sd = orc.random_state_dict(shapes, seed=CASE["seed"])
+    if requires_grad:
+        for k, v in sd.items():
+            if "running" not in k:
+                v.requires_grad_(True)
+    return sd
+
+
+def inputs():
+    B, (Hh, Ww) = CASE["batch"], CASE["hw"]
+    x = orc.random_input((B, 3, Hh, Ww), seed=CASE["seed"] + 1)
+    rs = np.random.RandomState(CASE["seed"] + 2)
+    t = rs.randint(0, 19, size=(B, Hh // 8, Ww // 8)).astype(np.int64)
+    t[rs.uniform(size=t.shape) < 0.05] = 255
+    return x, torch.from_numpy(t)
+
+
+def cfg():
+    return sno.SupernetConfig(layers=CASE["layers"])
+
+
+FWD = [("max.a0", 0, "max", True, None, None), ("min.a0", 0, "min", True, None, None),
+       ("random.a1", 1, "random", True, 5, None), ("arch_ratio.a1", 1, None, True, None, 7),
+       ("eval.max.a0", 0, "max", False, None, None)]
+
+
+@pytest.mark.parametrize("tag,arch_idx,mode,train,np_seed,torch_seed", FWD)
+def test_supernet_forward_matches_reference(tag, arch_idx, mode, train, np_seed, torch_seed):
+    z = H.load_npz("supernet.npz")
+    sd = make_sd()
+    x, _ = inputs()
+    if np_seed is not None:
+        np.random.seed(np_seed)
+    if torch_seed is not None:
+        torch.manual_seed(torch_seed)
+    with torch.no_grad():
+        preds = sno.supernet_forward(x, sd, cfg(), arch_idx, mode, train)
+    for i, p in enumerate(preds):
+        ref = z["%s/pred%d" % (tag, i)]
+        got = p.numpy() if train else p.numpy()[:, :, ::8, ::8]
+        assert H.rel_err(got, ref) < 2e-4, (tag, i, H.rel_err(got, ref))
+    if train:
+        for k in z.files:
+            if k.startswith(tag + "/after:"):
+                np.testing.assert_allclose(sd[k.split("after:")[1]].numpy(), z[k], rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag,pretrain,np_seed,torch_seed", [("loss.pretrain", True, 11, 12), ("loss.search", "some-dir", 13, 14)])
+def test_supernet_loss_and_grads_match_reference(tag, pretrain, np_seed, torch_seed):
+    z = H.load_npz("supernet.npz")
+    sd = make_sd(requires_grad=True)
+    x, tgt = inputs()
+    np.random.seed(np_seed)
+    torch.manual_seed(torch_seed)
+    loss = sno.supernet_loss(x, tgt, sd, cfg(), nn.CrossEntropyLoss(ignore_index=255), pretrain)
+    loss.backward()
+    assert abs(float(loss) - float(z[tag + "/loss"][0])) < 1e-4 * abs(float(z[tag + "/loss"][0]))
+    n = 0
+    for k in z.files:
+        if k.startswith(tag + "/grad:"):
+            key = k.split("grad:")[1]
+            assert sd[key].grad is not None, key
+            # train-mode BN chains are ill-conditioned: two fp32 CPU evaluations that differ only in summation order
+            # (ATen conv of the sliced weight view vs our restatement) already disagree at the 5e-3 level on alpha grads
+            assert H.rel_err(sd[key].grad.numpy(), z[k]) < 3e-2, (key, H.rel_err(sd[key].grad.numpy(), z[k]))
+            n += 1
+    assert n >= 12
+    no_grad = sorted(k for k, v in sd.items() if v.requires_grad and v.grad is None)
+    assert len(no_grad) == META[tag + ".no_grad_count"]
+    for k in META[tag + ".no_grad_sample"]:
+        assert k in no_grad, k
+    sq = sum(float((v.grad.double() ** 2).sum()) for v in sd.values() if v.requires_grad and v.grad is not None)
+    assert abs(sq ** 0.5 - float(z[tag + "/grad_norm"][0])) < 1e-2 * float(z[tag + "/grad_norm"][0])
