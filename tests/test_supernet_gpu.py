@@ -98,6 +98,19 @@ def test_supernet_loss_backward(tag, pretrain, np_seed, torch_seed):
     for k, g in grads.items():
         if g is None or np.linalg.norm(g32[k]) < 1e-10:
             continue
+        if k.startswith("ratio_"):
+            # d loss / d(width score) = <d out, out> / score: every consumer of `out` starts with conv -> BatchNorm, which makes
+            # the loss invariant to the scale of `out`, so this inner product is ~0 in exact arithmetic and what any
+            # implementation (fp32 included) returns is cancellation noise.  Gate it in ABSOLUTE terms against the alpha
+            # gradients, which are the same kind of quantity without the cancellation.
+            scale = float(np.linalg.norm(g32["alpha_1_0"]))
+            a_ours = float(np.linalg.norm(g.float().cpu().numpy() - g32[k]))
+            a_emu = float(np.linalg.norm(g16[k] - g32[k]))
+            print("   grad %-12s |g32| %.2e  abs err ours %.2e, emulation %.2e  (|alpha_1_0 grad| %.2e)" % (
+                k, float(np.linalg.norm(g32[k])), a_ours, a_emu, scale))
+            assert a_ours <= 3.0 * a_emu + 0.05 * scale, k
+            checked += 1
+            continue
         e_ours, e_emu = H.rel_err(g.float().cpu().numpy(), g32[k]), H.rel_err(g16[k], g32[k])
         e_emu = max(e_emu, typical)  # tiny tensors (a 4x2 beta) can be lucky in one realisation
         worst = max(worst, e_ours / (e_emu + 1e-9))
