@@ -112,14 +112,21 @@ def batchnorm(x, weight, bias, running_mean, running_var, training, momentum=BN_
     return y * weight.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
 
 
+RESIZE_IMPL = {"aten": False}  # bench.py's CPU-baseline legs switch to the reference's own ATen call for a fair timing
+
+
 def bilinear_ac(x, size):
     """F.interpolate(mode='bilinear', align_corners=True), search/operations.py:271,275,437,444.
 
     src = dst * (in - 1) / (out - 1) (0 when out == 1); two-tap lerp per axis.
-    Written out (not via F.interpolate) so that the oracle states the formula itself.
+    Written out (not via F.interpolate) so that the oracle states the formula itself; tests/test_oracle_golden.py checks the
+    formula against F.interpolate outputs of the reference.  RESIZE_IMPL["aten"] routes to F.interpolate (what the
+    reference executes) -- used only when TIMING the CPU baseline, where the gather-based formula would be unfairly slow.
     """
     N, C, H, W = x.shape
     Ho, Wo = int(size[0]), int(size[1])
+    if RESIZE_IMPL["aten"]:
+        return F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True)
 
     def taps(n_in, n_out):
         if n_out > 1:

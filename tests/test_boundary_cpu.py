@@ -117,3 +117,31 @@ def test_supernet_state_dict_and_parameter_order_match_reference():
     assert m._arch_names[1]["ratios"] == ["ratio_1_0", "ratio_1_1", "ratio_1_2"]
     # teacher ('max') has a single width choice, the student ('arch_ratio') five (model_search.py:522-529)
     assert tuple(m.ratio_0_0.shape) == (meta["case"]["layers"] - 1, 1) and tuple(m.ratio_1_2.shape) == (meta["case"]["layers"] - 2, 5)
+
+
+def test_launcher_shadows_reference_module_names():
+    """`from operations import *` / `from model_search import Network_Multi_Path` in the unmodified drivers must resolve to
+    our modules (fasterseg_b200/launch.py)."""
+    import importlib
+    import sys
+    from fasterseg_b200 import launch
+    saved = {n: sys.modules.get(n) for n in launch.SHADOWED}
+    try:
+        launch.install_compat_patches()
+        launch.install_shadow_modules()
+        ops = importlib.import_module("operations")
+        ms = importlib.import_module("model_search")
+        mseg = importlib.import_module("model_seg")
+        assert ops.__name__ == "fasterseg_b200.operations" and hasattr(ops, "OPS")
+        assert ms.Network_Multi_Path.__module__ == "fasterseg_b200.model_search"
+        assert mseg.Network_Multi_Path_Infer.__module__ == "fasterseg_b200.model_seg"
+        ns = {}
+        exec("from operations import *\nfrom slimmable_ops import USConv2d, USBatchNorm2d\nfrom seg_oprs import Head, FeatureFusion\n"
+             "from genotypes import PRIMITIVES", ns)
+        assert set(ops.__all__) <= set(ns) and ns["PRIMITIVES"][0] == "skip"
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
