@@ -31,6 +31,7 @@ _SIGS = {
     "fsb_last_error_string": (C.c_char_p, []),
     "fsb_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "fsb_set_pdl": (C.c_int, [C.c_int]),
+    "fsb_debug_set_buffer": (C.c_int, [_P]),
     "fsb_conv_packed_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "fsb_pack_conv_weight": (C.c_int, [C.POINTER(ConvDesc), _P, C.c_int64, C.c_int64, _P, _P]),
     "fsb_bn_fold": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P]),

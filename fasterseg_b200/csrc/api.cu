@@ -83,6 +83,8 @@ int wsum_bwd_launch(int, int64_t, int, const void*, int, const void* const*, con
                     float*, float, cudaStream_t);
 int add_inplace_launch(int64_t, int, const void*, int, void*, int, cudaStream_t);
 
+extern unsigned long long* g_dbg_buffer;
+
 static int check_desc(const fsb_conv_desc* d) {
   if (!d) return set_error(FSB_ERR_INVALID, "null conv desc");
   if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0)
@@ -113,6 +115,11 @@ const char* fsb_last_error_string(void) { return g_err; }
 
 int fsb_set_pdl(int enabled) {
   g_pdl = enabled ? 1 : 0;
+  return FSB_OK;
+}
+
+int fsb_debug_set_buffer(void* dev_u64x128) {
+  g_dbg_buffer = static_cast<unsigned long long*>(dev_u64x128);
   return FSB_OK;
 }
 
@@ -153,7 +160,7 @@ int fsb_conv_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, con
   if (!x || !wpacked || !y) return set_error(FSB_ERR_INVALID, "conv_fwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((d->flags & FSB_CONV_FORCE_DIRECT) || !conv_tc_supported(d)) return conv_direct_launch(d, x, wpacked, scale, shift, y, stats, st);
-  return conv_tc_launch(d, x, wpacked, scale, shift, y, stats, st);
+  return conv_tc_dispatch(d, x, wpacked, scale, shift, y, stats, st);
 }
 
 int fsb_stem_conv_nchw(int N, int H, int W, int Cout, const void* x, int x_is_f32, const float* w, const float* scale,

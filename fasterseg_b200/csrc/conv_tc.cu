@@ -26,6 +26,9 @@ constexpr int kThreads = 192;
 struct ConvTcParams {
   CUtensorMap tmap_a[4];
   CUtensorMap tmap_b;
+  CUtensorMap tmap_y[2];  // output maps for the TMA-store epilogue: [0] 64-channel slabs (SW128), [1] tail slab (dense)
+  int tma_store;          // 1: fp16 tile staged in smem and written with cp.async.bulk.tensor (full-line, clipped stores)
+  int tail_w;             // channels in the last slab of an N tile when n_tile % 64 != 0
   int taps;
   int tap_map[9];
   int tap_dh[9];
@@ -163,10 +166,19 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c = 0; c < p.n_tile; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c, v);
+    // TMEM loads are latency-bound (~250 ns per dependent tcgen05.ld + wait): issue up to four 16-column loads, wait once
+    for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
+      uint32_t vv[4][16];
+      const int nb = min(4, (p.n_tile - c0) >> 4);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < nb) tmem_ld16(taddr + c0 + 16 * b, vv[b]);
       tmem_ld_wait();
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+      if (b >= nb) break;
+      const int c = c0 + 16 * b;
+      uint32_t (&v)[16] = vv[b];
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -204,6 +216,28 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
           for (int j = 0; j < 16; ++j)
             if (j < remaining) yrow32[c + j] = f[j];
         }
+      } else if (p.tma_store) {
+        // stage this thread's 16 channels of pixel m: slab = 64 channels; full slabs use the 128B-swizzled layout of the
+        // output tensor map, the tail slab is dense (tail_w * 2 bytes per pixel)
+        uint4 o0, o1;
+        o0.x = pack_half2(f[0], f[1]);
+        o0.y = pack_half2(f[2], f[3]);
+        o0.z = pack_half2(f[4], f[5]);
+        o0.w = pack_half2(f[6], f[7]);
+        o1.x = pack_half2(f[8], f[9]);
+        o1.y = pack_half2(f[10], f[11]);
+        o1.z = pack_half2(f[12], f[13]);
+        o1.w = pack_half2(f[14], f[15]);
+        uint8_t* slab = smem + static_cast<size_t>(c0 >> 6) * (kTileM * 128);
+        const int ch16 = (c - c0) >> 3;  // 16-byte chunk index inside the slab row
+        if (p.n_tile - c0 >= 64) {
+          *reinterpret_cast<uint4*>(slab + m * 128 + ((ch16 ^ (m & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4*>(slab + m * 128 + (((ch16 + 1) ^ (m & 7)) << 4)) = o1;
+        } else {
+          uint8_t* row = slab + m * (p.tail_w * 2) + (ch16 << 4);
+          *reinterpret_cast<uint4*>(row) = o0;
+          *reinterpret_cast<uint4*>(row + 16) = o1;
+        }
       } else if (pix_ok) {
         const int remaining = p.Cout - (n0 + c);
         if (remaining >= 16 && vec_ok) {
@@ -225,7 +259,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             if (j < remaining) yrow[c + j] = __float2half_rn(f[j]);
         }
       }
-    }
+      }  // 16-column chunk
+      if (p.tma_store) {
+        fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(1, 128);             // the 4 epilogue warps
+        if (warp == 2 && lane == 0) {
+          const bool full = (p.n_tile - c0) >= 64;
+          tma_store_4d(&p.tmap_y[full ? 0 : 1], smem + static_cast<size_t>(c0 >> 6) * (kTileM * 128), n0 + c0, w0, h0, img);
+          tma_store_commit();
+        }
+      }
+    }  // 64-column batch
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_read();  // smem must outlive the bulk reads
     tc_fence_before();
   }
   __syncthreads();
@@ -252,7 +297,8 @@ static int encode_tiled(CUtensorMap* map, const void* base, int rank, const uint
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                              : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                          : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
                    bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -266,6 +312,11 @@ static int encode_tiled(CUtensorMap* map, const void* base, int rank, const uint
     return set_error(FSB_ERR_CUDA, buf);
   }
   return FSB_OK;
+}
+
+int encode_tiled_generic(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, int swizzle_bytes) {
+  return encode_tiled(map, base, rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -332,7 +383,29 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > k_iters) stages = k_iters;
   p.stages = stages;
-  const size_t smem_bytes = stage_bytes * stages + 1024;
+  size_t smem_bytes = stage_bytes * stages + 1024;
+  // ---- TMA-store epilogue: fp16 output whose pixels start on 16 B and whose channel count is a multiple of 8 ----
+  p.tma_store = 0;
+  if (!(d->flags & FSB_CONV_OUT_F32) && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+      n_tile % 8 == 0 && !getenv("FSB_NO_TMA_STORE")) {
+    const uint64_t ycs = static_cast<uint64_t>(d->y_cstride) * 2;
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->Wo), static_cast<uint64_t>(d->Ho),
+                              static_cast<uint64_t>(d->N)};
+    const uint64_t str[3] = {ycs, ycs * d->Wo, ycs * d->Wo * d->Ho};
+    const uint32_t box64[4] = {64u, static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), 1u};
+    int rc = 0;
+    if (n_tile >= 64) rc = encode_tiled(&p.tmap_y[0], y, 4, dims, str, box64, 128);
+    p.tail_w = n_tile % 64;
+    if (!rc && p.tail_w) {
+      const uint32_t boxt[4] = {static_cast<uint32_t>(p.tail_w), static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), 1u};
+      rc = encode_tiled(&p.tmap_y[1], y, 4, dims, str, boxt, 0);
+    }
+    if (rc) return rc;
+    if (n_tile < 64) p.tmap_y[0] = p.tmap_y[1];
+    p.tma_store = 1;
+    const size_t staging = static_cast<size_t>((n_tile + 63) / 64) * kTileM * 128 + 1024;
+    if (smem_bytes < staging) smem_bytes = staging;
+  }
 
   // ---- A tensor maps ----
   const __half* xb = static_cast<const __half*>(x);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/fsb200.h"
@@ -63,6 +64,15 @@ inline cudaError_t last_launch_error() {
 int conv_tc_supported(const fsb_conv_desc* d);
 int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                    void* y, float* stats, cudaStream_t stream);
+int conv_tc2_supported(const fsb_conv_desc* d);
+int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
+                    void* y, float* stats, cudaStream_t stream);
+// picks the row-strip kernel for wide 3x3 stride-1 convs, the per-tap kernel otherwise
+inline int conv_tc_dispatch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
+                            void* y, float* stats, cudaStream_t stream) {
+  if (conv_tc2_supported(d)) return conv_tc2_launch(d, x, wpacked, scale, shift, y, stats, stream);
+  return conv_tc_launch(d, x, wpacked, scale, shift, y, stats, stream);
+}
 int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                        void* y, float* stats, cudaStream_t stream);
 

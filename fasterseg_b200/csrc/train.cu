@@ -347,7 +347,7 @@ int conv_dgrad_launch(const fsb_conv_desc* d, const void* dy, int dcs, const voi
                       int64_t si, void* dx, int xcs, cudaStream_t stream) {
   if (d->stride == 1 && d->off_h == 0 && d->off_w == 0 && wpacked_t && !(d->flags & FSB_CONV_FORCE_DIRECT)) {
     fsb_conv_desc t = dgrad_as_fwd_desc(d, dcs, xcs);
-    if (conv_tc_supported(&t)) return conv_tc_launch(&t, dy, wpacked_t, nullptr, nullptr, dx, nullptr, stream);
+    if (conv_tc_supported(&t)) return conv_tc_dispatch(&t, dy, wpacked_t, nullptr, nullptr, dx, nullptr, stream);
   }
   if (!w) return set_error(FSB_ERR_INVALID, "conv_dgrad: the direct path needs the fp32 master weight");
   DgradParams p;

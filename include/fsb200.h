@@ -74,6 +74,10 @@ int fsb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * With it a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps its predecessor's tail. */
 int fsb_set_pdl(int enabled);
 
+/* Developer aid: when set (device buffer of 128 uint64), the row-strip conv kernel records %globaltimer stamps of its
+ * pipeline phases for the first and last CTA.  NULL disables (default). */
+int fsb_debug_set_buffer(void* dev_u64x128);
+
 /* --- weights -------------------------------------------------------------------------------- */
 /* bytes of the packed fp16 weight buffer for `d` */
 size_t fsb_conv_packed_bytes(const fsb_conv_desc* d);

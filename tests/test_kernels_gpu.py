@@ -58,13 +58,23 @@ CONV_CASES = [
     (1, 192, 128, 3, 1, 32, 64),
     (3, 80, 48, 1, 1, 6, 10),
     (1, 16, 16, 3, 1, 8, 8),
+    # wide maps -> row-strip kernel (conv_tc2.cu): R rows x 128 columns per CTA, halo rows read once
+    (1, 64, 64, 3, 1, 20, 256),
+    (2, 32, 32, 3, 1, 9, 130),
+    (1, 128, 128, 3, 1, 16, 128),
+    (1, 96, 64, 3, 1, 12, 256),
+    (1, 64, 192, 3, 1, 8, 200),
+    (1, 256, 256, 3, 1, 6, 128),
+    (1, 80, 48, 3, 1, 5, 97),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("direct", [False, True])
-def test_conv_bn_relu_matches_oracle(case, direct):
+def test_conv_bn_relu_matches_oracle(case, direct, monkeypatch):
     F_ = _F()
+    if case[6] >= 96 and case[3] == 3 and case[4] == 1:
+        monkeypatch.setenv("FSB_CONV_TC2", "2")  # exercise the row-strip kernel on every wide 3x3 case, not only where it is faster
     N, Cin, Cout, k, stride, Hh, Ww = case
     seed = hash(case) % 100000
     x = _rand((N, Cin, Hh, Ww), seed).half().float()
