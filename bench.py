@@ -64,52 +64,74 @@ def synth_weights_(model, seed=12345):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled every 100 ms during the timed regions (B200_PROFILING.md).  Uses NVML in-process
+    (nvidia_ml_py): spawning `nvidia-smi -lms` next to a host-driven copy/launch pipeline halves its throughput because each
+    poll takes driver locks; the nvidia-smi CLI is only the fallback."""
 
     def __init__(self, gpu_index=0):
         self.gpu_index = gpu_index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nv = pynvml
+            self.mode = "nvml"
         except Exception:
-            self.proc = None
+            self.mode = "smi"
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            try:
+                return int(ids[self.gpu_index])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu_index
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                if self.mode == "nvml":
+                    nv = self.nv
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    smax = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.samples.append((float(sm), float(smax), int(reasons)))
+                else:
+                    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                                          "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-i",
+                                          str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    bits = 0
+                    for bit, val in zip((0x8, 0x40, 0x20, 0x4), f[2:6]):
+                        if val.lower().startswith("active"):
+                            bits |= bit
+                    self.samples.append((float(f[0]), float(f[1]), bits))
+            except Exception:
+                pass
+            time.sleep(0.1 if self.mode == "nvml" else 1.0)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({n for _, _, r in self.samples for bit, n in names.items() if r & bit})
+        return {"sm_mhz": statistics.median(s for s, _, _ in self.samples), "sm_max_mhz": max(m for _, m, _ in self.samples),
+                "reasons": reasons, "samples": len(self.samples), "via": self.mode}
 
 
 def measured_peaks():
