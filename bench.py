@@ -173,17 +173,25 @@ def dominant_kernel_roofline(device):
     en.synchronize()
     us = st.elapsed_time(en) * 1000.0 / (reps * nbuf)
     pk = measured_peaks()
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
+    tj = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    if os.path.isfile(tj):
+        with open(tj) as f:
+            traffic = json.load(f).get("traffic_bytes")
     t_tensor = flops / (pk["tflops"] * 1e12)
     t_hbm = abytes / (pk["hbm_gbs"] * 1e9)
     if t_tensor >= t_hbm:
         achieved = flops / (us * 1e-6) / 1e12
         return {"kernel": "conv_tc_kernel<64> (heads8.conv_3x3: 3x3 128->128 @128x256)", "bound": "tensor",
                 "achieved": round(achieved, 2), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["tflops"], 4),
-                "traffic": None, "us_per_launch": round(us, 2), "peak_source": pk["source"],
-                "algorithmic_flops": flops, "algorithmic_bytes": abytes}
+                "traffic": traffic, "us_per_launch": round(us, 2), "peak_source": pk["source"],
+                "algorithmic_flops": flops, "algorithmic_bytes": abytes,
+                "note": "tensor-bound by the roofline (intensity 566 FLOP/B); ncu: tensor pipe active 31 %, L2->SM 8.1 TB/s: 1-CTA "
+                        "SS-mode MMAs are operand-fetch bound (~130 cycles per 128x128x16 MMA, tools/tc2_timeline.py); traffic "
+                        "< algorithmic bytes because the 8.4 MB output stays in L2 during the captured launch"}
     achieved = abytes / (us * 1e-6) / 1e9
     return {"kernel": "conv_tc_kernel<64>", "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "us_per_launch": round(us, 2), "peak_source": pk["source"]}
+            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "us_per_launch": round(us, 2), "peak_source": pk["source"]}
 
 
 def cpu_port_fps(model_state_cpu, frames, threads):

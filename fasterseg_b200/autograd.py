@@ -17,6 +17,13 @@ from . import engine
 from . import functional as F_
 
 GRAD_SCALE = 1024.0
+# Weight gradients are accumulated by the wgrad kernel straight into `param.grad` (created zero-filled on first use) instead
+# of being returned to autograd as freshly allocated full-size tensors: the supernet's slimmable weights are max-width
+# masters of which a forward touches one corner, and it runs 4 forwards per backward.  `loss.backward()` users (the
+# reference drivers, architect.py's first-order step) see exactly the same `.grad`; code that needs
+# `torch.autograd.grad(loss, weights)` can switch this off.
+import os as _os
+FUSED_WGRAD_ACCUMULATION = _os.environ.get("FSB_FUSED_WGRAD", "1") != "0"
 
 
 def set_grad_scale(v: float):
@@ -47,10 +54,16 @@ def _conv_backward(ctx_conv, x, draw, ci, co, off, need_dx, need_dw):
     w = ctx_conv.weight.detach()
     dx = dw = None
     if need_dx:
-        wt = _dgrad_pack(ctx_conv, ci, co) if (s == 1 and off == (0, 0)) else None
+        wt = _dgrad_pack(ctx_conv, ci, co)  # stride 1: one launch; stride 2: one launch per input parity plane
         dx = F_.conv_dgrad(draw, w, tuple(x.shape), ci, co, k, s, p, off=off, wpacked_t=wt)
     if need_dw:
-        dw = F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off)
+        if FUSED_WGRAD_ACCUMULATION:
+            wparam = ctx_conv.weight
+            if wparam.grad is None:
+                wparam.grad = torch.zeros_like(wparam, memory_format=torch.contiguous_format)
+            F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off, accumulate_into=wparam.grad)
+        else:
+            dw = F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off)
     return dx, dw
 
 

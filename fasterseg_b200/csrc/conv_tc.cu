@@ -33,6 +33,7 @@ struct ConvTcParams {
   int tap_map[9];
   int tap_dh[9];
   int tap_dw[9];
+  int tap_widx[9];  // which [tap] slice of the packed weights each tap multiplies (identity for plain convs)
   int k_chunks;
   int Ho, Wo;
   int tiles_w, tiles_h;
@@ -122,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           tma_load_4d(sa, ma, &full_bar[s], kc * BK, cw, chh, img);
-          tma_load_3d(sb, &p.tmap_b, &full_bar[s], kc * BK, n0, tap);
+          tma_load_3d(sb, &p.tmap_b, &full_bar[s], kc * BK, n0, p.tap_widx[tap]);
         }
       }
     }
@@ -337,20 +338,23 @@ int conv_tc_supported(const fsb_conv_desc* d) {
 }
 
 int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
-                   void* y, float* stats, cudaStream_t stream) {
+                   void* y, float* stats, cudaStream_t stream, const ConvTcCustom* cu) {
   const ConvGeom g = conv_geom(d);
+  if (cu && (d->stride != 1 || (d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS))))
+    return set_error(FSB_ERR_INVALID, "conv_tc: custom tap tables need a stride-1 fp16 problem");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wpacked) & 15))
     return set_error(FSB_ERR_INVALID, "conv_tc: x / wpacked must be 16-byte aligned");
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
-  p.taps = g.taps;
+  p.taps = cu ? cu->ntaps : g.taps;
   p.k_chunks = g.kpad / g.bk;
-  p.Ho = d->Ho;
-  p.Wo = d->Wo;
-  p.tw = d->Wo >= 16 ? 16 : 8;
+  p.Ho = cu ? cu->Ho : d->Ho;
+  p.Wo = cu ? cu->Wo : d->Wo;
+  p.tw = p.Wo >= 16 ? 16 : 8;
   p.th = kTileM / p.tw;
-  p.tiles_w = (d->Wo + p.tw - 1) / p.tw;
-  p.tiles_h = (d->Ho + p.th - 1) / p.th;
+  p.tiles_w = (p.Wo + p.tw - 1) / p.tw;
+  p.tiles_h = (p.Ho + p.th - 1) / p.th;
+  for (int i = 0; i < 9; ++i) p.tap_widx[i] = i;
   p.Cout = d->Cout;
   // Output-channel tiling.  Default: one N tile (<= 256 columns).  When the spatial tiling alone cannot fill the
   // machine (small maps at 1/16, 1/32 resolution), split N further so that more SMs pull operands from L2 in parallel
@@ -387,11 +391,16 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   // ---- TMA-store epilogue: fp16 output whose pixels start on 16 B and whose channel count is a multiple of 8 ----
   p.tma_store = 0;
   if (!(d->flags & FSB_CONV_OUT_F32) && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      n_tile % 8 == 0 && !getenv("FSB_NO_TMA_STORE")) {
+      n_tile % 8 == 0 && (cu || !getenv("FSB_NO_TMA_STORE"))) {
     const uint64_t ycs = static_cast<uint64_t>(d->y_cstride) * 2;
-    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->Wo), static_cast<uint64_t>(d->Ho),
-                              static_cast<uint64_t>(d->N)};
-    const uint64_t str[3] = {ycs, ycs * d->Wo, ycs * d->Wo * d->Ho};
+    uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->Wo), static_cast<uint64_t>(d->Ho),
+                        static_cast<uint64_t>(d->N)};
+    uint64_t str[3] = {ycs, ycs * d->Wo, ycs * d->Wo * d->Ho};
+    if (cu) {  // output = a strided sub-lattice (parity plane) of the destination tensor
+      y = const_cast<void*>(cu->y_base);
+      for (int i = 0; i < 4; ++i) dims[i] = cu->y_dims[i];
+      for (int i = 0; i < 3; ++i) str[i] = cu->y_strides[i];
+    }
     const uint32_t box64[4] = {64u, static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), 1u};
     int rc = 0;
     if (n_tile >= 64) rc = encode_tiled(&p.tmap_y[0], y, 4, dims, str, box64, 128);
@@ -406,6 +415,7 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
     const size_t staging = static_cast<size_t>((n_tile + 63) / 64) * kTileM * 128 + 1024;
     if (smem_bytes < staging) smem_bytes = staging;
   }
+  if (cu && !p.tma_store) return set_error(FSB_ERR_UNSUPPORTED, "conv_tc: custom output lattice needs the TMA-store epilogue");
 
   // ---- A tensor maps ----
   const __half* xb = static_cast<const __half*>(x);
@@ -423,6 +433,13 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
         p.tap_map[tp] = 0;
         p.tap_dh[tp] = r * d->dil - d->pad + d->off_h;
         p.tap_dw[tp] = s * d->dil - d->pad + d->off_w;
+      }
+    if (cu)
+      for (int i = 0; i < cu->ntaps; ++i) {
+        p.tap_map[i] = 0;
+        p.tap_dh[i] = cu->dh[i];
+        p.tap_dw[i] = cu->dw[i];
+        p.tap_widx[i] = cu->widx[i];
       }
   } else {
     bool used[4] = {false, false, false, false};

@@ -61,9 +61,19 @@ inline cudaError_t last_launch_error() {
   return e;
 }
 
+// Generalised launch of the per-tap kernel: arbitrary tap subset / offsets / weight-slice indices and an output written
+// to a strided sub-lattice of the destination through the TMA-store tensor map (used by the stride-2 data gradient).
+struct ConvTcCustom {
+  int ntaps;
+  int dh[9], dw[9], widx[9];
+  int Ho, Wo;             // extent of the output lattice (tiling)
+  const void* y_base;     // address of lattice point (n=0, 0, 0, c=0)
+  uint64_t y_dims[4];     // {C, Wl, Hl, N}
+  uint64_t y_strides[3];  // bytes: lattice step in W, in H, image
+};
 int conv_tc_supported(const fsb_conv_desc* d);
 int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
-                   void* y, float* stats, cudaStream_t stream);
+                   void* y, float* stats, cudaStream_t stream, const ConvTcCustom* cu = nullptr);
 int conv_tc2_supported(const fsb_conv_desc* d);
 int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                     void* y, float* stats, cudaStream_t stream);
@@ -73,6 +83,9 @@ inline int conv_tc_dispatch(const fsb_conv_desc* d, const void* x, const void* w
   if (conv_tc2_supported(d)) return conv_tc2_launch(d, x, wpacked, scale, shift, y, stats, stream);
   return conv_tc_launch(d, x, wpacked, scale, shift, y, stats, stream);
 }
+int conv_wgrad_tc_supported(const fsb_conv_desc* d, int dy_cstride);
+int conv_wgrad_tc_launch(const fsb_conv_desc* d, const void* x, const void* dy, int dcs, float* dw, int64_t so, int64_t si,
+                         float gscale, cudaStream_t stream);
 int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                        void* y, float* stats, cudaStream_t stream);
 

@@ -349,6 +349,61 @@ int conv_dgrad_launch(const fsb_conv_desc* d, const void* dy, int dcs, const voi
     fsb_conv_desc t = dgrad_as_fwd_desc(d, dcs, xcs);
     if (conv_tc_supported(&t)) return conv_tc_dispatch(&t, dy, wpacked_t, nullptr, nullptr, dx, nullptr, stream);
   }
+  // stride 2: the input pixels of each (row, column) parity receive contributions from a fixed subset of filter taps; each
+  // parity plane is a stride-1 implicit GEMM over dy with that tap subset, written to the plane through a strided tensor map
+  if (d->stride == 2 && wpacked_t && !(d->flags & FSB_CONV_FORCE_DIRECT) && d->Cin % 8 == 0 && xcs % 8 == 0 && dcs % 8 == 0 &&
+      d->Cout >= 16 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && !getenv("FSB_DGRAD_S2_DIRECT")) {
+    fsb_conv_desc t = dgrad_as_fwd_desc(d, dcs, xcs);  // stride-1 problem over dy; geometry fields only feed the packer
+    t.pad = 0;
+    t.Ho = d->Ho;
+    t.Wo = d->Wo;
+    const int K = d->ksize;
+    bool need_zero = false;
+    ConvTcCustom planes[4];
+    bool live[4];
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        ConvTcCustom& c = planes[ph * 2 + pw];
+        memset(&c, 0, sizeof(c));
+        const int Hl = (d->H - ph + 1) / 2, Wl = (d->W - pw + 1) / 2;
+        for (int r = 0; r < K; ++r) {
+          const int th = ph - d->off_h + d->pad - r * d->dil;
+          if (th & 1) continue;
+          for (int s = 0; s < K; ++s) {
+            const int tw = pw - d->off_w + d->pad - s * d->dil;
+            if (tw & 1) continue;
+            c.dh[c.ntaps] = th / 2;  // exact: th is even (may be negative)
+            c.dw[c.ntaps] = tw / 2;
+            c.widx[c.ntaps] = (K - 1 - r) * K + (K - 1 - s);  // pack_dgrad_kernel stores the flipped filter
+            ++c.ntaps;
+          }
+        }
+        live[ph * 2 + pw] = c.ntaps > 0 && Hl > 0 && Wl > 0;
+        if (c.ntaps == 0 && Hl > 0 && Wl > 0) need_zero = true;
+        c.Ho = Hl;
+        c.Wo = Wl;
+        c.y_base = static_cast<const __half*>(dx) + (static_cast<size_t>(ph) * d->W + pw) * xcs;
+        c.y_dims[0] = d->Cin;
+        c.y_dims[1] = Wl;
+        c.y_dims[2] = Hl;
+        c.y_dims[3] = d->N;
+        c.y_strides[0] = 2ull * xcs * 2;
+        c.y_strides[1] = 2ull * d->W * xcs * 2;
+        c.y_strides[2] = static_cast<uint64_t>(d->H) * d->W * xcs * 2;
+      }
+    if (need_zero) {
+      cudaError_t e = cudaMemsetAsync(dx, 0, static_cast<size_t>(d->N) * d->H * d->W * xcs * 2, stream);
+      if (e != cudaSuccess) return set_cuda_error(e, "conv_dgrad: memset");
+    }
+    if (conv_tc_supported(&t)) {
+      for (int i = 0; i < 4; ++i) {
+        if (!live[i]) continue;
+        int rc = conv_tc_launch(&t, dy, wpacked_t, nullptr, nullptr, dx, nullptr, stream, &planes[i]);
+        if (rc) return rc;
+      }
+      return FSB_OK;
+    }
+  }
   if (!w) return set_error(FSB_ERR_INVALID, "conv_dgrad: the direct path needs the fp32 master weight");
   DgradParams p;
   p.d = *d;
@@ -473,6 +528,8 @@ int conv_wgrad_launch(const fsb_conv_desc* d, const void* x, const void* dy, int
     cudaError_t e0 = last_launch_error();
     if (e0 != cudaSuccess) return set_cuda_error(e0, "zero_wgrad launch");
   }
+  if (conv_wgrad_tc_supported(d, dcs) && !(d->flags & FSB_CONV_FORCE_DIRECT))
+    return conv_wgrad_tc_launch(d, x, dy, dcs, dw, so, si, gscale, stream);
   WgradParams p;
   p.d = *d;
   p.x = static_cast<const __half*>(x);

@@ -17,7 +17,14 @@ from ._lib import (ConvDesc, FSB_ACT_IN_F32, FSB_CONV_AFFINE, FSB_CONV_FORCE_DIR
                    FSB_CONV_STATS, check)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs ~15 us per call (device lookups, Stream
+    object construction); the raw accessor is ~50x cheaper and this is called once per kernel launch."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -278,15 +285,24 @@ def conv_dgrad(dy, w, x_shape, Cin, Cout, ksize, stride, pad, off=(0, 0), wpacke
     return dx
 
 
-def conv_wgrad(x, dy, w_like, Cin, Cout, ksize, stride, pad, gscale, off=(0, 0)):
-    """fp32 gradient with the shape/strides of the master weight `w_like` (zero outside the active corner)."""
+def conv_wgrad(x, dy, w_like, Cin, Cout, ksize, stride, pad, gscale, off=(0, 0), accumulate_into=None, force_direct=False):
+    """fp32 gradient with the shape/strides of the master weight `w_like` (zero outside the active corner).
+    accumulate_into: an existing fp32 gradient tensor (e.g. param.grad) to add into instead of allocating -- for max-width
+    slimmable weights this avoids writing a full-size zero tensor per invocation (4 GB per supernet step otherwise)."""
     N, Cx, H, W, xcs = nhwc_info(x)
     _, Cd, Ho, Wo, dcs = nhwc_info(dy)
     assert Cx == Cin and Cd == Cout
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, Cout,
+                 FSB_CONV_FORCE_DIRECT if force_direct else 0)
+    if accumulate_into is not None:
+        dw = accumulate_into
+        assert dw.dtype == torch.float32 and dw.shape == w_like.shape and dw.stride(3) == 1 and dw.stride(2) == ksize
+        check(_lib.lib().fsb_conv_wgrad(C.byref(d), _ptr(x), _ptr(dy), dcs, _ptr(dw), dw.stride(0), dw.stride(1), 1, float(gscale),
+                                        _stream()), "fsb_conv_wgrad")
+        return dw
     full = (w_like.shape[0] == Cout and w_like.shape[1] == Cin)
     dw = torch.empty_like(w_like, dtype=torch.float32, memory_format=torch.contiguous_format) if full else \
         torch.zeros_like(w_like, dtype=torch.float32, memory_format=torch.contiguous_format)
-    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, Cout, 0)
     check(_lib.lib().fsb_conv_wgrad(C.byref(d), _ptr(x), _ptr(dy), dcs, _ptr(dw), dw.stride(0), dw.stride(1), 0, float(gscale),
                                     _stream()), "fsb_conv_wgrad")
     return dw

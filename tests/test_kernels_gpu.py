@@ -279,3 +279,48 @@ def test_errors_are_loud():
     bad_out = F_.empty_nhwc(1, 32, 7, 8, "cuda")
     with pytest.raises((FsbError, AssertionError)):
         F_.conv_fwd(x, wp, 32, 3, 1, 1, out=bad_out)
+
+
+WGRAD_CASES = [
+    # N, Cin, Cout, k, stride, H, W
+    (2, 64, 64, 3, 1, 16, 24),
+    (1, 32, 128, 3, 1, 20, 36),
+    (2, 96, 48, 3, 1, 9, 13),
+    (1, 128, 64, 1, 1, 16, 32),
+    (2, 64, 128, 3, 2, 18, 30),
+    (1, 192, 320, 3, 1, 8, 16),
+    (3, 80, 160, 1, 1, 6, 10),
+    (2, 32, 64, 3, 2, 9, 13),
+    (1, 384, 384, 3, 1, 8, 16),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad_and_dgrad_match_oracle(case):
+    """K7: tensor-core weight gradient (MN-major operands) and data gradient vs CPU autograd of F.conv2d; the CUDA-core
+    kernels are checked on the same inputs."""
+    F_ = _F()
+    N, Cin, Cout, k, stride, Hh, Ww = case
+    seed = hash(case) % 100000
+    pad = 1 if k == 3 else 0
+    x = _rand((N, Cin, Hh, Ww), seed).half().float().requires_grad_(True)
+    w = (_rand((Cout, Cin, k, k), seed + 1) * (2.0 / (Cin * k * k)) ** 0.5).half().float().requires_grad_(True)
+    y = orc.conv2d(x, w, None, stride, pad)
+    gy = _rand(tuple(y.shape), seed + 2).half().float()
+    y.backward(gy)
+    xg, gyg, wg = _nhwc(x.detach()), _nhwc(gy), w.detach().cuda()
+    for direct in (False, True):
+        dw = F_.conv_wgrad(xg, gyg, wg, Cin, Cout, k, stride, pad, 1.0, force_direct=direct)
+        torch.cuda.synchronize()
+        err = H.rel_err(dw.cpu().numpy(), w.grad.numpy())
+        assert err < 1e-3, "wgrad (direct=%s) rel err %.3e" % (direct, err)
+        wt = F_.pack_conv_weight_dgrad(wg, Cin, Cout, k)
+        dx = F_.conv_dgrad(gyg, wg, (N, Cin, Hh, Ww), Cin, Cout, k, stride, pad, wpacked_t=wt, force_direct=direct)
+        torch.cuda.synchronize()
+        errx = H.rel_err(dx.float().cpu().numpy(), x.grad.numpy())
+        assert errx < 1.5e-3, "dgrad (direct=%s) rel err %.3e" % (direct, errx)
+    # accumulation into an existing gradient (a cell invoked twice, model_search.py:326-329)
+    acc = dw.clone()
+    F_.conv_wgrad(xg, gyg, wg, Cin, Cout, k, stride, pad, 1.0, accumulate_into=acc)
+    torch.cuda.synchronize()
+    assert H.rel_err(acc.cpu().numpy(), 2 * w.grad.numpy()) < 1e-3

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Secondary metric of BASELINE.json: supernet step time.
+  pretrain step (configs[2]): search/train_search.py:246-250 with C.pretrain=True -- _loss = 4 forwards (max, min, random,
+                              random) + backward + clip_grad_norm_(5) + SGD step, batch 3 x 3 x 256 x 512 per GPU
+  search step   (configs[4]): architect.step (first-order: _loss on the search batch + Adam on arch params, architect.py:42-76,
+                              latency term omitted: latency_weight[0] = 0 and the table lookups are scalar python) followed by the
+                              weight step, batch 2 x 3 x 224 x 448 per GPU
+Synthetic data per SURVEY 8(d).  Prints one JSON line."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import synth_weights_  # noqa: E402
+from fasterseg_b200.model_search import Network_Multi_Path  # noqa: E402
+
+WML = [4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.]
+
+
+def build(layers):
+    crit = nn.CrossEntropyLoss(ignore_index=255)
+    m = Network_Multi_Path(19, layers, crit, Fch=12, width_mult_list=WML, prun_modes=['max', 'arch_ratio'],
+                           stem_head_width=[(1, 1), (8. / 12, 8. / 12)])
+    synth_weights_(m)
+    with torch.no_grad():
+        for ps in m._arch_parameters:
+            for p in ps:
+                p.fill_(1e-3)
+    return m.cuda().train()
+
+
+def weight_params(m):
+    ps = []
+    for mod in (m.stem, m.cells, m.refine32, m.refine16, m.head0, m.head1, m.head2, m.head02, m.head12):
+        ps += list(mod.parameters())
+    return ps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--mode", default="pretrain", choices=["pretrain", "search"])
+    args = ap.parse_args()
+    torch.manual_seed(12345)
+    np.random.seed(12345)
+    model = build(args.layers)
+    params = weight_params(model)
+    opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=5e-4)
+    arch_opts = [torch.optim.Adam(ps, lr=3e-4, betas=(0.5, 0.999)) for ps in model._arch_parameters]
+    if args.mode == "pretrain":
+        B, H, W = 3, 256, 512
+    else:
+        B, H, W = 2, 224, 448
+    x = torch.randn(B, 3, H, W, device="cuda")
+    t = torch.randint(0, 19, (B, H // 8, W // 8), device="cuda")
+    t[torch.rand(t.shape, device="cuda") < 0.05] = 255
+
+    def step():
+        if args.mode == "search":
+            for o in arch_opts:
+                o.zero_grad()
+            loss = model._loss(x, t, "dir")          # architect._backward_step on the search batch
+            loss.backward()
+            for o in arch_opts:
+                o.step()
+        opt.zero_grad()
+        loss = model._loss(x, t, True if args.mode == "pretrain" else "dir")
+        loss.backward()
+        nn.utils.clip_grad_norm_(model.parameters(), 5)
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        loss = step()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]  # median: the step is host-bound and shares the host with other tenants
+    print(json.dumps({"metric": "supernet_%s_step_ms" % args.mode, "value": round(dt * 1e3, 1), "min_ms": round(times[0] * 1e3, 1),
+                      "max_ms": round(times[-1] * 1e3, 1), "unit": "ms/step", "layers": args.layers,
+                      "batch": [B, 3, H, W], "loss": float(loss.detach()), "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
+                      "mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
+
+
+if __name__ == "__main__":
+    main()
