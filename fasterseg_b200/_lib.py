@@ -60,6 +60,10 @@ _SIGS = {
     "fsb_wsum_fwd": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "fsb_wsum_bwd": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_float, _P]),
     "fsb_add_inplace": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "fsb_conv_bn_act_train_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, C.c_int, _P,
+                                            C.c_int, _P, C.c_int, _P]),
+    "fsb_conv_bn_act_train_bwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P,
+                                            C.c_int64, C.c_int64, _P, C.c_int, _P, _P, C.c_int, _P, C.c_float, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -68,33 +68,59 @@ def _conv_backward(ctx_conv, x, draw, ci, co, off, need_dx, need_dw):
 
 
 class ConvBnActFn(torch.autograd.Function):
-    """act(BN_train(conv(x))): conv with fused per-channel statistics -> finalize (running-stat update) -> apply."""
+    """act(BN_train(conv(x))): conv with fused per-channel statistics -> finalize (running-stat update) -> apply.
+    Single process: one fused C-ABI call per direction (csrc/train_fused.cu); with SyncBN the statistics are all-reduced
+    between the stages, so the separate entry points are used."""
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, conv, bn, relu, ci, co, off):
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         wp = engine.packed_weight(conv, ci, co)
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        ctx.conv, ctx.relu, ctx.ci, ctx.co, ctx.off = conv, relu, ci, co, off
+        if engine.dp_world_size() == 1:
+            track = bn.track_running_stats
+            y, raw, vec, d = F_.conv_bn_act_train_fwd(x, wp, co, k, s, p, off, gamma, beta, bn.eps, momentum,
+                                                      bn.running_mean if track else None, bn.running_var if track else None,
+                                                      bn.num_batches_tracked if track else None, relu)
+            ctx.fused, ctx.desc = True, d
+            ctx.save_for_backward(x, raw, y, vec, gamma)
+            return y
         stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
         raw = F_.conv_fwd(x, wp, co, k, s, p, relu=False, off=off, stats=stats, out_f32=True)
         N, _, Ho, Wo = raw.shape
         stats = engine.dp_allreduce_stats(stats)
         count = N * Ho * Wo * engine.dp_world_size()
-        momentum = bn.momentum if bn.momentum is not None else 0.1
         scale, shift, mean, invstd = F_.bn_finalize(stats, count, gamma, beta, bn.eps, momentum,
                                                     bn.running_mean if bn.track_running_stats else None,
                                                     bn.running_var if bn.track_running_stats else None, want_save=True)
         if bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         y = F_.affine_act(raw, scale, shift, relu=relu)
-        ctx.conv, ctx.relu, ctx.ci, ctx.co, ctx.off, ctx.count = conv, relu, ci, co, off, count
+        ctx.fused, ctx.count = False, count
         ctx.save_for_backward(x, raw, y, mean, invstd, gamma)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, raw, y, mean, invstd, gamma = ctx.saved_tensors
         dy = _dy(dy)
         need = ctx.needs_input_grad
+        if ctx.fused:
+            x, raw, y, vec, gamma = ctx.saved_tensors
+            conv = ctx.conv
+            dw_acc = None
+            if need[1]:
+                if not FUSED_WGRAD_ACCUMULATION:
+                    raise RuntimeError("the fused training unit accumulates weight gradients into param.grad; set "
+                                       "FSB_FUSED_WGRAD=1 or enable SyncBN mode for the unfused path")
+                if conv.weight.grad is None:
+                    conv.weight.grad = torch.zeros_like(conv.weight, memory_format=torch.contiguous_format)
+                dw_acc = conv.weight.grad
+            wt = _dgrad_pack(conv, ctx.ci, ctx.co) if need[0] else None
+            dx, dgamma, dbeta = F_.conv_bn_act_train_bwd(ctx.desc, x, dy, y, raw, vec, gamma, ctx.relu, wt, conv.weight.detach(),
+                                                         bool(need[0]), dw_acc, GRAD_SCALE)
+            return dx, None, dgamma if need[2] else None, dbeta if need[3] else None, None, None, None, None, None, None
+        x, raw, y, mean, invstd, gamma = ctx.saved_tensors
         sync = engine.dp_allreduce_stats if engine.dp_world_size() > 1 else None
         draw, dgamma, dbeta = F_.bn_bwd(dy, y, raw, mean, invstd, gamma, ctx.count, ctx.relu, GRAD_SCALE,
                                         want_param_grads=bool(need[2] or need[3]), allreduce=sync)

@@ -63,7 +63,7 @@ int copy_channels_launch(int64_t, int, const void*, int, void*, int, cudaStream_
 int bn_fold_launch(int, const float*, const float*, const float*, const float*, float, const float*, float*, float*, cudaStream_t);
 int bn_stats_launch(int64_t, int, const void*, int, int, float*, cudaStream_t);
 int bn_finalize_launch(int, const float*, double, const float*, const float*, float, float, float*, float*, float*, float*,
-                       float*, float*, cudaStream_t);
+                       float*, float*, cudaStream_t, long long* = nullptr);
 int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t);
 
 int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*, int,

@@ -135,10 +135,11 @@ int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32,
 
 __global__ void bn_finalize_kernel(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                                   float* save_mean, float* save_invstd) {
+                                   float* save_mean, float* save_invstd, long long* num_batches_tracked) {
   pdl_launch_dependents();
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (c >= C) return;
   const double mean = static_cast<double>(stats[c]) / count;
   double var = static_cast<double>(stats[C + c]) / count - mean * mean;
@@ -158,9 +159,9 @@ __global__ void bn_finalize_kernel(int C, const float* stats, double count, cons
 }
 int bn_finalize_launch(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
-                       float* save_invstd, cudaStream_t stream) {
+                       float* save_invstd, cudaStream_t stream, long long* num_batches_tracked) {
   FSB_LAUNCH(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, C, stats, count, gamma, beta, eps, momentum, running_mean,
-                                                         running_var, scale, shift, save_mean, save_invstd);
+                                                         running_var, scale, shift, save_mean, save_invstd, num_batches_tracked);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_finalize launch");
   return FSB_OK;

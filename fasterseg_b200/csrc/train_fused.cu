@@ -1,0 +1,77 @@
+// train_fused.cu -- native orchestration of one training "unit" (conv -> BatchNorm(train) -> activation) so that the host
+// pays for ONE C-ABI call per unit and direction instead of a dozen Python-level calls.  The supernet step launches
+// ~3 400 such units per forward pass set (search/model_search.py:487-500) and is host-bound otherwise.
+#include "fsb_internal.h"
+
+namespace fsb {
+
+int bn_finalize_launch(int, const float*, double, const float*, const float*, float, float, float*, float*, float*, float*,
+                       float*, float*, cudaStream_t, long long*);
+int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t);
+int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*, int,
+                         float*, cudaStream_t);
+int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
+                        const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t);
+int conv_dgrad_launch(const fsb_conv_desc*, const void*, int, const void*, const float*, int64_t, int64_t, void*, int, cudaStream_t);
+int conv_wgrad_launch(const fsb_conv_desc*, const void*, const void*, int, float*, int64_t, int64_t, int, float, cudaStream_t);
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" {
+
+/* vec: fp32[6*Cout] = [sum | sumsq | scale | shift | mean | invstd]; zeroed here, mean/invstd are what backward needs. */
+int fsb_conv_bn_act_train_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* gamma, const float* beta,
+                              float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                              void* raw_f32, int raw_cstride, void* y, int y_cstride, float* vec, int relu, void* stream) {
+  if (!d || !x || !wpacked || !raw_f32 || !y || !vec) return set_error(FSB_ERR_INVALID, "conv_bn_act_train_fwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = d->Cout;
+  cudaError_t e = cudaMemsetAsync(vec, 0, sizeof(float) * 2 * C, st);
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_bn_act_train_fwd: memset");
+  fsb_conv_desc c = *d;
+  c.y_cstride = raw_cstride;
+  c.flags = (d->flags & FSB_CONV_FORCE_DIRECT) | FSB_CONV_OUT_F32 | FSB_CONV_STATS;
+  int rc = (c.flags & FSB_CONV_FORCE_DIRECT) || !conv_tc_supported(&c) ? conv_direct_launch(&c, x, wpacked, nullptr, nullptr, raw_f32, vec, st)
+                                                                       : conv_tc_dispatch(&c, x, wpacked, nullptr, nullptr, raw_f32, vec, st);
+  if (rc) return rc;
+  const int64_t pixels = static_cast<int64_t>(d->N) * d->Ho * d->Wo;
+  rc = bn_finalize_launch(C, vec, static_cast<double>(pixels), gamma, beta, eps, momentum, running_mean, running_var, vec + 2 * C,
+                          vec + 3 * C, vec + 4 * C, vec + 5 * C, st, num_batches_tracked);
+  if (rc) return rc;
+  return affine_act_launch(pixels, C, raw_f32, raw_cstride, vec + 2 * C, vec + 3 * C, y, y_cstride,
+                           (relu ? FSB_CONV_RELU : 0u) | FSB_ACT_IN_F32, st);
+}
+
+/* Backward of the unit.  vec_fwd: the forward's vec (mean at 4C, invstd at 5C).  vec_bwd: fp32[4*Cout] = [sum dz | sum dz*xhat |
+ * dgamma | dbeta], zeroed here.  draw: scratch NHWC fp16 (Cout channels).  dx / dw may be NULL; dw is ACCUMULATED into. */
+int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void* dy, int dy_cstride, const void* y, int y_cstride,
+                              const void* raw_f32, int raw_cstride, const float* vec_fwd, const float* gamma, int relu,
+                              const void* wpacked_t, const float* w, int64_t so, int64_t si, void* draw, int draw_cstride,
+                              float* vec_bwd, void* dx, int dx_cstride, float* dw, float gscale, void* stream) {
+  if (!d || !dy || !raw_f32 || !vec_fwd || !vec_bwd || !draw) return set_error(FSB_ERR_INVALID, "conv_bn_act_train_bwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = d->Cout;
+  const int64_t pixels = static_cast<int64_t>(d->N) * d->Ho * d->Wo;
+  cudaError_t e = cudaMemsetAsync(vec_bwd, 0, sizeof(float) * 4 * C, st);
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_bn_act_train_bwd: memset");
+  int rc = bn_bwd_reduce_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, relu,
+                                vec_bwd, st);
+  if (rc) return rc;
+  rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
+                           static_cast<double>(pixels), relu, draw, draw_cstride, vec_bwd + 2 * C, vec_bwd + 3 * C, gscale, st);
+  if (rc) return rc;
+  if (dx) {
+    rc = conv_dgrad_launch(d, draw, draw_cstride, wpacked_t, w, so, si, dx, dx_cstride, st);
+    if (rc) return rc;
+  }
+  if (dw) {
+    if (!x) return set_error(FSB_ERR_INVALID, "conv_bn_act_train_bwd: wgrad needs x");
+    rc = conv_wgrad_launch(d, x, draw, draw_cstride, dw, so, si, 1, gscale, st);
+    if (rc) return rc;
+  }
+  return FSB_OK;
+}
+
+}  // extern "C"

@@ -368,3 +368,57 @@ def add_inplace(x, y):
     N, Cc, H, W, xcs = nhwc_info(x)
     check(_lib.lib().fsb_add_inplace(N * H * W, Cc, _ptr(x), xcs, _ptr(y), nhwc_info(y)[4], _stream()), "fsb_add_inplace")
     return y
+
+
+# ----------------------------------------------------------------------------------------------
+# fused training unit (one C-ABI call per direction; see csrc/train_fused.cu)
+# ----------------------------------------------------------------------------------------------
+def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta, eps, momentum, running_mean, running_var,
+                          num_batches_tracked, relu):
+    """-> (y fp16 NHWC, raw fp32 NHWC, vec fp32[6*Cout] = [sum|sumsq|scale|shift|mean|invstd], desc)"""
+    N, Cin, H, W, xcs = nhwc_info(x)
+    Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    cpad = (Cout + 7) // 8 * 8
+    dev = x.device
+    raw = torch.empty((N, Ho, Wo, cpad), device=dev, dtype=torch.float32)
+    y = torch.empty((N, Ho, Wo, cpad), device=dev, dtype=torch.float16)
+    vec = torch.empty(6 * Cout, device=dev, dtype=torch.float32)
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, cpad, 0)
+    check(_lib.lib().fsb_conv_bn_act_train_fwd(C.byref(d), x.data_ptr(), wpacked.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                               float(eps), float(momentum),
+                                               None if running_mean is None else running_mean.data_ptr(),
+                                               None if running_var is None else running_var.data_ptr(),
+                                               None if num_batches_tracked is None else num_batches_tracked.data_ptr(),
+                                               raw.data_ptr(), cpad, y.data_ptr(), cpad, vec.data_ptr(), int(relu), _stream()),
+          "fsb_conv_bn_act_train_fwd")
+    yv = y.permute(0, 3, 1, 2)
+    rv = raw.permute(0, 3, 1, 2)
+    if cpad != Cout:
+        yv, rv = yv[:, :Cout], rv[:, :Cout]
+    return yv, rv, vec, d
+
+
+def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale):
+    """-> (dx or None, dgamma, dbeta); the weight gradient is accumulated into `dw_accum` (fp32, master layout) when given."""
+    N, Cout, Ho, Wo, dcs = nhwc_info(dy)
+    dev = dy.device
+    cpad = d.y_cstride
+    draw = torch.empty((N, Ho, Wo, cpad), device=dev, dtype=torch.float16)
+    vb = torch.empty(4 * Cout, device=dev, dtype=torch.float32)
+    dx = None
+    xcs = 0
+    if need_dx:
+        cin_pad = (d.Cin + 7) // 8 * 8
+        dxb = torch.empty((N, d.H, d.W, cin_pad), device=dev, dtype=torch.float16)
+        dx = dxb.permute(0, 3, 1, 2)
+        if cin_pad != d.Cin:
+            dx = dx[:, :d.Cin]
+        xcs = cin_pad
+    check(_lib.lib().fsb_conv_bn_act_train_bwd(C.byref(d), x.data_ptr(), dy.data_ptr(), dcs, y.data_ptr(), y.stride(3), raw.data_ptr(),
+                                               raw.stride(3), vec.data_ptr(), gamma.data_ptr(), int(relu),
+                                               None if wpacked_t is None else wpacked_t.data_ptr(), w.data_ptr(), w.stride(0),
+                                               w.stride(1), draw.data_ptr(), cpad, vb.data_ptr(),
+                                               None if dx is None else dx.data_ptr(), xcs,
+                                               None if dw_accum is None else dw_accum.data_ptr(), float(gscale), _stream()),
+          "fsb_conv_bn_act_train_bwd")
+    return dx, vb[2 * Cout:3 * Cout], vb[3 * Cout:]

@@ -199,6 +199,20 @@ int fsb_wsum_fwd(int K, int64_t pixels, int C, const void* const* xs, const int*
 int fsb_wsum_bwd(int K, int64_t pixels, int C, const void* dout, int dout_cstride, const void* const* xs,
                  const int* x_cstrides, const float* wts, void* const* dxs, const int* dx_cstrides, float* dwts, float gscale,
                  void* stream);
+/* One training unit per call (host-overhead reduction; same kernels as the separate entry points):
+ * forward  = conv (fp32 raw output + fused per-channel statistics) -> fsb_bn_finalize (+ running stats, num_batches_tracked)
+ *            -> fsb_affine_act.   vec: fp32[6*Cout] = [sum | sumsq | scale | shift | mean | invstd] (zeroed by the call).
+ * backward = fsb_bn_bwd_reduce -> fsb_bn_bwd_apply -> fsb_conv_dgrad (if dx) -> fsb_conv_wgrad accumulate (if dw).
+ *            vec_bwd: fp32[4*Cout] = [sum dz | sum dz*xhat | dgamma | dbeta] (zeroed by the call); draw: fp16 NHWC scratch.
+ * Single-process only: with SyncBN the statistics need an all-reduce between the stages, use the separate entry points. */
+int fsb_conv_bn_act_train_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* gamma, const float* beta,
+                              float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                              void* raw_f32, int raw_cstride, void* y, int y_cstride, float* vec, int relu, void* stream);
+int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void* dy, int dy_cstride, const void* y, int y_cstride,
+                              const void* raw_f32, int raw_cstride, const float* vec_fwd, const float* gamma, int relu,
+                              const void* wpacked_t, const float* w, int64_t w_stride_o, int64_t w_stride_i, void* draw,
+                              int draw_cstride, float* vec_bwd, void* dx, int dx_cstride, float* dw, float gscale, void* stream);
+
 /* y (+)= x elementwise over a channel-slice view (gradient accumulation when a tensor feeds several consumers) */
 int fsb_add_inplace(int64_t pixels, int C, const void* x, int x_cstride, void* y, int y_cstride, void* stream);
 
