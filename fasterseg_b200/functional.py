@@ -244,14 +244,23 @@ def bn_bwd(dy, y, raw, mean, invstd, gamma, count, relu, gscale, want_param_grad
     sums = torch.zeros(2 * Cc, device=dy.device, dtype=torch.float32)
     check(_lib.lib().fsb_bn_bwd_reduce(pixels, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                        _ptr(invstd), int(relu), _ptr(sums), _stream()), "fsb_bn_bwd_reduce")
+    local_dg = local_db = None
     if allreduce is not None:
-        sums = allreduce(sums)
+        # SyncBN: dx needs the GLOBAL sums, but gamma/beta gradients must stay LOCAL sums -- the data-parallel gradient average
+        # (parallel.GradSync) divides every parameter gradient by the world size afterwards, like DDP + torch SyncBatchNorm
+        if want_param_grads:
+            local_db = sums[:Cc] / gscale
+            local_dg = sums[Cc:] / gscale
+        sums = allreduce(sums.clone() if want_param_grads else sums)
     draw = empty_nhwc(N, Cc, H, W, dy.device)
-    dg = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
-    db = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    fused_pg = want_param_grads and allreduce is None
+    dg = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if fused_pg else None
+    db = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if fused_pg else None
     check(_lib.lib().fsb_bn_bwd_apply(pixels, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                       _ptr(invstd), _ptr(gamma), _ptr(sums), float(count), int(relu), _ptr(draw),
                                       nhwc_info(draw)[4], _ptr(dg), _ptr(db), float(gscale), _stream()), "fsb_bn_bwd_apply")
+    if local_dg is not None:
+        dg, db = local_dg, local_db
     return draw, dg, db
 
 
