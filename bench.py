@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 METRIC = "fasterseg_student_fps_1024x2048"
 UNIT = "frames/s"
 H, W = 1024, 2048
+WORKLOAD = "FasterSeg student arch_1 (F12.L16, lasts=[2,1]) inference, 1x3x1024x2048, batch 1 per GPU"  # BASELINE configs[1]
 STUDENT_GFLOP = 55.54  # 2*MAC over the 45 convs of arch_1 @1024x2048
 
 
@@ -231,10 +232,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from fasterseg_b200 import zoo
-    model = zoo.build_network(1)
-    synth_weights_(model)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    # nothing of the product (fasterseg_b200) is on this arm: structure, weights and arithmetic all come from oracle/
+    from oracle import fasterseg_oracle as orc
+    from tests import helpers as Hh
+    st, _ = Hh.student_structure(1)
+    sd = orc.random_state_dict(orc.student_param_shapes(st, training=False), seed=12345)
     threads = best_cpu_threads(sd)
     for _ in range(max(0, min(args.warmup, 3) - 1)):
         cpu_port_fps(sd, 1, threads)
@@ -242,11 +244,30 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1000.0 / fps, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "FasterSeg student arch_1 F12.L16 inference 1x3x1024x2048 (reference CPU path, oracle port)"},
+            "config": {"workload": WORKLOAD, "arithmetic": "reference CPU path (oracle port): fp32 NCHW, torch CPU (ATen/oneDNN)"},
             "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d frames of 1x3x1024x2048, torch CPU fp32 (ATen/oneDNN), best of {all, 1/2, 32, 16} threads = %d (host has %d)" % (args.steps, threads, os.cpu_count() or 1)},
             "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def supernet_step_metric():
+    """Second half of BASELINE.json's metric: supernet pretrain step (configs[2], 3x3x256x512 per GPU, 16 layers, 252 M
+    parameters: 4 forwards + backward + clip + SGD) through the reference-facing classes.  Extra key only -- it never fails
+    the headline line.  Multi-GPU numbers for it come from `torchrun ... tools/search_step_bench.py` (profiles/)."""
+    try:
+        import importlib.util
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "search_step_bench.py")
+        spec = importlib.util.spec_from_file_location("search_step_bench", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        res = mod.measure("pretrain", 16, steps=3, warmup=2)
+        res["timing"] = "host wall clock around step + synchronize, median of 3 (the step is host-launch-bound: ~20 k launches)"
+        return res
+    except Exception as e:  # noqa: BLE001 -- secondary metric, reported not raised
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    finally:
+        torch.cuda.empty_cache()
 
 
 def main():
@@ -256,6 +277,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-supernet-step", action="store_true",
+                    help="skip the secondary metric (supernet pretrain-step ms, BASELINE configs[2]) reported at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 30:
@@ -343,8 +366,8 @@ def main():
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16", "data": "synthetic",
-        "config": {"workload": "FasterSeg student arch_1 (F12.L16, lasts=[2,1]) inference, 1x3x1024x2048, batch 1 per GPU, "
-                               "fp16 storage / fp32 accumulate, full-res fp16 logits materialised",
+        "config": {"workload": WORKLOAD,
+                   "arithmetic": "fp16 NHWC storage / fp32 accumulate, full-res fp16 logits materialised",
                    "parallelism": "replicas x%d (no exchange step in inference)" % world,
                    "l2_policy": "inputs rotate through a 6-frame device pool (151 MB > 126 MB L2); activations per frame "
                                 "(~430 MB) exceed L2",
@@ -359,6 +382,8 @@ def main():
         "roofline": roof,
         "frame_tflops": round(STUDENT_GFLOP * value / world / 1000.0, 2),
     }
+    if world == 1 and not args.no_supernet_step:
+        line["supernet_step"] = supernet_step_metric()
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
         threads = best_cpu_threads(sd)

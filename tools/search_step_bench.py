@@ -5,7 +5,9 @@
   search step   (configs[4]): architect.step (first-order: _loss on the search batch + Adam on arch params, architect.py:42-76,
                               latency term omitted: latency_weight[0] = 0 and the table lookups are scalar python) followed by the
                               weight step, batch 2 x 3 x 224 x 448 per GPU
-Synthetic data per SURVEY 8(d).  Prints one JSON line."""
+Synthetic data per SURVEY 8(d).  Prints one JSON line.
+Data parallel: launch with torchrun (--nproc-per-node N): per-rank shard of the same per-GPU batch (weak scaling), SyncBN
+statistics + end-of-backward gradient all-reduce (fasterseg_b200/parallel.py); the time is the max over ranks."""
 import argparse
 import json
 import os
@@ -18,6 +20,7 @@ import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import synth_weights_  # noqa: E402
+from fasterseg_b200 import parallel  # noqa: E402
 from fasterseg_b200.model_search import Network_Multi_Path  # noqa: E402
 
 WML = [4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.]
@@ -42,15 +45,10 @@ def weight_params(m):
     return ps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--layers", type=int, default=16)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--mode", default="pretrain", choices=["pretrain", "search"])
-    args = ap.parse_args()
-    torch.manual_seed(12345)
-    np.random.seed(12345)
+def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1):
+    """Time `steps` optimizer steps; returns the result dict (identical on every rank)."""
+    args = argparse.Namespace(mode=mode, layers=layers, steps=steps, warmup=warmup)
+    parallel.seed_all_ranks_identically(12345)   # identical weights + lock-step width sampling / gumbel noise on every rank
     model = build(args.layers)
     params = weight_params(model)
     opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=5e-4)
@@ -59,9 +57,12 @@ def main():
         B, H, W = 3, 256, 512
     else:
         B, H, W = 2, 224, 448
-    x = torch.randn(B, 3, H, W, device="cuda")
-    t = torch.randint(0, 19, (B, H // 8, W // 8), device="cuda")
-    t[torch.rand(t.shape, device="cuda") < 0.05] = 255
+    g = torch.Generator().manual_seed(977 + rank)  # private per-rank data stream (different shard on every rank)
+    x = torch.randn(B, 3, H, W, generator=g).cuda()
+    t = torch.randint(0, 19, (B, H // 8, W // 8), generator=g)
+    t[torch.rand(t.shape, generator=g) < 0.05] = 255
+    t = t.cuda()
+    sync = parallel.GradSync(list(model.parameters())).install() if world > 1 else None
 
     def step():
         if args.mode == "search":
@@ -88,11 +89,35 @@ def main():
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     times.sort()
-    dt = times[len(times) // 2]  # median: the step is host-bound and shares the host with other tenants
-    print(json.dumps({"metric": "supernet_%s_step_ms" % args.mode, "value": round(dt * 1e3, 1), "min_ms": round(times[0] * 1e3, 1),
-                      "max_ms": round(times[-1] * 1e3, 1), "unit": "ms/step", "layers": args.layers,
-                      "batch": [B, 3, H, W], "loss": float(loss.detach()), "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
-                      "mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
+    stat = torch.tensor([times[len(times) // 2], times[0], times[-1]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(stat, op=torch.distributed.ReduceOp.MAX)   # a step ends when the slowest rank ends
+    dt, tmin, tmax = (float(v) for v in stat)  # median: the step is host-bound and shares the host with other tenants
+    if sync:
+        sync.uninstall()
+    return {"metric": "supernet_%s_step_ms" % args.mode, "value": round(dt * 1e3, 1), "min_ms": round(tmin * 1e3, 1),
+            "max_ms": round(tmax * 1e3, 1), "unit": "ms/step", "n_gpus": world, "layers": args.layers, "steps": args.steps,
+            "warmup": args.warmup, "batch_per_gpu": [B, 3, H, W], "images_per_s": round(B * world / dt, 2),
+            "grad_syncs": sync.syncs if sync else 0, "loss": float(loss.detach()),
+            "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
+            "mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--mode", default="pretrain", choices=["pretrain", "search"])
+    args = ap.parse_args()
+    rank, local_rank, world = parallel.init_from_env()
+    torch.cuda.set_device(local_rank)
+    res = measure(args.mode, args.layers, args.steps, args.warmup, rank, world)
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
