@@ -1,0 +1,332 @@
+"""TEST INFRASTRUCTURE ONLY -- a torch-CPU stand-in for the tensor-level wrappers of `fasterseg_b200.functional`.
+
+The product has no CPU path (`_lib.lib()` raises without the CUDA library).  To test the HOST LOGIC of the boundary on the
+build machine -- which operator calls which unit with which channel slice, the zero-copy concat offsets, the autograd wiring of
+the training units, gradient accumulation into `param.grad`, the branch / cell / MixedOp plumbing of both networks -- the
+`-m "not gpu"` tests swap the ~35 wrappers for the functions below (same signatures, same tensor conventions: logical NCHW
+fp16 views with channels-last strides, fp32 master weights, fp16 gradients carrying GRAD_SCALE) and run the real
+`fasterseg_b200` modules on CPU tensors against the oracle.  Arithmetic is fp32 with results rounded where the kernels store
+fp16, i.e. the storage semantics documented in include/fsb200.h.  Nothing here is imported by the package.
+"""
+import contextlib
+import types
+
+import torch
+import torch.nn.functional as TF
+
+from fasterseg_b200 import functional as F_
+from fasterseg_b200._lib import ConvDesc
+
+_empty = F_.empty_nhwc  # pure torch, device-agnostic: reused as is
+
+
+def nhwc_info(t, dtype=torch.float16):
+    if t.dtype != dtype or t.dim() != 4:
+        raise ValueError("expected a 4-D %s tensor, got %s %s" % (dtype, t.dtype, tuple(t.shape)))
+    N, Cc, H, W = t.shape
+    sn, sc, sh, sw = t.stride()
+    cs = sw
+    ok = (Cc == 1 or sc == 1) and cs >= Cc and (H == 1 or sh == W * cs) and (N == 1 or sn == H * W * cs)
+    if W == 1:
+        cs = sh if H > 1 else (sn if N > 1 else max(Cc, 1))
+        ok = (Cc == 1 or sc == 1)
+    if not ok:
+        raise ValueError("tensor is not NHWC-addressable: shape %s strides %s" % (tuple(t.shape), t.stride()))
+    return N, Cc, H, W, cs
+
+
+def _put(out, val):
+    """store `val` (fp32, logical NCHW) into the view `out`, rounding to its dtype"""
+    out.copy_(val.to(out.dtype))
+    return out
+
+
+def to_nhwc_half(x):
+    if F_.is_nhwc_half(x):
+        return x
+    if x.dim() != 4 or x.dtype not in (torch.float32, torch.float16):
+        raise ValueError("expected an NCHW fp32/fp16 tensor")
+    N, Cc, H, W = x.shape
+    return _put(_empty(N, Cc, H, W, x.device), x.detach().float())
+
+
+def to_nchw(x, dtype=torch.float32):
+    nhwc_info(x)
+    return x.detach().to(dtype).contiguous()
+
+
+def pack_conv_weight(w, Cin, Cout, ksize):
+    assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] == ksize and w.shape[3] == ksize
+    return w[:Cout, :Cin].detach().half().contiguous()
+
+
+def bn_fold(gamma, beta, mean, var, eps, conv_bias=None):
+    g = torch.ones_like(mean) if gamma is None else gamma.float()
+    b = torch.zeros_like(mean) if beta is None else beta.float()
+    scale = g / torch.sqrt(var.float() + eps)
+    shift = b - mean.float() * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _raw_conv(x, w16, stride, pad, off):
+    xin = x[:, :, off[0]:, off[1]:].float()
+    return TF.conv2d(xin, w16.float(), None, stride, pad)
+
+
+def _add_stats(stats, y, Cout):
+    stats[:Cout] += y.sum((0, 2, 3))
+    stats[Cout:2 * Cout] += (y * y).sum((0, 2, 3))
+
+
+def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=False, out=None, off=(0, 0),
+             stats=None, force_direct=False, out_f32=False):
+    N, Cin, H, W, _ = nhwc_info(x)
+    assert tuple(wpacked.shape) == (Cout, Cin, ksize, ksize), (tuple(wpacked.shape), (Cout, Cin, ksize, ksize))
+    y = _raw_conv(x, wpacked, stride, pad, off)
+    Ho, Wo = F_.conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    assert tuple(y.shape) == (N, Cout, Ho, Wo)
+    if stats is not None:
+        _add_stats(stats, y, Cout)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.view(1, -1, 1, 1)
+    if relu:
+        y = y.relu()
+    odt = torch.float32 if out_f32 else torch.float16
+    if out is None:
+        out = _empty(N, Cout, Ho, Wo, x.device, dtype=odt)
+    assert tuple(out.shape) == (N, Cout, Ho, Wo) and out.dtype == odt
+    nhwc_info(out, odt)
+    return _put(out, y)
+
+
+def stem_conv_nchw(x, w, scale, shift, relu=True, out=None):
+    assert x.dim() == 4 and x.shape[1] == 3 and tuple(w.shape[1:]) == (3, 3, 3)
+    y = TF.conv2d(x.half().float(), w.half().float(), None, 2, 1)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if relu:
+        y = y.relu()
+    if out is None:
+        out = _empty(y.shape[0], y.shape[1], y.shape[2], y.shape[3], x.device)
+    return _put(out, y)
+
+
+def _interp(x32, size):
+    return TF.interpolate(x32, size=(int(size[0]), int(size[1])), mode="bilinear", align_corners=True)
+
+
+def bilinear(x, size, relu=False, out=None):
+    N, Cc, _, _, _ = nhwc_info(x)
+    y = _interp(x.float(), size)
+    if relu:
+        y = y.relu()
+    if out is None:
+        out = _empty(N, Cc, int(size[0]), int(size[1]), x.device)
+    assert tuple(out.shape) == tuple(y.shape)
+    return _put(out, y)
+
+
+def upsample_logits(x, size, dtype=torch.float32, out=None):
+    nhwc_info(x)
+    y = _interp(x.float(), size).to(dtype).contiguous()
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def upsample_argmax(x, size, out=None):
+    nhwc_info(x)
+    lab = _interp(x.float(), size).argmax(1).to(torch.uint8)
+    if out is not None:
+        out.copy_(lab)
+        return out
+    return lab
+
+
+def copy_channels(x, out):
+    assert tuple(x.shape) == tuple(out.shape)
+    nhwc_info(x), nhwc_info(out)
+    out.copy_(x)
+    return out
+
+
+def bn_stats(x, stats=None):
+    N, Cc, H, W, _ = nhwc_info(x)
+    if stats is None:
+        stats = torch.zeros(2 * Cc, dtype=torch.float32)
+    _add_stats(stats, x.float(), Cc)
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, want_save=False):
+    Cc = stats.numel() // 2
+    mean = stats[:Cc].double() / count
+    var = (stats[Cc:].double() / count - mean * mean).clamp_min(0)
+    invstd = 1.0 / torch.sqrt(var + eps)
+    scale = gamma.detach().double() * invstd
+    shift = beta.detach().double() - mean * scale
+    if running_mean is not None:
+        with torch.no_grad():
+            running_mean.mul_(1 - momentum).add_(momentum * mean.float())
+            unbiased = var * (count / max(count - 1, 1))
+            running_var.mul_(1 - momentum).add_(momentum * unbiased.float())
+    return scale.float(), shift.float(), mean.float(), invstd.float()
+
+
+def affine_act(x, scale, shift, relu=False, out=None):
+    N, Cc, H, W, _ = nhwc_info(x, x.dtype)
+    y = x.float() * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if relu:
+        y = y.relu()
+    if out is None:
+        out = _empty(N, Cc, H, W, x.device)
+    return _put(out, y)
+
+
+def bn_bwd(dy, y, raw, mean, invstd, gamma, count, relu, gscale, want_param_grads=True, allreduce=None):
+    N, Cc, H, W, _ = nhwc_info(dy)
+    dz = dy.float()
+    if relu:
+        dz = dz * (y.float() > 0)
+    v = lambda t: t.detach().float().view(1, -1, 1, 1)
+    xhat = (raw.float() - v(mean)) * v(invstd)
+    sums = torch.cat([dz.sum((0, 2, 3)), (dz * xhat).sum((0, 2, 3))])
+    local = sums.clone()
+    if allreduce is not None:
+        sums = allreduce(sums)
+    draw = v(gamma) * v(invstd) * (dz - v(sums[:Cc]) / count - xhat * v(sums[Cc:]) / count)
+    out = _put(_empty(N, Cc, H, W, dy.device), draw)
+    if not want_param_grads:
+        return out, None, None
+    return out, local[Cc:] / gscale, local[:Cc] / gscale
+
+
+def relu_bwd(dy, y):
+    N, Cc, H, W, _ = nhwc_info(dy)
+    return _put(_empty(N, Cc, H, W, dy.device), dy.float() * (y.float() > 0))
+
+
+def pack_conv_weight_dgrad(w, Cin, Cout, ksize):
+    return w[:Cout, :Cin].detach().half().contiguous()
+
+
+def conv_dgrad(dy, w, x_shape, Cin, Cout, ksize, stride, pad, off=(0, 0), wpacked_t=None, force_direct=False):
+    N, _, H, W = x_shape
+    nhwc_info(dy)
+    w16 = w[:Cout, :Cin].detach().half().float()
+    eff = (N, Cin, H - off[0], W - off[1])
+    g = torch.nn.grad.conv2d_input(eff, w16, dy.float(), stride=stride, padding=pad)
+    full = torch.zeros((N, Cin, H, W), dtype=torch.float32)
+    full[:, :, off[0]:, off[1]:] = g
+    return _put(_empty(N, Cin, H, W, dy.device), full)
+
+
+def conv_wgrad(x, dy, w_like, Cin, Cout, ksize, stride, pad, gscale, off=(0, 0), accumulate_into=None, force_direct=False):
+    xin = x[:, :, off[0]:, off[1]:].float()
+    g = torch.nn.grad.conv2d_weight(xin, (Cout, Cin, ksize, ksize), dy.float(), stride=stride, padding=pad) / gscale
+    if accumulate_into is not None:
+        assert accumulate_into.dtype == torch.float32 and accumulate_into.shape == w_like.shape
+        with torch.no_grad():
+            accumulate_into[:Cout, :Cin] += g
+        return accumulate_into
+    dw = torch.zeros(w_like.shape, dtype=torch.float32)
+    dw[:Cout, :Cin] = g
+    return dw
+
+
+def _interp_bwd(g32, in_hw):
+    x0 = torch.zeros((g32.shape[0], g32.shape[1], in_hw[0], in_hw[1]), dtype=torch.float32, requires_grad=True)
+    with torch.enable_grad():
+        y0 = _interp(x0, g32.shape[2:])
+    return torch.autograd.grad(y0, x0, g32)[0]
+
+
+def bilinear_bwd(dy, in_hw, relu_mask_y=None):
+    N, Cc, _, _, _ = nhwc_info(dy)
+    g = dy.float()
+    if relu_mask_y is not None:
+        g = g * (relu_mask_y.float() > 0)
+    return _put(_empty(N, Cc, in_hw[0], in_hw[1], dy.device), _interp_bwd(g, in_hw))
+
+
+def upsample_logits_bwd(dy_nchw, in_hw, gscale):
+    N, Cc = dy_nchw.shape[:2]
+    return _put(_empty(N, Cc, in_hw[0], in_hw[1], dy_nchw.device), _interp_bwd(dy_nchw.float() * gscale, in_hw))
+
+
+def nchw_grad_to_nhwc(dy_nchw, gscale):
+    N, Cc, H, W = dy_nchw.shape
+    return _put(_empty(N, Cc, H, W, dy_nchw.device), dy_nchw.float() * gscale)
+
+
+def wsum_fwd(xs, wts, out=None):
+    N, Cc, H, W, _ = nhwc_info(xs[0])
+    acc = sum(float(wts[k]) * xs[k].float() for k in range(len(xs)))
+    if out is None:
+        out = _empty(N, Cc, H, W, xs[0].device)
+    return _put(out, acc)
+
+
+def wsum_bwd(dout, xs, wts, need_dx, need_dw, gscale):
+    N, Cc, H, W, _ = nhwc_info(dout)
+    g = dout.float()
+    dxs = [_put(_empty(N, Cc, H, W, dout.device), float(wts[k]) * g) if need_dx[k] else None for k in range(len(xs))]
+    dw = torch.stack([(g * xs[k].float()).sum() / gscale for k in range(len(xs))]).float() if need_dw else None
+    return dxs, dw
+
+
+def add_inplace(x, y):
+    y.copy_((y.float() + x.float()).to(y.dtype))
+    return y
+
+
+def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta, eps, momentum, running_mean, running_var,
+                          num_batches_tracked, relu):
+    N, Cin, H, W, xcs = nhwc_info(x)
+    Ho, Wo = F_.conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    stats = torch.zeros(2 * Cout, dtype=torch.float32)
+    raw = conv_fwd(x, wpacked, Cout, ksize, stride, pad, off=off, stats=stats, out_f32=True)
+    scale, shift, mean, invstd = bn_finalize(stats, N * Ho * Wo, gamma, beta, eps, momentum, running_mean, running_var, True)
+    if num_batches_tracked is not None:
+        num_batches_tracked += 1
+    y = affine_act(raw, scale, shift, relu=relu)
+    vec = torch.cat([stats, scale, shift, mean, invstd])
+    cpad = (Cout + 7) // 8 * 8
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, cpad, 0)
+    return y, raw, vec, d
+
+
+def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale):
+    N, Cout, Ho, Wo, _ = nhwc_info(dy)
+    mean, invstd = vec[4 * Cout:5 * Cout], vec[5 * Cout:6 * Cout]
+    draw, dg, db = bn_bwd(dy, y, raw, mean, invstd, gamma, N * Ho * Wo, relu, gscale)
+    off = (d.off_h, d.off_w)
+    dx = conv_dgrad(draw, w, (N, d.Cin, d.H, d.W), d.Cin, Cout, d.ksize, d.stride, d.pad, off=off) if need_dx else None
+    if dw_accum is not None:
+        conv_wgrad(x, draw, w, d.Cin, Cout, d.ksize, d.stride, d.pad, gscale, off=off, accumulate_into=dw_accum)
+    return dx, dg, db
+
+
+_PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold", "conv_fwd", "stem_conv_nchw", "bilinear",
+            "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd", "relu_bwd",
+            "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
+            "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd")
+
+
+@contextlib.contextmanager
+def installed():
+    """Swap the wrappers of fasterseg_b200.functional for the CPU stand-ins for the duration of the block."""
+    saved = {name: getattr(F_, name) for name in _PATCHED}
+    here = globals()
+    try:
+        for name in _PATCHED:
+            setattr(F_, name, here[name])
+        yield types.SimpleNamespace(names=_PATCHED)
+    finally:
+        for name, fn in saved.items():
+            setattr(F_, name, fn)

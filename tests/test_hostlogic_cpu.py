@@ -1,0 +1,206 @@
+"""Host logic of the boundary on the build machine: the REAL `fasterseg_b200` operator classes, networks and autograd
+functions run on CPU tensors with the tensor-level wrappers of `fasterseg_b200.functional` swapped for the torch stand-ins of
+tests/cpu_backend.py (test infrastructure; the product itself has no CPU path), and are compared with the same reference
+goldens / oracle the GPU parity tests use.  What this pins without a GPU: which unit every operator calls and with which
+channel slices (zero-copy concat offsets, FactorizedReduce's shifted second conv), the branch / cell sharing and the
+arm-refine-fusion wiring of the derived network, MixedOp / beta aggregation and width sampling of the supernet, the autograd
+graph of the training units (including accumulation of weight gradients straight into `param.grad` and the set of parameters
+that must stay grad-less), running-statistic updates, and GRAD_SCALE bookkeeping."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import fasterseg_oracle as orc
+from oracle import supernet_oracle as sno
+from tests import cpu_backend
+from tests import helpers as H
+from tests.test_boundary_cpu import _build_student, _build_supernet
+from tests.test_supernet_oracle import CASE, FWD, META, cfg, inputs, make_sd
+
+
+@pytest.fixture(autouse=True)
+def _cpu_backend():
+    with cpu_backend.installed():
+        yield
+
+
+def _load_seeded(model, g, seed, key="state_dict_shapes"):
+    full = {k: tuple(v) for k, v in g[key].items() if not k.endswith("num_batches_tracked")}
+    sd = orc.random_state_dict(full, seed=seed)
+    own = model.state_dict()
+    seen = set()
+    for k in sorted(sd):  # shared cells: first key wins (same rule as oracle/make_golden.py)
+        if own[k].data_ptr() in seen:
+            continue
+        seen.add(own[k].data_ptr())
+        own[k].copy_(sd[k])
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.eps, m.momentum = orc.BN_EPS, orc.BN_MOMENTUM
+    return sd
+
+
+@pytest.mark.parametrize("arch_idx,hw", [(1, (64, 128)), (0, (64, 128)), (1, (96, 160))])
+def test_student_eval_wiring_vs_reference_golden(arch_idx, hw):
+    z = H.load_npz("student.npz")
+    model, g = _build_student(arch_idx)
+    model = model.eval()
+    _load_seeded(model, g, 2024 + arch_idx)
+    x = orc.random_input((1, 3) + hw, seed=99 + arch_idx)
+    with torch.no_grad():
+        y = model(x)
+        lab = model.predict_labels(x)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (1, 19) + hw and y.is_contiguous()
+    tag = "arch%d.%dx%d.eval" % (arch_idx, hw[0], hw[1])
+    yn = y.numpy()
+    ref = z[tag + "/logits.s4"]
+    nerr = H.rel_err(yn[:, :, ::4, ::4], ref)
+    print(tag, "norm-wise rel err vs the reference (fp16-storage emulation on CPU): %.3e" % nerr)
+    assert nerr < 3e-3
+    assert (lab.numpy() == z[tag + "/argmax"]).mean() > 0.995
+    assert np.array_equal(lab.numpy(), yn.argmax(1).astype(np.uint8))
+
+
+def test_student_train_forward_and_running_stats_vs_reference_golden():
+    z = H.load_npz("student.npz")
+    model, g = _build_student(1, training=True)
+    model = model.train()
+    _load_seeded(model, g, 2025, key="state_dict_shapes_train")
+    x = orc.random_input((2, 3, 192, 384), seed=100)
+    with torch.no_grad():
+        preds = model(x)
+    tag = "arch1.192x384.train"
+    for name, o in zip(("pred8", "pred16", "pred32"), preds):
+        nerr = H.rel_err(o.float().numpy()[:, :, ::4, ::4], z[tag + "/" + name + ".s4"])
+        print(tag, name, "%.3e" % nerr)
+        assert nerr < 6e-2, name  # ill-conditioned train-mode chain, see tests/test_student_gpu.py
+    sd = model.state_dict()
+    for k in ("stem.0.conv.1.running_mean", "stem.0.conv.1.running_var", "heads8.conv_3x3.bn.running_var"):
+        np.testing.assert_allclose(sd[k].numpy(), z[tag + "/after:" + k], rtol=3e-3, atol=3e-4)
+    assert int(sd["stem.0.conv.1.num_batches_tracked"]) == 1
+
+
+def test_student_train_step_autograd_wiring_vs_oracle():
+    """forward + backward of the train-mode student through the real autograd Functions; gradients against CPU autograd
+    through the fp16-storage-emulating oracle (same storage semantics -> tight) and the set of grad-less parameters."""
+    model, g = _build_student(1, training=True)
+    model = model.train()
+    sd = _load_seeded(model, g, 31, key="state_dict_shapes_train")
+    st, _ = H.student_structure(1)
+    x = orc.random_input((2, 3, 96, 192), seed=32)
+    tgt = [orc.random_input((2, 19, 96, 192), seed=33 + i) for i in range(3)]
+
+    def run_oracle(emulate):
+        orc.EMULATE_FP16["on"] = emulate
+        try:
+            sd_ref = {k: v.clone().requires_grad_(not ("running" in k)) for k, v in sd.items()}
+            outs = orc.student_forward(x, sd_ref, st, training=True)
+            sum((o * t).mean() for o, t in zip(outs, tgt)).backward()
+        finally:
+            orc.EMULATE_FP16["on"] = False
+        return {k: v.grad.numpy() for k, v in sd_ref.items() if v.grad is not None}
+
+    g32, g16 = run_oracle(False), run_oracle(True)
+    outs = model(x)
+    sum((o * t).mean() for o, t in zip(outs, tgt)).backward()
+    e_ours, e_emu = [], []
+    for k, p in model.named_parameters():
+        if k not in g32 or np.linalg.norm(g32[k]) < 1e-12:
+            continue
+        assert p.grad is not None and p.grad.dtype == torch.float32 and p.grad.shape == p.shape, k
+        e_ours.append(H.rel_err(p.grad.numpy(), g32[k]))
+        e_emu.append(H.rel_err(g16[k], g32[k]))
+    med_ours, med_emu = float(np.median(e_ours)), float(np.median(e_emu))
+    print("checked %d gradients: median err vs fp32 oracle ours %.3e | fp16-emulating oracle %.3e" % (len(e_ours), med_ours, med_emu))
+    assert len(e_ours) > 100
+    assert med_ours <= 1.5 * med_emu + 1e-2
+    assert max(e_ours) <= 4.0 * max(max(e_emu), med_emu) + 5e-2
+    no_grad_ours = {k for k, p in model.named_parameters() if p.grad is None}
+    no_grad_ref = {k for k in dict(model.named_parameters()) if k not in g32}
+    assert no_grad_ours == no_grad_ref, sorted(no_grad_ours ^ no_grad_ref)
+
+
+@pytest.mark.parametrize("tag,arch_idx,mode,train,np_seed,torch_seed", FWD)
+def test_supernet_forward_wiring_vs_reference_golden(tag, arch_idx, mode, train, np_seed, torch_seed):
+    z = H.load_npz("supernet.npz")
+    model = _build_supernet(CASE["layers"])
+    own = model.state_dict()
+    for k, v in make_sd().items():
+        own[k].copy_(v)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.eps, m.momentum = orc.BN_EPS, orc.BN_MOMENTUM
+    model.train(train)
+    x, _ = inputs()
+    if np_seed is not None:
+        np.random.seed(np_seed)
+    if torch_seed is not None:
+        torch.manual_seed(torch_seed)
+    model.arch_idx, model.prun_mode = arch_idx, mode
+    with torch.no_grad():
+        preds = model(x)
+    worst = 0.0
+    for i, p in enumerate(preds):
+        assert p.dtype == torch.float32 and p.is_contiguous()
+        ref = z["%s/pred%d" % (tag, i)]
+        got = p.numpy() if train else p.numpy()[:, :, ::8, ::8]
+        worst = max(worst, H.rel_err(got, ref))
+    print("%s: worst norm-wise rel err over the 5 logits %.3e" % (tag, worst))
+    assert worst < (5e-3 if not train else 5e-2)
+    if train:
+        sd = model.state_dict()
+        for k in z.files:
+            if k.startswith(tag + "/after:"):
+                np.testing.assert_allclose(sd[k.split("after:")[1]].numpy(), z[k], rtol=2e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("tag,pretrain,np_seed,torch_seed", [("loss.pretrain", True, 11, 12), ("loss.search", "some-dir", 13, 14)])
+def test_supernet_loss_backward_wiring(tag, pretrain, np_seed, torch_seed):
+    """`_loss` (4 forwards) + backward through WsumFn / ConvBnActFn / FactorizedReduceFn / CatFn / ToNCHWFn on CPU: the loss,
+    the set of parameters that receive no gradient, and the gradients against the fp32 oracle within the fp16-storage band."""
+    x, tgt = inputs()
+    crit = nn.CrossEntropyLoss(ignore_index=255)
+
+    def run_oracle(emulate):
+        sd = make_sd(requires_grad=True)
+        np.random.seed(np_seed)
+        torch.manual_seed(torch_seed)
+        orc.EMULATE_FP16["on"] = emulate
+        try:
+            loss = sno.supernet_loss(x, tgt, sd, cfg(), crit, pretrain)
+            loss.backward()
+        finally:
+            orc.EMULATE_FP16["on"] = False
+        return float(loss.detach()), {k: v.grad.numpy() for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+    l32, g32 = run_oracle(False)
+    l16, g16 = run_oracle(True)
+    model = _build_supernet(CASE["layers"])
+    own = model.state_dict()
+    for k, v in make_sd().items():
+        own[k].copy_(v)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.eps, m.momentum = orc.BN_EPS, orc.BN_MOMENTUM
+    model.train(True)
+    np.random.seed(np_seed)
+    torch.manual_seed(torch_seed)
+    loss = model._loss(x, tgt, pretrain)
+    loss.backward()
+    lo = float(loss.detach())
+    print("%s: loss ours(CPU stand-in) %.5f | fp32 oracle %.5f | fp16-emulating oracle %.5f" % (tag, lo, l32, l16))
+    assert abs(lo - l32) <= 1.5 * abs(l16 - l32) + 2e-3 * abs(l32)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert sorted(k for k, g in grads.items() if g is None) == sorted(k for k in grads if k not in g32)
+    assert len([k for k, g in grads.items() if g is None]) == META[tag + ".no_grad_count"]
+    e_ours, e_emu = [], []
+    for k, g in grads.items():
+        if g is None or np.linalg.norm(g32[k]) < 1e-10 or k.startswith("ratio_"):
+            continue  # ratio_*: pure cancellation noise, see tests/test_supernet_gpu.py
+        e_ours.append(H.rel_err(g.float().numpy(), g32[k]))
+        e_emu.append(H.rel_err(g16[k], g32[k]))
+    med_ours, med_emu = float(np.median(e_ours)), float(np.median(e_emu))
+    print("%s: %d gradients, median err vs fp32 oracle ours %.3e | emulation %.3e" % (tag, len(e_ours), med_ours, med_emu))
+    assert len(e_ours) > 300
+    assert med_ours <= 1.5 * med_emu + 1e-2
