@@ -1,20 +1,28 @@
-"""Derived (teacher / student) network + genotype decoder -- drop-in for the reference's train/model_seg.py.
+"""Derived (teacher / student) network -- drop-in for the reference's train/model_seg.py.
 
-Kept from the reference (train/model_seg.py:12-408): the decoder functions and their exact (mutating) semantics,
-`MixedOp` / `Cell` / `Network_Multi_Path_Infer` with the same constructor arguments, `build_structure`,
-`num_filters`, `forward`, `forward_latency`, attribute names (`ops0.. path2.. branch_groups, cells, ch_16 ...`)
-and every parameter name (`stem.0.conv.0.weight`, `cells.3-1._op._op.conv1.weight`, `arms32.0...`, `ffm...`, `heads8...`).
+Same public surface as the reference (train/model_seg.py:138-408): `MixedOp` / `Cell` / `Network_Multi_Path_Infer` with the
+same constructor arguments, `build_structure`, `num_filters`, `forward`, `forward_latency`, attribute names (`ops0.. path2..
+branch_groups, cells, ch_16 ...`) and every parameter name (`stem.0.conv.0.weight`, `cells.3-1._op._op.conv1.weight`,
+`arms32.0...`, `ffm...`, `heads8...`); the decoder functions it exports live in `decode.py`.
 
-B200-side differences: NHWC fp16 activations, each conv+BN+ReLU one fused tcgen05 kernel, torch.cat call sites
-(:307,312,319,331) replaced by producers writing into channel slices of one buffer, final x8 upsample as one
-kernel writing NCHW logits (or, via `predict_labels`, a fused upsample+argmax that never materialises them).
+Organisation (ours): `build_structure` compiles the decoded branches into a flat *schedule* -- one `_CellStep` per distinct
+cell in execution order (which branches share it, where a stream fork happens) plus one `_Tail` per branch (its
+arm / refine chain towards the 1/8 feature) -- and `forward`, `predict_labels` and `forward_latency` are interpreters of
+that schedule.  B200 side: NHWC fp16 activations, each conv+BN+ReLU one fused tcgen05 kernel, the torch.cat call sites
+(:307,312,319,331) replaced by producers writing into channel slices of one buffer, independent branches on their own CUDA
+streams inside one CUDA graph, the final x8 upsample as one kernel writing NCHW logits (or, via `predict_labels`, a fused
+upsample+argmax that never materialises them).
 """
+from collections import OrderedDict, namedtuple
+
 import numpy as np
 import torch
 import torch.nn as nn
-from torch.nn import functional as F
 
+from . import decode
 from . import functional as F_
+from .decode import (alphas2ops_path_width, betas2path, downs2path, network_metas, path2downs, path2widths,  # noqa: F401
+                     softmax)
 from .genotypes import PRIMITIVES
 from .operations import *  # noqa: F401,F403  (the reference does `from operations import *`)
 from .operations import OPS, BasicResidual2x, ConvNorm
@@ -22,124 +30,11 @@ from .seg_oprs import FeatureFusion, Head
 
 BatchNorm2d = nn.BatchNorm2d
 
-
-# ------------------------------------------------------------------------------------------------------------
-# genotype decoder: pure python/numpy, runs once at construction (reference: train/model_seg.py:12-135)
-# ------------------------------------------------------------------------------------------------------------
-def softmax(x):
-    return np.exp(x) / (np.exp(x).sum() + np.spacing(1))
+SCALES = (8, 16, 32)                      # feature strides the decoder tails tap
+_CellStep = namedtuple("_CellStep", "key layer lead members fork")   # one distinct cell of the trunk
+_Tail = namedtuple("_Tail", "branch last")                          # how branch b reaches the 1/8 fusion input
 
 
-def path2downs(path):
-    '''0 same 1 down'''
-    steps = [b - a for a, b in zip(path[:-1], path[1:])]
-    assert all(s in (0, 1) for s in steps)
-    return steps + [0]
-
-
-def downs2path(downs):
-    path = [0]
-    for down in downs[:-1]:
-        path.append(path[-1] + (1 if down == 1 else 0))
-    return path
-
-
-def _skip_prob(alphas, path, i):
-    return F.softmax(alphas[path[i]][i - path[i]], dim=-1)[0]
-
-
-def alphas2ops_path_width(alphas, path, widths, ignore_skip=False):
-    '''alphas: [alphas0, ..., alphas3] -- MUTATED in place (entries set to -inf), like the reference.'''
-    assert len(path) == len(widths) + 1, "len(path) %d, len(widths) %d" % (len(path), len(widths))
-    L = len(path)
-    min_len = int(np.round(L / 3.)) + path[-1] * 2
-    prunable = []  # (position, softmax prob of 'skip') of skip-connects that may be dropped
-    for i in range(L):
-        row = alphas[path[i]][i - path[i]]
-        if ignore_skip:
-            row[0] = -float('inf')
-        if row.argmax() == 0 and (i == L - 1 or path[i] == path[i + 1]):
-            prunable.append((i, _skip_prob(alphas, path, i)))
-    skip_at = [pos for pos, _ in prunable]
-    down_at = [pos for pos in range(L - 1) if path[pos] < path[pos + 1]]
-    if len(down_at) > 0:
-        down_at.append(L)
-        for lo, hi in zip(down_at[:-1], down_at[1:]):
-            # between two downsamples (and from the last one to the end) at least one real op must survive
-            whole_run = (lo + 1 in skip_at and hi - 1 in skip_at and
-                         skip_at.index(hi - 1) - skip_at.index(lo + 1) == (hi - 1) - (lo + 1))
-            if whole_run:
-                weakest = [1, -1]
-                for j in range(lo + 1, hi):
-                    score = _skip_prob(alphas, path, j)
-                    if score <= weakest[0]:
-                        weakest = [score, j]
-                j = weakest[1]
-                alphas[path[j]][j - path[j]][0] = -float('inf')
-    if len(prunable) > L - min_len:
-        prunable = sorted(prunable, key=lambda t: t[1], reverse=True)[:L - min_len]
-    skip_at = [pos for pos, _ in prunable]
-    ops, path_compact, widths_compact = [], [], []
-    for i in range(L):
-        row = alphas[path[i]][i - path[i]]
-        op = row.argmax()
-        if op == 0:
-            if i in skip_at:
-                if i == L - 1:
-                    widths_compact = widths_compact[:-1]  # the pruned last layer takes its width with it
-                continue
-            row[0] = -float('inf')
-            op = row.argmax()
-        path_compact.append(path[i])
-        if i < len(widths):
-            widths_compact.append(widths[i])
-        ops.append(op)
-    assert len(path_compact) >= min_len
-    return ops, path_compact, widths_compact
-
-
-def betas2path(betas, last, layers):
-    downs = [0] * layers
-    # betas1 is of length layers-2; beta2: layers-3
-    if last == 1:
-        down_idx = np.argmax([beta[0] for beta in betas[1][1:-1].cpu().numpy()]) + 1
-        downs[down_idx] = 1
-    elif last == 2:
-        best, best_ij = 0, (0, 1)
-        for j in range(layers - 4):
-            for i in range(1, j - 1):
-                prob = betas[1][i][0] * betas[2][j][0]
-                if prob > best:
-                    best, best_ij = prob, (i, j)
-        downs[best_ij[0] + 1] = 1
-        downs[best_ij[1] + 2] = 1
-    path = downs2path(downs)
-    assert path[-1] == last
-    return path
-
-
-def path2widths(path, ratios, width_mult_list):
-    widths = []
-    for layer in range(1, len(path)):
-        scale = path[layer]
-        row = ratios[scale][layer - 1] if scale == 0 else ratios[scale][layer - scale]
-        widths.append(width_mult_list[row.argmax()])
-    return widths
-
-
-def network_metas(alphas, betas, ratios, width_mult_list, layers, last, ignore_skip=False):
-    # NOTE (kept quirk): betas[1]/betas[2] are re-softmaxed in place on every call
-    betas[1] = F.softmax(betas[1], dim=-1)
-    betas[2] = F.softmax(betas[2], dim=-1)
-    path = betas2path(betas, last, layers)
-    widths = path2widths(path, ratios, width_mult_list)
-    ops, path, widths = alphas2ops_path_width(alphas, path, widths, ignore_skip=ignore_skip)
-    assert len(ops) == len(path) and len(path) == len(widths) + 1, "op %d, path %d, width%d" % (len(ops), len(path), len(widths))
-    downs = path2downs(path)  # 0 same 1 down
-    return ops, path, downs, widths
-
-
-# ------------------------------------------------------------------------------------------------------------
 class MixedOp(nn.Module):
     """Single selected primitive (non-slimmable, fixed channels)."""
 
@@ -172,15 +67,10 @@ class Network_Multi_Path_Infer(nn.Module):
     def __init__(self, alphas, betas, ratios, num_classes=19, layers=9, criterion=nn.CrossEntropyLoss(ignore_index=-1),
                  Fch=12, width_mult_list=[1., ], stem_head_width=(1., 1.), ignore_skip=False):
         super(Network_Multi_Path_Infer, self).__init__()
-        self._num_classes = num_classes
         assert layers >= 2
-        self._layers = layers
-        self._criterion = criterion
-        self._Fch = Fch
-        if ratios[0].size(1) == 1:
-            self._width_mult_list = [1., ] if ignore_skip else [4. / 12, ]
-        else:
-            self._width_mult_list = width_mult_list
+        self._num_classes, self._layers, self._criterion, self._Fch = num_classes, layers, criterion, Fch
+        single_width = ratios[0].size(1) == 1          # genotypes searched without width options (model_seg.py:183-189)
+        self._width_mult_list = ([1., ] if ignore_skip else [4. / 12, ]) if single_width else width_mult_list
         self._stem_head_width = stem_head_width
         self.latency = 0
         self.logits_dtype = torch.float32  # dtype of the upsampled logits returned by forward (fp16 halves the HBM write)
@@ -189,112 +79,139 @@ class Network_Multi_Path_Infer(nn.Module):
         # before the feature-fusion module.
         self.parallel_branches = True
 
-        w0 = stem_head_width[0]
+        c2, c4, c8 = (self.num_filters(s, stem_head_width[0]) for s in (2, 4, 8))
         self.stem = nn.Sequential(
-            ConvNorm(3, self.num_filters(2, w0) * 2, kernel_size=3, stride=2, padding=1, bias=False, groups=1, slimmable=False),
-            BasicResidual2x(self.num_filters(2, w0) * 2, self.num_filters(4, w0) * 2, kernel_size=3, stride=2, groups=1, slimmable=False),
-            BasicResidual2x(self.num_filters(4, w0) * 2, self.num_filters(8, w0), kernel_size=3, stride=2, groups=1, slimmable=False))
+            ConvNorm(3, c2 * 2, kernel_size=3, stride=2, padding=1, bias=False, groups=1, slimmable=False),
+            BasicResidual2x(c2 * 2, c4 * 2, kernel_size=3, stride=2, groups=1, slimmable=False),
+            BasicResidual2x(c4 * 2, c8, kernel_size=3, stride=2, groups=1, slimmable=False))
 
-        for last in (0, 1, 2):  # order matters: the decoder mutates alphas / betas between calls
-            ops, path, downs, widths = network_metas(alphas, betas, ratios, self._width_mult_list, layers, last,
-                                                     ignore_skip=ignore_skip)
-            setattr(self, "ops%d" % last, ops)
-            setattr(self, "path%d" % last, path)
-            setattr(self, "downs%d" % last, downs)
-            setattr(self, "widths%d" % last, widths)
+        # one decoder for the three candidate branches; the order 0, 1, 2 matters (decode.py: the stages talk through
+        # in-place edits of alphas / betas)
+        decoder = decode.BranchDecoder(alphas, betas, ratios, self._width_mult_list, layers, ignore_skip)
+        for last in (0, 1, 2):
+            g = decoder.decode(last)
+            for field in ("ops", "path", "downs", "widths"):
+                setattr(self, "%s%d" % (field, last), getattr(g, field))
 
     def num_filters(self, scale, width=1.0):
         return int(np.round(scale * self._Fch * width))
 
+    # ---------------------------------------------------------------------------------------------------------
+    # structure
+    # ---------------------------------------------------------------------------------------------------------
     def build_structure(self, lasts):
         self._branch = len(lasts)
         self.lasts = lasts
-        self.ops = [getattr(self, "ops%d" % last) for last in lasts]
-        self.paths = [getattr(self, "path%d" % last) for last in lasts]
-        self.downs = [getattr(self, "downs%d" % last) for last in lasts]
-        self.widths = [getattr(self, "widths%d" % last) for last in lasts]
+        self.ops, self.paths, self.downs, self.widths = ([getattr(self, name % last) for last in lasts]
+                                                         for name in ("ops%d", "path%d", "downs%d", "widths%d"))
         self.branch_groups, self.cells = self.get_branch_groups_cells(self.ops, self.paths, self.downs, self.widths, self.lasts)
         self.build_arm_ffm_head()
+        self._compile_schedule()
 
-    def build_arm_ffm_head(self):
-        hw = self._stem_head_width[1]
-        f8, f16, f32 = self.num_filters(8, hw), self.num_filters(16, hw), self.num_filters(32, hw)
-        if self.training:  # auxiliary heads only exist in a train-mode build (model_seg.py:217-226)
-            if 2 in self.lasts:
-                self.heads32 = Head(f32, self._num_classes, True, norm_layer=BatchNorm2d)
-                self.heads16 = Head(f16 + self.ch_16 if 1 in self.lasts else self.ch_16, self._num_classes, True, norm_layer=BatchNorm2d)
-            else:
-                self.heads16 = Head(f16, self._num_classes, True, norm_layer=BatchNorm2d)
-        self.heads8 = Head(f8 * self._branch, self._num_classes, Fch=self._Fch, scale=4, branch=self._branch, is_aux=False,
-                           norm_layer=BatchNorm2d)
-        if 2 in self.lasts:
-            self.arms32 = nn.ModuleList([ConvNorm(f32, f16, 1, 1, 0, slimmable=False), ConvNorm(f16, f8, 1, 1, 0, slimmable=False)])
-            self.refines32 = nn.ModuleList([ConvNorm(f16 + self.ch_16, f16, 3, 1, 1, slimmable=False),
-                                            ConvNorm(f8 + self.ch_8_2, f8, 3, 1, 1, slimmable=False)])
-        if 1 in self.lasts:
-            self.arms16 = ConvNorm(f16, f8, 1, 1, 0, slimmable=False)
-            self.refines16 = ConvNorm(f8 + self.ch_8_1, f8, 3, 1, 1, slimmable=False)
-        self.ffm = FeatureFusion(f8 * self._branch, f8 * self._branch, reduction=1, Fch=self._Fch, scale=8, branch=self._branch,
-                                 norm_layer=BatchNorm2d)
+    def _cell_channels(self, branch, layer):
+        """(C_in, C_out) of the cell of `branch` at `layer`: stem width in, head width out, searched widths in between."""
+        path, widths = self.paths[branch], self.widths[branch]
+        stride = 2 ** (path[layer] + 3)
+        grow = self.downs[branch][layer] + 1
+        first, final = layer == 0, layer == len(path) - 1
+        if final and not first:
+            assert self.downs[branch][layer] == 0
+        w_in = self._stem_head_width[0] if first else widths[layer - 1]
+        if first or not final:
+            return self.num_filters(stride, w_in), self.num_filters(stride * grow, widths[layer])
+        return self.num_filters(stride, w_in), self.num_filters(stride, self._stem_head_width[1])
 
     def get_branch_groups_cells(self, ops, paths, downs, widths, lasts):
-        """Branches share a cell while scale, op, width and next scale agree (model_seg.py:241-296)."""
-        num_branch = len(ops)
-        layers = max(len(path) for path in paths)
-        groups_all = []
-        self.ch_16 = 0; self.ch_8_2 = 0; self.ch_8_1 = 0
-        cells = nn.ModuleDict()  # "layer-branch" -> Cell
-        still_merged = np.ones((num_branch, num_branch))
-        for l in range(layers):
-            same_here = np.ones((num_branch, num_branch))
-            for i in range(num_branch):
-                for j in range(i + 1, num_branch):
-                    differs = (len(paths[i]) <= l + 1 or len(paths[j]) <= l + 1 or paths[i][l + 1] != paths[j][l + 1]
-                               or ops[i][l] != ops[j][l] or widths[i][l] != widths[j][l])
-                    if differs:
-                        same_here[i, j] = same_here[j, i] = 0
-            still_merged *= same_here
-            branch_groups = []
-            for branch in range(num_branch):
-                if len(paths[branch]) < l + 1:
-                    continue
-                inserted = False
-                for group in branch_groups:
-                    if still_merged[group[0], branch] == 1:
-                        group.append(branch)
-                        inserted = True
-                        continue
-                if not inserted:
-                    branch_groups.append([branch])
-            for group in branch_groups:
-                lead = group[0]
-                for other in group[1:]:
-                    assert (ops[lead][l] == ops[other][l] and paths[lead][l + 1] == paths[other][l + 1]
-                            and downs[lead][l] == downs[other][l] and widths[lead][l] == widths[other][l])
-                op = ops[lead][l]
-                scale = 2 ** (paths[lead][l] + 3)
-                down = downs[lead][l]
-                if l < len(paths[lead]) - 1:
-                    assert down == paths[lead][l + 1] - paths[lead][l]
-                assert down in [0, 1]
-                if l == 0:
-                    c_in, c_out = self.num_filters(scale, self._stem_head_width[0]), self.num_filters(scale * (down + 1), widths[lead][l])
-                elif l == len(paths[lead]) - 1:
-                    assert down == 0  # last cell of this branch
-                    c_in, c_out = self.num_filters(scale, widths[lead][l - 1]), self.num_filters(scale, self._stem_head_width[1])
-                else:
-                    c_in, c_out = self.num_filters(scale, widths[lead][l - 1]), self.num_filters(scale * (down + 1), widths[lead][l])
-                cell = Cell(op, c_in, c_out, down)
-                # channel counts of the skip features the refine convs will concatenate
-                if 2 in self.lasts and self.lasts.index(2) in group and down and scale == 16: self.ch_16 = cell._C_in
-                if 2 in self.lasts and self.lasts.index(2) in group and down and scale == 8: self.ch_8_2 = cell._C_in
-                if 1 in self.lasts and self.lasts.index(1) in group and down and scale == 8: self.ch_8_1 = cell._C_in
-                for branch in group:
-                    cells[str(l) + "-" + str(branch)] = cell
-            groups_all.append(branch_groups)
-        return groups_all, cells
+        """Branches share a cell for as long as, layer after layer, they agree on (next scale, op, width)
+        (model_seg.py:241-296).  Returns ([per layer: groups of branch ids], ModuleDict "layer-branch" -> Cell)."""
+        n_branch = len(ops)
 
-    # --------------------------------------------------------------------------------------------------------
+        def fingerprint(b, layer):
+            if len(paths[b]) <= layer + 1:
+                return ("last-cell-of", b)     # a branch's final cell is never shared
+            return (paths[b][layer + 1], int(ops[b][layer]), widths[b][layer])
+
+        self.ch_16 = self.ch_8_2 = self.ch_8_1 = 0
+        taps = {}   # which branch's skip feature feeds which refine conv: (last, stride) -> attribute
+        for attr, last, stride in (("ch_16", 2, 16), ("ch_8_2", 2, 8), ("ch_8_1", 1, 8)):
+            if last in lasts:
+                taps[(lasts.index(last), stride)] = attr
+
+        cells, groups_per_layer = nn.ModuleDict(), []
+        history = [() for _ in range(n_branch)]        # fingerprints so far; equal histories = still the same cell
+        for layer in range(max(len(p) for p in paths)):
+            buckets = OrderedDict()
+            for b in range(n_branch):
+                history[b] = history[b] + (fingerprint(b, layer),)
+                if len(paths[b]) >= layer + 1:
+                    buckets.setdefault(history[b], []).append(b)
+            groups = list(buckets.values())
+            for members in groups:
+                lead = members[0]
+                for other in members[1:]:
+                    assert (ops[lead][layer] == ops[other][layer] and paths[lead][layer + 1] == paths[other][layer + 1]
+                            and downs[lead][layer] == downs[other][layer] and widths[lead][layer] == widths[other][layer])
+                down = downs[lead][layer]
+                assert down in [0, 1]
+                if layer < len(paths[lead]) - 1:
+                    assert down == paths[lead][layer + 1] - paths[lead][layer]
+                c_in, c_out = self._cell_channels(lead, layer)
+                cell = Cell(ops[lead][layer], c_in, c_out, down)
+                if down:   # the feature entering a down-sampling cell is what the refine conv of the finer scale concatenates
+                    stride = 2 ** (paths[lead][layer] + 3)
+                    for b in members:
+                        if (b, stride) in taps:
+                            setattr(self, taps[(b, stride)], cell._C_in)
+                for b in members:
+                    cells["%d-%d" % (layer, b)] = cell
+            groups_per_layer.append(groups)
+        return groups_per_layer, cells
+
+    def build_arm_ffm_head(self):
+        """Decoder modules (model_seg.py:214-239); attribute names are the checkpoint format."""
+        n_cls, bn = self._num_classes, BatchNorm2d
+        f8, f16, f32 = (self.num_filters(s, self._stem_head_width[1]) for s in SCALES)
+        has16, has32 = 1 in self.lasts, 2 in self.lasts
+        if self.training:  # auxiliary heads only exist in a train-mode build (model_seg.py:217-226)
+            if has32:
+                self.heads32 = Head(f32, n_cls, True, norm_layer=bn)
+                self.heads16 = Head(f16 + self.ch_16 if has16 else self.ch_16, n_cls, True, norm_layer=bn)
+            else:
+                self.heads16 = Head(f16, n_cls, True, norm_layer=bn)
+        fused = f8 * self._branch
+        self.heads8 = Head(fused, n_cls, Fch=self._Fch, scale=4, branch=self._branch, is_aux=False, norm_layer=bn)
+        point = dict(kernel_size=1, stride=1, padding=0, slimmable=False)
+        box = dict(kernel_size=3, stride=1, padding=1, slimmable=False)
+        if has32:
+            self.arms32 = nn.ModuleList([ConvNorm(f32, f16, **point), ConvNorm(f16, f8, **point)])
+            self.refines32 = nn.ModuleList([ConvNorm(f16 + self.ch_16, f16, **box), ConvNorm(f8 + self.ch_8_2, f8, **box)])
+        if has16:
+            self.arms16 = ConvNorm(f16, f8, **point)
+            self.refines16 = ConvNorm(f8 + self.ch_8_1, f8, **box)
+        self.ffm = FeatureFusion(fused, fused, reduction=1, Fch=self._Fch, scale=8, branch=self._branch, norm_layer=bn)
+
+    def _compile_schedule(self):
+        steps = []
+        for layer, groups in enumerate(self.branch_groups):
+            for n, members in enumerate(groups):
+                steps.append(_CellStep("%d-%d" % (layer, members[0]), layer, members[0], tuple(members),
+                                       fork=(n == 0 and len(groups) > 1)))
+        # plain (non-Module, non-persistent) attributes: the schedule is derived data
+        self.__dict__["_steps"] = steps
+        self.__dict__["_tails"] = [_Tail(b, last) for b, last in enumerate(self.lasts)]
+
+    def _tail_modules(self, last):
+        """[(arm 1x1, refine 3x3, stride of the coarse input, stride of the skip input, extra skip channels)] for a branch
+        ending at scale index `last`, coarse to fine."""
+        if last == 2:
+            return [(self.arms32[0], self.refines32[0], 32, 16, self.ch_16), (self.arms32[1], self.refines32[1], 16, 8, self.ch_8_2)]
+        if last == 1:
+            return [(self.arms16, self.refines16, 16, 8, self.ch_8_1)]
+        return []
+
+    # ---------------------------------------------------------------------------------------------------------
+    # execution
+    # ---------------------------------------------------------------------------------------------------------
     def _arm_refine(self, arm, refine, coarse, skip, out=None):
         """arm 1x1 -> bilinear to skip's size -> cat([up, skip]) -> refine 3x3, with the concat done by writing both
         producers into one buffer (model_seg.py:304-307, 309-312, 316-319)."""
@@ -310,8 +227,8 @@ class Network_Multi_Path_Infer(nn.Module):
         F_.copy_channels(F_.to_nhwc_half(skip), cat[:, c_up:])
         return refine(cat, out=out)
 
-    # ---- multi-stream plumbing (inference only) ----------------------------------------------------------
     def _side_streams(self, device):
+        """one extra CUDA stream per additional branch (inference only)"""
         if not self.parallel_branches or self._branch < 2 or self.training or device.type != "cuda":
             return None
         streams = self.__dict__.get("_fsb_streams")
@@ -320,134 +237,129 @@ class Network_Multi_Path_Infer(nn.Module):
             self.__dict__["_fsb_streams"] = streams
         return streams
 
-    def agg_ffm(self, outputs8, outputs16, outputs32, ctx=None):
-        training = self.training
-        ctx = ctx if ctx is not None else _BranchCtx(None)
-        pred32, pred16 = [], []
-        f8 = self.num_filters(8, self._stem_head_width[1])
-        ref = outputs8[0]
-        fused_in = getattr(ctx, "fused_in", None)  # allocated before the fork (see _trunk)
-        if fused_in is None:
-            fused_in = F_.empty_nhwc(ref.shape[0], f8 * self._branch, ref.shape[2], ref.shape[3], ref.device)  # cat(pred8)
-        grad = torch.is_grad_enabled() and any(t.requires_grad for t in outputs8 + outputs16 + outputs32)
-        pred8_list = []
-        for branch in range(self._branch):
-            last = self.lasts[branch]
-            slot = None if grad else fused_in[:, branch * f8:(branch + 1) * f8]
-            with ctx.on(branch):
-                if last == 2:
-                    if training: pred32.append(outputs32[branch])
-                    out = self._arm_refine(self.arms32[0], self.refines32[0], outputs32[branch], outputs16[branch])
-                    if training: pred16.append(outputs16[branch])
-                    pred8_list.append(self._arm_refine(self.arms32[1], self.refines32[1], out, outputs8[branch], out=slot))
-                elif last == 1:
-                    if training: pred16.append(outputs16[branch])
-                    pred8_list.append(self._arm_refine(self.arms16, self.refines16, outputs16[branch], outputs8[branch], out=slot))
-                elif last == 0:
-                    pred8_list.append(outputs8[branch])
-                    if not grad:
-                        F_.copy_channels(F_.to_nhwc_half(outputs8[branch]), slot)
-        ctx.join()
-        if grad:
-            fused_in = _cat_channels(pred8_list)
-        pred8 = self.heads8(self.ffm(fused_in))
-        if not training:
-            return pred8
-        pred32 = self.heads32(_cat_channels(pred32)) if len(pred32) > 0 else None
-        pred16 = self.heads16(_cat_channels(pred16)) if len(pred16) > 0 else None
-        return pred8, pred16, pred32
-
     def _trunk(self, input, ctx=None):
-        H = input.size(2)
+        """stem + cells -> per scale, the latest feature of every branch ({8: [...], 16: [...], 32: [...]})"""
+        full_h = input.size(2)
         ctx = ctx if ctx is not None else _BranchCtx(None)
         stem = self.stem(input)
         # The concat buffer that the side streams will write into is allocated on the main stream BEFORE the fork, so the
         # block the caching allocator hands out cannot still be in use by main-stream work the side streams do not wait for.
         f8 = self.num_filters(8, self._stem_head_width[1])
         ctx.fused_in = F_.empty_nhwc(stem.shape[0], f8 * self._branch, stem.shape[2], stem.shape[3], stem.device)
-        # last feature map of each branch at each scale
-        outputs8 = [stem] * self._branch
-        outputs16 = [stem] * self._branch
-        outputs32 = [stem] * self._branch
-        outputs = [stem] * self._branch
-        for layer in range(len(self.branch_groups)):
-            groups = self.branch_groups[layer]
-            if len(groups) > 1:
+        latest = [stem] * self._branch
+        taps = {s: [stem] * self._branch for s in SCALES}
+        for step in self._steps:
+            if step.fork:
                 ctx.fork()
-            for group in groups:
-                with ctx.on(group[0]):
-                    output = self.cells[str(layer) + "-" + str(group[0])](outputs[group[0]])
-                scale = int(H // output.size(2))
-                for branch in group:
-                    outputs[branch] = output
-                    if scale == 8: outputs8[branch] = output
-                    elif scale == 16: outputs16[branch] = output
-                    elif scale == 32: outputs32[branch] = output
-        return outputs8, outputs16, outputs32
+            with ctx.on(step.lead):
+                feat = self.cells[step.key](latest[step.lead])
+            stride = int(full_h // feat.size(2))
+            for b in step.members:
+                latest[b] = feat
+                if stride in taps:
+                    taps[stride][b] = feat
+        return taps[8], taps[16], taps[32]
 
-    def forward(self, input):
+    def agg_ffm(self, outputs8, outputs16, outputs32, ctx=None):
+        """per-branch arm/refine tails -> concat at 1/8 -> FeatureFusion -> heads (model_seg.py:298-335)"""
+        training = self.training
+        ctx = ctx if ctx is not None else _BranchCtx(None)
+        taps = {8: outputs8, 16: outputs16, 32: outputs32}
+        f8 = self.num_filters(8, self._stem_head_width[1])
+        fused_in = getattr(ctx, "fused_in", None)  # allocated before the fork (see _trunk)
+        if fused_in is None:
+            ref = outputs8[0]
+            fused_in = F_.empty_nhwc(ref.shape[0], f8 * self._branch, ref.shape[2], ref.shape[3], ref.device)  # cat(pred8)
+        grad = torch.is_grad_enabled() and any(t.requires_grad for t in outputs8 + outputs16 + outputs32)
+        aux = {16: [], 32: []}          # train mode: inputs of the auxiliary heads, in branch order
+        at8 = []
+        for tail in self._tails:
+            b = tail.branch
+            slot = None if grad else fused_in[:, b * f8:(b + 1) * f8]
+            with ctx.on(b):
+                chain = self._tail_modules(tail.last)
+                feat = None
+                for n, (arm, refine, s_coarse, s_skip, _) in enumerate(chain):
+                    coarse = taps[s_coarse][b] if n == 0 else feat
+                    if training and n == 0:
+                        aux[s_coarse].append(coarse)
+                    if training and n == 1:
+                        aux[s_coarse].append(taps[s_coarse][b])   # the trunk's 1/16 feature, not the refined one
+                    feat = self._arm_refine(arm, refine, coarse, taps[s_skip][b], out=slot if n == len(chain) - 1 else None)
+                if not chain:
+                    feat = outputs8[b]
+                    if not grad:
+                        F_.copy_channels(F_.to_nhwc_half(feat), slot)
+                at8.append(feat)
+        ctx.join()
+        if grad:
+            fused_in = _cat_channels(at8)
+        pred8 = self.heads8(self.ffm(fused_in))
+        if not training:
+            return pred8
+        pred32 = self.heads32(_cat_channels(aux[32])) if aux[32] else None
+        pred16 = self.heads16(_cat_channels(aux[16])) if aux[16] else None
+        return pred8, pred16, pred32
+
+    def _features(self, input):
         ctx = _BranchCtx(self._side_streams(input.device))
         outputs8, outputs16, outputs32 = self._trunk(input, ctx)
-        if self.training:
-            pred8, pred16, pred32 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
-            up = _upsample_logits
-            pred8 = up(pred8, (pred8.size(2) * 8, pred8.size(3) * 8), self.logits_dtype)
-            if pred16 is not None:
-                pred16 = up(pred16, (pred16.size(2) * 16, pred16.size(3) * 16), self.logits_dtype)
-            if pred32 is not None:
-                pred32 = up(pred32, (pred32.size(2) * 32, pred32.size(3) * 32), self.logits_dtype)
-            return pred8, pred16, pred32
-        pred8 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
-        return F_.upsample_logits(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), dtype=self.logits_dtype)
+        return self.agg_ffm(outputs8, outputs16, outputs32, ctx)
+
+    def forward(self, input):
+        if not self.training:
+            pred8 = self._features(input)
+            return F_.upsample_logits(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), dtype=self.logits_dtype)
+        outs = []
+        for pred, factor in zip(self._features(input), SCALES):   # (pred8, pred16, pred32)
+            if pred is not None:
+                pred = _upsample_logits(pred, (pred.size(2) * factor, pred.size(3) * factor), self.logits_dtype)
+            outs.append(pred)
+        return tuple(outs)
 
     @torch.no_grad()
     def predict_labels(self, input, out=None):
         """argmax(forward(input), dim=1) as uint8, fused into the x8 upsample: the evaluator's
         `exp -> cpu -> argmax` (tools/engine/evaluator.py:315-318) without materialising full-resolution logits."""
         assert not self.training
-        ctx = _BranchCtx(self._side_streams(input.device))
-        outputs8, outputs16, outputs32 = self._trunk(input, ctx)
-        pred8 = self.agg_ffm(outputs8, outputs16, outputs32, ctx)
+        pred8 = self._features(input)
         return F_.upsample_argmax(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), out=out)
 
+    # ---------------------------------------------------------------------------------------------------------
+    # latency model (table lookups, model_seg.py:368-408)
+    # ---------------------------------------------------------------------------------------------------------
     def forward_latency(self, size):
-        _, H, W = size
-        latency_total = 0
-        for stem_op in self.stem:
-            latency, size = stem_op.forward_latency(size)
-            latency_total += latency
-        outputs8 = [size] * self._branch
-        outputs16 = [size] * self._branch
-        outputs32 = [size] * self._branch
-        outputs = [size] * self._branch
-        for layer in range(len(self.branch_groups)):
-            for group in self.branch_groups[layer]:
-                latency, size = self.cells[str(layer) + "-" + str(group[0])].forward_latency(outputs[group[0]])
-                latency_total += latency
-                scale = int(H // size[1])
-                for branch in group:
-                    outputs[branch] = size
-                    # kept quirk: the reference tests `scale == 4` here (and would NameError on it), so the 1/8
-                    # entry keeps the stem size; harmless because only outputs16/32 and `out_size` are read below
-                    if scale == 16: outputs16[branch] = size
-                    elif scale == 32: outputs32[branch] = size
-        for branch in range(self._branch):
-            last = self.lasts[branch]
-            if last == 2:
-                latency, size = self.arms32[0].forward_latency(outputs32[branch]); latency_total += latency
-                latency, size = self.refines32[0].forward_latency((size[0] + self.ch_16, size[1] * 2, size[2] * 2)); latency_total += latency
-                latency, size = self.arms32[1].forward_latency(size); latency_total += latency
-                latency, size = self.refines32[1].forward_latency((size[0] + self.ch_8_2, size[1] * 2, size[2] * 2)); latency_total += latency
-                out_size = size
-            elif last == 1:
-                latency, size = self.arms16.forward_latency(outputs16[branch]); latency_total += latency
-                latency, size = self.refines16.forward_latency((size[0] + self.ch_8_1, size[1] * 2, size[2] * 2)); latency_total += latency
-                out_size = size
-            elif last == 0:
-                out_size = outputs8[branch]
-        latency, size = self.ffm.forward_latency((out_size[0] * self._branch, out_size[1], out_size[2])); latency_total += latency
-        latency, size = self.heads8.forward_latency(size); latency_total += latency
-        return latency_total, size
+        full_h = size[1]
+        total = 0
+
+        def run(module, shape):
+            nonlocal total
+            ms, shape = module.forward_latency(shape)
+            total += ms
+            return shape
+
+        for block in self.stem:
+            size = run(block, size)
+        latest = [size] * self._branch
+        # kept quirk: the reference never records the 1/8 shape of a cell here (it tests `scale == 4`), so the entry of a
+        # branch that ends at 1/8 stays the stem's shape; only the 1/16 and 1/32 shapes are tracked
+        taps = {s: [size] * self._branch for s in SCALES}
+        for step in self._steps:
+            shape = run(self.cells[step.key], latest[step.lead])
+            stride = int(full_h // shape[1])
+            for b in step.members:
+                latest[b] = shape
+                if stride in (16, 32):
+                    taps[stride][b] = shape
+        for tail in self._tails:
+            chain = self._tail_modules(tail.last)
+            shape = taps[8][tail.branch]
+            for n, (arm, refine, s_coarse, _, c_skip) in enumerate(chain):
+                shape = run(arm, taps[s_coarse][tail.branch] if n == 0 else shape)
+                shape = run(refine, (shape[0] + c_skip, shape[1] * 2, shape[2] * 2))
+        shape = run(self.ffm, (shape[0] * self._branch, shape[1], shape[2]))   # shape of the LAST branch, like the reference
+        shape = run(self.heads8, shape)
+        return total, shape
 
 
 class _NullCtx:
