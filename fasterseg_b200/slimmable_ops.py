@@ -1,11 +1,11 @@
 """Slimmable (width-switchable) conv / BN -- drop-in for the reference's slimmable_ops.py.
 
-Same class names, constructor signatures, attributes and state_dict keys as
-search/slimmable_ops.py:5-70; both classes stay subclasses of nn.Conv2d / nn.BatchNorm2d because
-tools/utils/init_func.py:5-15 and thop select modules by isinstance.  The arithmetic runs on the
-sm_100a kernels of libfsb200 (no torch.nn.functional on the hot path).
+Same class names, constructor signatures, attributes and state_dict keys as search/slimmable_ops.py:5-70; both classes stay
+subclasses of nn.Conv2d / nn.BatchNorm2d because tools/utils/init_func.py:5-15 and thop select modules by isinstance.
+The master tensors always have the maximum width; a width choice only selects which corner the kernels read
+(`engine.conv_bn_act` asks `_resolve_channels()` / `_active_bn()`), so switching widths costs nothing and the packed fp16
+weight copies are cached per (c_in, c_out) corner.  No torch.nn.functional on the hot path.
 """
-import torch
 import torch.nn as nn
 
 from . import engine
@@ -13,63 +13,68 @@ from . import functional as F_
 
 
 def make_divisible(v, divisor=8, min_value=1):
-    """Round a channel count to a multiple of `divisor`, never dropping by more than 10 %
-    (reference: search/slimmable_ops.py:5-18)."""
-    floor = divisor if min_value is None else min_value
-    rounded = (int(v + divisor / 2) // divisor) * divisor
-    out = rounded if rounded > floor else floor
-    return out + divisor if out < 0.9 * v else out
+    """Channel count for a fractional width: nearest multiple of `divisor` (ties up), at least `min_value`
+    (`divisor` when that is None), bumped by one `divisor` if rounding lost more than 10 % (slimmable_ops.py:5-18)."""
+    lowest = divisor if min_value is None else min_value
+    nearest = int(v + divisor / 2) // divisor * divisor
+    channels = max(nearest, lowest)
+    if channels < 0.9 * v:
+        channels += divisor
+    return channels
 
 
-class USConv2d(nn.Conv2d):
-    """Conv2d whose active in/out channels are a ratio of the max width; the weight tensor keeps the max
-    shape and the kernel reads the [:out, :in] corner in place (reference forward: slimmable_ops.py:36-48)."""
-
-    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
-                 depthwise=False, bias=True, width_mult_list=[1.]):
-        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
-                         dilation=dilation, groups=groups, bias=bias)
-        self.depthwise = depthwise
-        self.in_channels_max = in_channels
-        self.out_channels_max = out_channels
-        self.width_mult_list = width_mult_list
-        self.ratio = (1., 1.)
+class _WidthSwitch:
+    """`set_ratio` plumbing shared by the two slimmable modules: remembers the requested fraction(s) and validates them
+    against the module's `width_mult_list` at use time (the reference asserts inside forward)."""
 
     def set_ratio(self, ratio):
         self.ratio = ratio
 
+    def _checked(self, fraction):
+        assert fraction in self.width_mult_list, str(fraction) + " in? " + str(self.width_mult_list)
+        return fraction
+
+
+class USConv2d(_WidthSwitch, nn.Conv2d):
+    """Conv2d over the active corner weight[:c_out, :c_in] of a max-width master weight (slimmable_ops.py:21-48)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 depthwise=False, bias=True, width_mult_list=[1.]):
+        nn.Conv2d.__init__(self, in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                           groups=groups, bias=bias)
+        self.in_channels_max, self.out_channels_max = in_channels, out_channels
+        self.depthwise = depthwise
+        self.width_mult_list = width_mult_list
+        self.ratio = (1., 1.)
+
     def _resolve_channels(self):
-        r_in, r_out = self.ratio
-        assert r_in in self.width_mult_list, str(r_in) + " in? " + str(self.width_mult_list)
-        assert r_out in self.width_mult_list, str(r_out) + " in? " + str(self.width_mult_list)
-        # the reference mutates these attributes on every forward; callers (and thop) read them
-        self.in_channels = make_divisible(self.in_channels_max * r_in)
-        self.out_channels = make_divisible(self.out_channels_max * r_out)
-        self.groups = self.in_channels if self.depthwise else 1
-        return self.in_channels, self.out_channels
+        """(c_in, c_out) for the current ratio.  Like the reference's forward this also overwrites `in_channels`,
+        `out_channels` and `groups`, which callers (and thop's counters) read afterwards."""
+        fractions = [self._checked(r) for r in self.ratio]
+        active = [make_divisible(full * r) for full, r in zip((self.in_channels_max, self.out_channels_max), fractions)]
+        self.in_channels, self.out_channels = active
+        self.groups = active[0] if self.depthwise else 1
+        return tuple(active)
 
     def forward(self, input):
         return engine.conv_bn_act(input, self, None, relu=False)
 
 
-class USBatchNorm2d(nn.BatchNorm2d):
-    """One full nn.BatchNorm2d per candidate width under `self.bn` (keys `bn.{i}.*`); the module's own
-    weight/bias (from super().__init__, track_running_stats=False) exist but are never used -- kept because
-    they are part of the reference checkpoint format (slimmable_ops.py:51-62)."""
+class USBatchNorm2d(_WidthSwitch, nn.BatchNorm2d):
+    """One complete nn.BatchNorm2d per candidate width under `self.bn` (state_dict keys `bn.{i}.*`).  The module's own
+    `weight` / `bias` (created by the base class, no running statistics) are never used in forward but belong to the
+    reference checkpoint format and to `parameters()` (slimmable_ops.py:51-62)."""
 
     def __init__(self, num_features, width_mult_list=[1.]):
-        super().__init__(num_features, affine=True, track_running_stats=False)
+        nn.BatchNorm2d.__init__(self, num_features, affine=True, track_running_stats=False)
         self.num_features_max = num_features
         self.width_mult_list = width_mult_list
-        self.bn = nn.ModuleList(nn.BatchNorm2d(make_divisible(num_features * w), affine=True) for w in width_mult_list)
+        per_width = [nn.BatchNorm2d(make_divisible(num_features * fraction), affine=True) for fraction in width_mult_list]
+        self.bn = nn.ModuleList(per_width)
         self.ratio = 1.
 
-    def set_ratio(self, ratio):
-        self.ratio = ratio
-
     def _active_bn(self):
-        assert self.ratio in self.width_mult_list
-        return self.bn[self.width_mult_list.index(self.ratio)]
+        return self.bn[self.width_mult_list.index(self._checked(self.ratio))]
 
     def forward(self, input):
         return batchnorm_forward(input, self._active_bn())
