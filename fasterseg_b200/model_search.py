@@ -1,16 +1,20 @@
 """Multi-resolution search supernet -- drop-in for the reference's search/model_search.py.
 
-Kept (search/model_search.py:14-548): gumbel helpers, `MixedOp` / `Cell` / `Network_Multi_Path` with the same constructor
-arguments, `sample_prun_ratio`, `forward`, `forward_latency`, `_loss`, `_build_arch_parameters`, `_reset_arch_parameters`,
-attributes (`_arch_names`, `_arch_parameters`, `arch_idx`, `prun_mode`, `_prun_modes` ...) and every parameter name
-(`stem.0.0.conv.0.weight`, `cells.3.1._op._ops.4.bn2.bn.2.running_var`, `alpha_0_1`, `beta_1_2`, `ratio_1_0` ...), so
-search/train_search.py and search/architect.py drive it unchanged.
+Same public surface as the reference (search/model_search.py:14-548): gumbel helpers, `MixedOp` / `Cell` /
+`Network_Multi_Path` with the same constructor arguments, `sample_prun_ratio`, `forward`, `forward_latency`, `_loss`,
+`_build_arch_parameters`, `_reset_arch_parameters`, attributes (`_arch_names`, `_arch_parameters`, `arch_idx`, `prun_mode`,
+`_prun_modes` ...) and every parameter name (`stem.0.0.conv.0.weight`, `cells.3.1._op._ops.4.bn2.bn.2.running_var`,
+`alpha_0_1`, `beta_1_2`, `ratio_1_0` ...), so search/train_search.py and search/architect.py drive it unchanged.
 
-B200 side: NHWC fp16 activations; every conv+BN+ReLU is one fused tcgen05 kernel (train mode: conv with fused statistics,
-finalize, apply); the `result + op(x) * w * r0 * r1` accumulation over the five primitives and the beta-weighted mix of
-the two cell invocations are single weighted-sum kernels (K5) whose backward also yields the scalar gradients of
-alphas / betas / ratios; logits leave as NCHW fp32 through one layout kernel.
+Organisation (ours): the trellis of cells is described once as a list of `_Node`s (layer, scale, which outputs of the
+previous layer feed it, which beta row mixes them); `forward` and `forward_latency` walk that list, and `_loss` runs a list
+of (architecture, width-mode) passes.  B200 side: NHWC fp16 activations; every conv+BN+ReLU is one fused tcgen05 unit (train
+mode: conv with fused statistics, finalize, apply); the `result + op(x) * w * r0 * r1` accumulation over the five
+primitives and the beta-weighted mix of the two cell invocations are single weighted-sum kernels (K5) whose backward also
+yields the scalar gradients of alphas / betas / ratios; logits leave as NCHW fp32 through one layout kernel.
 """
+from collections import namedtuple
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -24,31 +28,47 @@ from .operations import *  # noqa: F401,F403
 from .operations import OPS, BasicResidual2x, ConvNorm
 from .seg_oprs import Head
 
+KEEP, DOWN = 0, 1   # the two outputs of a cell: same scale / next coarser scale
+_Node = namedtuple("_Node", "layer scale feeds beta_row")   # feeds: ((source scale, KEEP | DOWN), ...) in invocation order
 
-# https://github.com/YongfeiYan/Gumbel_Softmax_VAE (as cited by the reference, model_search.py:13)
+
+def _trellis(layers):
+    """Cells of the supernet in execution order.  Scale j appears from layer j on; a cell on the diagonal (layer == scale) or
+    at scale 0 has one input; any other cell runs twice per forward -- first on the down output of the finer scale, then on
+    the keep output of its own scale -- and mixes the results with betas[scale][layer - scale - 1] (model_search.py:289-334)."""
+    nodes = []
+    for layer in range(layers):
+        for scale in range(min(layer, 2) + 1):
+            if scale == 0:
+                nodes.append(_Node(layer, scale, ((0, KEEP),), None))
+            elif layer == scale:
+                nodes.append(_Node(layer, scale, ((scale - 1, DOWN),), None))
+            else:
+                nodes.append(_Node(layer, scale, ((scale - 1, DOWN), (scale, KEEP)), layer - scale - 1))
+    return nodes
+
+
+# ---- gumbel-softmax width sampling (model_search.py:13-43; technique: github.com/YongfeiYan/Gumbel_Softmax_VAE) ---------
 def sample_gumbel(shape, eps=1e-20, device=None):
-    U = torch.rand(shape)  # CPU generator, like the reference (which then moves U to the GPU)
+    uniform = torch.rand(shape)          # drawn from the CPU generator like the reference, then moved
     if device is not None:
-        U = U.to(device)
-    return -torch.log(-torch.log(U + eps) + eps)
+        uniform = uniform.to(device)
+    return -torch.log(eps - torch.log(uniform + eps))
 
 
 def gumbel_softmax_sample(logits, temperature=1):
-    y = logits + sample_gumbel(logits.size(), device=logits.device)
-    return F.softmax(y / temperature, dim=-1)
+    noisy = logits + sample_gumbel(logits.size(), device=logits.device)
+    return F.softmax(noisy / temperature, dim=-1)
 
 
 def gumbel_softmax(logits, temperature=1, hard=False):
-    """ST-gumbel-softmax: one-hot forward value, soft gradient."""
-    y = gumbel_softmax_sample(logits, temperature)
+    """Straight-through estimator: the forward value is the one-hot of the sample, the gradient that of the soft sample."""
+    soft = gumbel_softmax_sample(logits, temperature)
     if not hard:
-        return y
-    shape = y.size()
-    _, ind = y.max(dim=-1)
-    y_hard = torch.zeros_like(y).view(-1, shape[-1])
-    y_hard.scatter_(1, ind.view(-1, 1), 1)
-    y_hard = y_hard.view(*shape)
-    return (y_hard - y).detach() + y
+        return soft
+    winner = soft.max(dim=-1)[1]
+    one_hot = torch.zeros_like(soft).view(-1, soft.size(-1)).scatter_(1, winner.view(-1, 1), 1).view(*soft.size())
+    return (one_hot - soft).detach() + soft
 
 
 def _resolve_ratio(r, width_mult_list):
@@ -59,65 +79,66 @@ def _resolve_ratio(r, width_mult_list):
     return r, 1.
 
 
+def _needs_graph(*tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 class MixedOp(nn.Module):
     def __init__(self, C_in, C_out, stride=1, width_mult_list=[1.]):
         super(MixedOp, self).__init__()
-        self._ops = nn.ModuleList()
         self._width_mult_list = width_mult_list
-        for primitive in PRIMITIVES:
-            self._ops.append(OPS[primitive](C_in, C_out, stride, True, width_mult_list=width_mult_list))
+        self._ops = nn.ModuleList(OPS[name](C_in, C_out, stride, True, width_mult_list=width_mult_list) for name in PRIMITIVES)
 
     def set_prun_ratio(self, ratio):
         for op in self._ops:
             op.set_ratio(ratio)
 
     def _scaled_weights(self, weights, ratios):
-        ratio0, r_score0 = _resolve_ratio(ratios[0], self._width_mult_list)
-        ratio1, r_score1 = _resolve_ratio(ratios[1], self._width_mult_list)
-        self.set_prun_ratio((ratio0, ratio1))
-        return weights * r_score0 * r_score1  # [len(PRIMITIVES)] scalar arithmetic (plumbing)
+        """switch every primitive to the (in, out) widths and fold the two width scores into the op weights"""
+        (w_in, score_in), (w_out, score_out) = (_resolve_ratio(r, self._width_mult_list) for r in ratios[:2])
+        self.set_prun_ratio((w_in, w_out))
+        return weights * score_in * score_out  # [len(PRIMITIVES)] scalar arithmetic (plumbing)
 
     def forward(self, x, weights, ratios):
-        # int: force #channel; tensor: arch_ratio; float(<=1): force width
+        # a ratio is a tensor (searched width distribution) or a float (forced width)
         wvec = self._scaled_weights(weights, ratios)
         outs = [F_.to_nhwc_half(op(x)) for op in self._ops]
-        if torch.is_grad_enabled() and (wvec.requires_grad or any(o.requires_grad for o in outs)):
+        if _needs_graph(wvec, *outs):
             return AG.weighted_sum(wvec, outs)
         return F_.wsum_fwd(outs, wvec.detach().float().contiguous())
 
     def forward_latency(self, size, weights, ratios):
         wvec = self._scaled_weights(weights, ratios)
-        result = 0
+        expected = 0
         for w, op in zip(wvec, self._ops):
-            latency, size_out = op.forward_latency(size)
-            result = result + latency * w
-        return result, size_out
+            ms, size_out = op.forward_latency(size)
+            expected = expected + ms * w
+        return expected, size_out
 
 
 class Cell(nn.Module):
     def __init__(self, C_in, C_out=None, down=True, width_mult_list=[1.]):
         super(Cell, self).__init__()
         self._C_in = C_in
-        if C_out is None: C_out = C_in
-        self._C_out = C_out
+        self._C_out = C_in if C_out is None else C_out
         self._down = down
         self._width_mult_list = width_mult_list
-        self._op = MixedOp(C_in, C_out, width_mult_list=width_mult_list)
+        self._op = MixedOp(C_in, self._C_out, width_mult_list=width_mult_list)
         if self._down:
             self.downsample = MixedOp(C_in, C_in * 2, stride=2, width_mult_list=width_mult_list)
 
+    def _both(self, method, x, alphas, ratios):
+        """(keep, down) through `method` of the two MixedOps; ratios = (in, out, down) and `down` is None iff no down path"""
+        assert (ratios[2] is not None) == bool(self._down)
+        keep = getattr(self._op, method)(x, alphas, (ratios[0], ratios[1]))
+        down = getattr(self.downsample, method)(x, alphas, (ratios[0], ratios[2])) if self._down else None
+        return keep, down
+
     def forward(self, input, alphas, ratios):
-        # ratios: (in, out, down)
-        out = self._op(input, alphas, (ratios[0], ratios[1]))
-        assert (self._down and (ratios[2] is not None)) or ((not self._down) and (ratios[2] is None))
-        down = self.downsample(input, alphas, (ratios[0], ratios[2])) if self._down else None
-        return out, down
+        return self._both("forward", input, alphas, ratios)
 
     def forward_latency(self, size, alphas, ratios):
-        out = self._op.forward_latency(size, alphas, (ratios[0], ratios[1]))
-        assert (self._down and (ratios[2] is not None)) or ((not self._down) and (ratios[2] is None))
-        down = self.downsample.forward_latency(size, alphas, (ratios[0], ratios[2])) if self._down else None
-        return out, down
+        return self._both("forward_latency", size, alphas, ratios)
 
 
 def _mix(betas_row, a, b):
@@ -125,60 +146,63 @@ def _mix(betas_row, a, b):
     if a is None and b is None:
         return 0
     a, b = F_.to_nhwc_half(a), F_.to_nhwc_half(b)
-    if torch.is_grad_enabled() and (betas_row.requires_grad or a.requires_grad or b.requires_grad):
+    if _needs_graph(betas_row, a, b):
         return AG.weighted_sum(betas_row, [a, b])
     return F_.wsum_fwd([a, b], betas_row.detach().float().contiguous())
+
+
+def _blend(brow, results):
+    """(keep, down) of a twice-invoked cell from its [(keep, down) | None, (keep, down) | None] results."""
+    first, second = results
+    if first is not None and second is not None:
+        return _mix(brow, first[KEEP], second[KEEP]), (_mix(brow, first[DOWN], second[DOWN]) if first[DOWN] is not None else 0)
+    # a beta underflowed to 0 and its invocation was skipped: plain scaled term, like the reference's sum()
+    alive, w = (second, brow[1]) if first is None else (first, brow[0])
+    if alive is None:
+        return 0, 0
+    solo = torch.stack([w, w * 0])
+    return _mix(solo, alive[KEEP], alive[KEEP]), (0 if alive[DOWN] is None else _mix(solo, alive[DOWN], alive[DOWN]))
 
 
 class Network_Multi_Path(nn.Module):
     def __init__(self, num_classes=19, layers=16, criterion=nn.CrossEntropyLoss(ignore_index=-1), Fch=12, width_mult_list=[1., ],
                  prun_modes=['arch_ratio', ], stem_head_width=[(1., 1.), ]):
         super(Network_Multi_Path, self).__init__()
-        self._num_classes = num_classes
         assert layers >= 3
-        self._layers = layers
-        self._criterion = criterion
-        self._Fch = Fch
+        self._num_classes, self._layers, self._criterion, self._Fch = num_classes, layers, criterion, Fch
         self._width_mult_list = width_mult_list
         self._prun_modes = prun_modes
         self.prun_mode = None  # prun_mode is higher priority than _prun_modes
         self._stem_head_width = stem_head_width
         self._flops = 0
         self._params = 0
-
         nf = self.num_filters
-        self.stem = nn.ModuleList([
-            nn.Sequential(
-                ConvNorm(3, nf(2, sr) * 2, kernel_size=3, stride=2, padding=1, bias=False, groups=1, slimmable=False),
-                BasicResidual2x(nf(2, sr) * 2, nf(4, sr) * 2, kernel_size=3, stride=2, groups=1, slimmable=False),
-                BasicResidual2x(nf(4, sr) * 2, nf(8, sr), kernel_size=3, stride=2, groups=1, slimmable=False))
-            for sr, _ in self._stem_head_width])
+        stem_widths = [w for w, _ in stem_head_width]
+        head_widths = [w for _, w in stem_head_width]
 
-        self.cells = nn.ModuleList()
-        for l in range(layers):
-            if l == 0:
-                scales, downs = [8], [True]
-            elif l == 1:
-                scales, downs = [8, 16], [True, True]
-            elif l < layers - 1:
-                scales, downs = [8, 16, 32], [True, True, False]
-            else:
-                scales, downs = [8, 16, 32], [False, False, False]
-            self.cells.append(nn.ModuleList(Cell(nf(s), down=d, width_mult_list=width_mult_list) for s, d in zip(scales, downs)))
+        def per(widths, make):
+            return nn.ModuleList([make(w) for w in widths])    # one copy per architecture (teacher / student)
 
         def cn(ci, co, k):
             return ConvNorm(ci, co, kernel_size=k, padding=1 if k == 3 else None, bias=False, groups=1, slimmable=False)
 
-        self.refine32 = nn.ModuleList([
-            nn.ModuleList([cn(nf(32, hr), nf(16, hr), 1), cn(nf(32, hr), nf(16, hr), 3), cn(nf(16, hr), nf(8, hr), 1),
-                           cn(nf(16, hr), nf(8, hr), 3)]) for _, hr in self._stem_head_width])
-        self.refine16 = nn.ModuleList([
-            nn.ModuleList([cn(nf(16, hr), nf(8, hr), 1), cn(nf(16, hr), nf(8, hr), 3)]) for _, hr in self._stem_head_width])
-        self.head0 = nn.ModuleList([Head(nf(8, hr), num_classes, False) for _, hr in self._stem_head_width])
-        self.head1 = nn.ModuleList([Head(nf(8, hr), num_classes, False) for _, hr in self._stem_head_width])
-        self.head2 = nn.ModuleList([Head(nf(8, hr), num_classes, False) for _, hr in self._stem_head_width])
-        self.head02 = nn.ModuleList([Head(nf(8, hr) * 2, num_classes, False) for _, hr in self._stem_head_width])
-        self.head12 = nn.ModuleList([Head(nf(8, hr) * 2, num_classes, False) for _, hr in self._stem_head_width])
+        self.stem = per(stem_widths, lambda w: nn.Sequential(
+            ConvNorm(3, nf(2, w) * 2, kernel_size=3, stride=2, padding=1, bias=False, groups=1, slimmable=False),
+            BasicResidual2x(nf(2, w) * 2, nf(4, w) * 2, kernel_size=3, stride=2, groups=1, slimmable=False),
+            BasicResidual2x(nf(4, w) * 2, nf(8, w), kernel_size=3, stride=2, groups=1, slimmable=False)))
+
+        self.__dict__["_nodes"] = _trellis(layers)
+        self.cells = nn.ModuleList(nn.ModuleList() for _ in range(layers))
+        for node in self._nodes:
+            # a cell has a down path unless it sits at the coarsest scale or in the last layer
+            has_down = node.scale < 2 and node.layer < max(layers - 1, 2)
+            self.cells[node.layer].append(Cell(nf(8 * 2 ** node.scale), down=has_down, width_mult_list=width_mult_list))
+
+        self.refine32 = per(head_widths, lambda w: nn.ModuleList([cn(nf(32, w), nf(16, w), 1), cn(nf(32, w), nf(16, w), 3),
+                                                                  cn(nf(16, w), nf(8, w), 1), cn(nf(16, w), nf(8, w), 3)]))
+        self.refine16 = per(head_widths, lambda w: nn.ModuleList([cn(nf(16, w), nf(8, w), 1), cn(nf(16, w), nf(8, w), 3)]))
+        for name, mult in (("head0", 1), ("head1", 1), ("head2", 1), ("head02", 2), ("head12", 2)):
+            setattr(self, name, per(head_widths, lambda w: Head(nf(8, w) * mult, num_classes, False)))
 
         # arch parameter names: {"alphas": [...], "betas": [...], "ratios": [...]} per architecture (teacher / student)
         self._arch_names = []
@@ -201,25 +225,20 @@ class Network_Multi_Path(nn.Module):
                 a.data.copy_(b.data)
         return model_new
 
+    # ---------------------------------------------------------------------------------------------------------
+    # width sampling
+    # ---------------------------------------------------------------------------------------------------------
     def sample_prun_ratio(self, mode="arch_ratio"):
         '''mode: "min"|"max"|"random"|"arch_ratio"(default)'''
         assert mode in ["min", "max", "random", "arch_ratio"]
-        counts = (self._layers - 1, self._layers - 1, self._layers - 2)
+        rows = (self._layers - 1, self._layers - 1, self._layers - 2)     # ratio rows per scale
         if mode == "arch_ratio":
-            names = self._arch_names[self.arch_idx]["ratios"]
-            out = []
-            for name, n in zip(names, counts):
-                param = getattr(self, name)
-                out.append([gumbel_softmax(F.log_softmax(param[layer], dim=-1), hard=True) for layer in range(n)])
-            return out
-        if mode == "min":
-            pick = lambda: self._width_mult_list[0]
-        elif mode == "max":
-            pick = lambda: self._width_mult_list[-1]
-        else:
-            pick = lambda: np.random.choice(self._width_mult_list)
-        # sampling order (scale 0 layers, then scale 1, then scale 2) matters for the shared numpy RNG stream
-        return [[pick() for _ in range(n)] for n in counts]
+            params = [getattr(self, name) for name in self._arch_names[self.arch_idx]["ratios"]]
+            return [[gumbel_softmax(F.log_softmax(p[row], dim=-1), hard=True) for row in range(n)] for p, n in zip(params, rows)]
+        choices = self._width_mult_list
+        draw = {"min": lambda: choices[0], "max": lambda: choices[-1], "random": lambda: np.random.choice(choices)}[mode]
+        # drawing order (all rows of scale 0, then scale 1, then scale 2) is part of the contract: shared numpy RNG stream
+        return [[draw() for _ in range(n)] for n in rows]
 
     def _arch(self, kind, i):
         return getattr(self, self._arch_names[self.arch_idx][kind][i])
@@ -237,143 +256,133 @@ class Network_Multi_Path(nn.Module):
             return (ratios[j][i - j - 1], ratios[j][i - j], ratios[j + 1][i - j])
         return (ratios[j][i - j], ratios[j][i - j + 1], ratios[j + 1][i - j])
 
-    def forward(self, input):
-        # out_prev: cell-state; index 0: keep; index 1: down
-        idx = self.arch_idx
-        stem, refine16, refine32 = self.stem[idx], self.refine16[idx], self.refine32[idx]
-        alphas = [F.softmax(self._arch("alphas", s), dim=-1) for s in range(3)]
-        betas = [None, F.softmax(self._arch("betas", 0), dim=-1), F.softmax(self._arch("betas", 1), dim=-1)]
-        # one host read instead of a GPU->CPU sync per `betas[...] > 0` test (model_search.py:326-329)
-        betas_pos = [None] + [(b.detach() > 0).tolist() for b in betas[1:]]
-        ratios = self.sample_prun_ratio(mode=self.prun_mode if self.prun_mode is not None else self._prun_modes[idx])
-
-        out_prev = [[stem(input), None]]  # stem: one cell
-        for i, cells in enumerate(self.cells):      # i: layer
-            out = []
-            for j, cell in enumerate(cells):        # j: scale
-                alpha = alphas[j][i - j]
-                ratio = self._ratio_triple(i, j, ratios)
-                if j == 0:
-                    out.append(cell(out_prev[0][0], alpha, ratio))
-                elif i == j:
-                    out.append(cell(out_prev[j - 1][1], alpha, ratio))
-                else:
-                    # the cell runs twice with the same weights: on the downsampled output of the scale above ("0: from
-                    # down") and on its own previous output ("1: from keep"); BN running stats see both, in this order
-                    out0 = down0 = out1 = down1 = None
-                    if betas_pos[j][i - j - 1][0]:
-                        out0, down0 = cell(out_prev[j - 1][1], alpha, ratio)
-                    if betas_pos[j][i - j - 1][1]:
-                        out1, down1 = cell(out_prev[j][0], alpha, ratio)
-                    brow = betas[j][i - j - 1]
-                    if out0 is None or out1 is None:  # a beta underflowed to 0: plain scaled term, like the reference's sum()
-                        keep = out1 if out0 is None else out0
-                        keepd = down1 if out0 is None else down0
-                        w = brow[1] if out0 is None else brow[0]
-                        out.append((_mix(torch.stack([w, w * 0]), keep, keep), 0 if keepd is None else _mix(torch.stack([w, w * 0]), keepd, keepd)))
-                    else:
-                        out.append((_mix(brow, out0, out1), _mix(brow, down0, down1) if down0 is not None else 0))
-            out_prev = out
-
-        up2 = lambda t: _resize2x(t)
-        out0 = out[0][0]
-        out1 = refine16[1](_cat([up2(refine16[0](out[1][0])), out[0][0]]))
-        out2 = refine32[1](_cat([up2(refine32[0](out[2][0])), out[1][0]]))
-        out2 = refine32[3](_cat([up2(refine32[2](out2)), out[0][0]]))
-
-        preds = [self.head0[idx](out0), self.head1[idx](out1), self.head2[idx](out2),
-                 self.head02[idx](_cat([out0, out2])), self.head12[idx](_cat([out1, out2]))]
-        if not self.training:
-            return tuple(_upsample8(p) for p in preds)
-        return tuple(_to_nchw(p) for p in preds)
-
-    def forward_latency(self, size, alpha=True, beta=True, ratio=True):
-        """Expected latency of the current architecture distribution from the per-op lookup table
-        (model_search.py:361-475): scalar arithmetic on the arch parameters' device."""
-        idx = self.arch_idx
-        stem = self.stem[idx]
+    def _distributions(self, alpha=True, beta=True):
+        """softmax of the architecture parameters, or uniform stand-ins (forward_latency's switches)"""
         dev = self._arch("alphas", 0).device
         if alpha:
             alphas = [F.softmax(self._arch("alphas", s), dim=-1) for s in range(3)]
         else:
             alphas = [torch.ones_like(self._arch("alphas", s)).to(dev) * 1. / len(PRIMITIVES) for s in range(3)]
         if beta:
-            betas = [None, F.softmax(self._arch("betas", 0), dim=-1), F.softmax(self._arch("betas", 1), dim=-1)]
+            betas = [None] + [F.softmax(self._arch("betas", s), dim=-1) for s in range(2)]
         else:
-            betas = [None, torch.ones_like(self._arch("betas", 0)).to(dev) * 1. / 2, torch.ones_like(self._arch("betas", 1)).to(dev) * 1. / 2]
-        if ratio:
-            ratios = self.sample_prun_ratio(mode=self.prun_mode if self.prun_mode is not None else self._prun_modes[idx])
-        else:
-            ratios = self.sample_prun_ratio(mode='max')
+            betas = [None] + [torch.ones_like(self._arch("betas", s)).to(dev) * 1. / 2 for s in range(2)]
+        return alphas, betas
 
-        stem_latency = 0
-        for op in stem:
-            latency, size = op.forward_latency(size)
-            stem_latency = stem_latency + latency
-        out_prev = [[size, None]]
-        latency_total = [[stem_latency, 0], [0, 0], [0, 0]]  # (out, down) per scale
+    def _current_mode(self):
+        return self.prun_mode if self.prun_mode is not None else self._prun_modes[self.arch_idx]
 
-        for i, cells in enumerate(self.cells):
-            out, latency = [], []
-            for j, cell in enumerate(cells):
-                out0 = out1 = down0 = down1 = None
-                a = alphas[j][i - j]
-                r = self._ratio_triple(i, j, ratios)
-                if j == 0:
-                    out1, down1 = cell.forward_latency(out_prev[0][0], a, r)
-                    out.append((out1[1], down1[1] if down1 is not None else None))
-                    latency.append([out1[0], down1[0] if down1 is not None else None])
-                elif i == j:
-                    out0, down0 = cell.forward_latency(out_prev[j - 1][1], a, r)
-                    out.append((out0[1], down0[1] if down0 is not None else None))
-                    latency.append([out0[0], down0[0] if down0 is not None else None])
+    # ---------------------------------------------------------------------------------------------------------
+    # execution
+    # ---------------------------------------------------------------------------------------------------------
+    def forward(self, input):
+        idx = self.arch_idx
+        refine16, refine32 = self.refine16[idx], self.refine32[idx]
+        alphas, betas = self._distributions()
+        # one host read instead of a GPU->CPU sync per `betas[...] > 0` test (model_search.py:326-329)
+        alive = [None] + [(b.detach() > 0).tolist() for b in betas[1:]]
+        ratios = self.sample_prun_ratio(mode=self._current_mode())
+
+        prev, cur, at_layer = {0: (self.stem[idx](input), None)}, {}, 0
+        for node in self._nodes:
+            if node.layer != at_layer:
+                prev, cur, at_layer = cur, {}, node.layer
+            cell = self.cells[node.layer][node.scale]
+            alpha = alphas[node.scale][node.layer - node.scale]
+            ratio = self._ratio_triple(node.layer, node.scale, ratios)
+            if node.beta_row is None:
+                (src, port), = node.feeds
+                cur[node.scale] = cell(prev[src][port], alpha, ratio)
+            else:
+                # same weights, two inputs ("0: from down", then "1: from keep"); BN running stats see both, in this order
+                flags = alive[node.scale][node.beta_row]
+                results = [cell(prev[src][port], alpha, ratio) if flags[n] else None for n, (src, port) in enumerate(node.feeds)]
+                cur[node.scale] = _blend(betas[node.scale][node.beta_row], results)
+        f8, f16, f32 = (cur[s][KEEP] for s in range(3))
+
+        out0 = f8
+        out1 = refine16[1](_cat([_resize2x(refine16[0](f16)), f8]))
+        out2 = refine32[1](_cat([_resize2x(refine32[0](f32)), f16]))
+        out2 = refine32[3](_cat([_resize2x(refine32[2](out2)), f8]))
+        preds = [self.head0[idx](out0), self.head1[idx](out1), self.head2[idx](out2),
+                 self.head02[idx](_cat([out0, out2])), self.head12[idx](_cat([out1, out2]))]
+        leave = _to_nchw if self.training else _upsample8
+        return tuple(leave(p) for p in preds)
+
+    def forward_latency(self, size, alpha=True, beta=True, ratio=True):
+        """Expected latency of the current architecture distribution from the per-op lookup table
+        (model_search.py:361-475): scalar arithmetic on the arch parameters' device.  The recurrences below reproduce the
+        reference's, including which beta row weights the running totals (see `pending`)."""
+        alphas, betas = self._distributions(alpha, beta)
+        ratios = self.sample_prun_ratio(mode=self._current_mode() if ratio else 'max')
+
+        stem_ms = 0
+        for block in self.stem[self.arch_idx]:
+            ms, size = block.forward_latency(size)
+            stem_ms = stem_ms + ms
+        total = [[stem_ms, 0], [0, 0], [0, 0]]            # expected latency up to (scale, KEEP | DOWN)
+        prev, cur, pending, at_layer = {0: (size, None)}, {}, [], 0
+
+        def settle(layer, pending):
+            """fold the per-cell latencies of one finished layer into the running totals"""
+            coarsest = len(pending) - 1
+            for scale, ms in enumerate(pending):
+                if scale == 0:
+                    if ms[KEEP] is not None: total[0][KEEP] = total[0][KEEP] + ms[KEEP]
+                    if ms[DOWN] is not None: total[0][DOWN] = total[0][KEEP] + ms[DOWN]
+                elif layer == scale:
+                    if ms[KEEP] is not None: total[scale][KEEP] = total[scale - 1][DOWN] + ms[KEEP]
+                    if ms[DOWN] is not None: total[scale][DOWN] = total[scale - 1][DOWN] + ms[DOWN]
                 else:
-                    if betas[j][i - j - 1][0] > 0:
-                        out0, down0 = cell.forward_latency(out_prev[j - 1][1], a, r)
-                    if betas[j][i - j - 1][1] > 0:
-                        out1, down1 = cell.forward_latency(out_prev[j][0], a, r)
-                    assert (out0 is None and out1 is None) or out0[1] == out1[1]
-                    assert (down0 is None and down1 is None) or down0[1] == down1[1]
-                    out.append((out0[1], down0[1] if down0 is not None else None))
-                    b = betas[j][i - j - 1]
-                    latency.append([
-                        sum(w * o for w, o in zip(b, [out0[0], out1[0]])),
-                        sum(w * d if d is not None else 0 for w, d in zip(b, [down0[0] if down0 is not None else None,
-                                                                             down1[0] if down1 is not None else None]))])
-            out_prev = out
-            for ii, lat in enumerate(latency):
-                # layer: i | scale: ii   (kept quirk: the beta row below is indexed with the LAST j of the loop above)
-                if ii == 0:
-                    if lat[0] is not None: latency_total[ii][0] = latency_total[ii][0] + lat[0]
-                    if lat[1] is not None: latency_total[ii][1] = latency_total[ii][0] + lat[1]
-                elif i == ii:
-                    if lat[0] is not None: latency_total[ii][0] = latency_total[ii - 1][1] + lat[0]
-                    if lat[1] is not None: latency_total[ii][1] = latency_total[ii - 1][1] + lat[1]
-                else:
-                    b = betas[j][i - j - 1]
-                    if lat[0] is not None: latency_total[ii][0] = b[1] * latency_total[ii][0] + b[0] * latency_total[ii - 1][1] + lat[0]
-                    if lat[1] is not None: latency_total[ii][1] = b[1] * latency_total[ii][0] + b[0] * latency_total[ii - 1][1] + lat[1]
-        return sum([latency_total[0][0], latency_total[1][0], latency_total[2][0]])
+                    # kept quirk: the mixing row is the one of the layer's COARSEST cell, for every scale of the layer
+                    b = betas[coarsest][layer - coarsest - 1]
+                    if ms[KEEP] is not None:
+                        total[scale][KEEP] = b[1] * total[scale][KEEP] + b[0] * total[scale - 1][DOWN] + ms[KEEP]
+                    if ms[DOWN] is not None:
+                        total[scale][DOWN] = b[1] * total[scale][KEEP] + b[0] * total[scale - 1][DOWN] + ms[DOWN]
+
+        for node in self._nodes:
+            if node.layer != at_layer:
+                settle(at_layer, pending)
+                prev, cur, pending, at_layer = cur, {}, [], node.layer
+            cell = self.cells[node.layer][node.scale]
+            a = alphas[node.scale][node.layer - node.scale]
+            r = self._ratio_triple(node.layer, node.scale, ratios)
+            if node.beta_row is None:
+                (src, port), = node.feeds
+                keep, down = cell.forward_latency(prev[src][port], a, r)
+                cur[node.scale] = (keep[1], down[1] if down is not None else None)
+                pending.append([keep[0], down[0] if down is not None else None])
+            else:
+                b = betas[node.scale][node.beta_row]
+                runs = [cell.forward_latency(prev[src][port], a, r) if b[n] > 0 else (None, None)
+                        for n, (src, port) in enumerate(node.feeds)]
+                (keep0, down0), (keep1, down1) = runs
+                assert (keep0 is None and keep1 is None) or keep0[1] == keep1[1]
+                assert (down0 is None and down1 is None) or down0[1] == down1[1]
+                cur[node.scale] = (keep0[1], down0[1] if down0 is not None else None)
+                pending.append([sum(w * k for w, k in zip(b, [keep0[0], keep1[0]])),
+                                sum(w * d if d is not None else 0
+                                    for w, d in zip(b, [None if down0 is None else down0[0], None if down1 is None else down1[0]]))])
+        settle(at_layer, pending)
+        return sum([total[0][KEEP], total[1][KEEP], total[2][KEEP]])
 
     def _loss(self, input, target, pretrain=False):
-        loss = 0
+        """Sum of the criterion over the 5 logits of every pass (model_search.py:478-505): search = one pass per architecture
+        with its own width mode, plus max / min width; pretrain = max, min and two random-width passes."""
+        passes = []   # (architecture to switch to | None = leave as is, width mode)
         if pretrain is not True:
-            # "random width": sampled by gumbel softmax
-            self.prun_mode = None
-            for idx in range(len(self._arch_names)):
-                self.arch_idx = idx
-                logits = self(input)
-                loss = loss + sum(self._criterion(logit, target) for logit in logits)
+            passes += [(idx, None) for idx in range(len(self._arch_names))]   # "random width": sampled by gumbel softmax
         if len(self._width_mult_list) > 1:
-            modes = ["max", "min"] + (["random", "random"] if pretrain == True else [])
-            for mode in modes:
-                self.prun_mode = mode
-                logits = self(input)
-                loss = loss + sum(self._criterion(logit, target) for logit in logits)
-        elif pretrain == True and len(self._width_mult_list) == 1:
-            self.prun_mode = "max"
-            logits = self(input)
-            loss = loss + sum(self._criterion(logit, target) for logit in logits)
+            passes += [(None, mode) for mode in ["max", "min"] + (["random", "random"] if pretrain == True else [])]  # noqa: E712
+        elif pretrain == True and len(self._width_mult_list) == 1:  # noqa: E712
+            passes.append((None, "max"))
+        loss = 0
+        for arch, mode in passes:
+            if arch is not None:
+                self.arch_idx = arch
+            self.prun_mode = mode
+            loss = loss + sum(self._criterion(logit, target) for logit in self(input))
         return loss
 
     def _arch_shapes(self, idx):
