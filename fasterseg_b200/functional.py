@@ -234,33 +234,49 @@ def affine_act(x, scale, shift, relu=False, out=None):
 # ----------------------------------------------------------------------------------------------
 # backward / training wrappers (kernels in csrc/train.cu)
 # ----------------------------------------------------------------------------------------------
-def bn_bwd(dy, y, raw, mean, invstd, gamma, count, relu, gscale, want_param_grads=True, allreduce=None):
-    """BatchNorm(+ReLU) backward -> (draw, dgamma, dbeta).  `allreduce(sums)` hook = SyncBN backward."""
+def bn_bwd_sums(dy, y, raw, mean, invstd, relu):
+    """First pass of the BatchNorm(+ReLU) backward: fp32 [2C] = per-channel (sum dz | sum dz * xhat), dz = dy masked by y > 0."""
     N, Cc, H, W, dcs = nhwc_info(dy)
     _, _, _, _, rcs = nhwc_info(raw, raw.dtype)
     rf32 = int(raw.dtype == torch.float32)
     ycs = nhwc_info(y)[4] if relu else 0
-    pixels = N * H * W
     sums = torch.zeros(2 * Cc, device=dy.device, dtype=torch.float32)
-    check(_lib.lib().fsb_bn_bwd_reduce(pixels, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
+    check(_lib.lib().fsb_bn_bwd_reduce(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                        _ptr(invstd), int(relu), _ptr(sums), _stream()), "fsb_bn_bwd_reduce")
-    local_dg = local_db = None
-    if allreduce is not None:
-        # SyncBN: dx needs the GLOBAL sums, but gamma/beta gradients must stay LOCAL sums -- the data-parallel gradient average
-        # (parallel.GradSync) divides every parameter gradient by the world size afterwards, like DDP + torch SyncBatchNorm
-        if want_param_grads:
-            local_db = sums[:Cc] / gscale
-            local_dg = sums[Cc:] / gscale
-        sums = allreduce(sums.clone() if want_param_grads else sums)
+    return sums
+
+
+def bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads=True):
+    """Second pass: draw = gamma * invstd * (dz - sums[:C] / count - xhat * sums[C:] / count) as fp16 NHWC, and (when asked)
+    dgamma = sums[C:] / gscale, dbeta = sums[:C] / gscale written by the same kernel."""
+    N, Cc, H, W, dcs = nhwc_info(dy)
+    _, _, _, _, rcs = nhwc_info(raw, raw.dtype)
+    rf32 = int(raw.dtype == torch.float32)
+    ycs = nhwc_info(y)[4] if relu else 0
     draw = empty_nhwc(N, Cc, H, W, dy.device)
-    fused_pg = want_param_grads and allreduce is None
-    dg = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if fused_pg else None
-    db = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if fused_pg else None
-    check(_lib.lib().fsb_bn_bwd_apply(pixels, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
+    dg = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    db = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    check(_lib.lib().fsb_bn_bwd_apply(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                       _ptr(invstd), _ptr(gamma), _ptr(sums), float(count), int(relu), _ptr(draw),
                                       nhwc_info(draw)[4], _ptr(dg), _ptr(db), float(gscale), _stream()), "fsb_bn_bwd_apply")
-    if local_dg is not None:
-        dg, db = local_dg, local_db
+    return draw, dg, db
+
+
+def bn_bwd(dy, y, raw, mean, invstd, gamma, count, relu, gscale, want_param_grads=True, allreduce=None):
+    """BatchNorm(+ReLU) backward -> (draw, dgamma, dbeta).  `allreduce(sums)` hook = SyncBN backward, `count` then being the
+    GLOBAL number of pixels per channel."""
+    Cc = dy.shape[1]
+    sums = bn_bwd_sums(dy, y, raw, mean, invstd, relu)
+    if allreduce is None:
+        return bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads)
+    # SyncBN: dx needs the GLOBAL sums, but gamma/beta gradients must stay LOCAL sums -- the data-parallel gradient average
+    # (parallel.GradSync) divides every parameter gradient by the world size afterwards, like DDP + torch SyncBatchNorm
+    dg = db = None
+    if want_param_grads:
+        db = sums[:Cc] / gscale
+        dg = sums[Cc:] / gscale
+    sums = allreduce(sums.clone() if want_param_grads else sums)
+    draw, _, _ = bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads=False)
     return draw, dg, db
 
 

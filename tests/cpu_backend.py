@@ -188,22 +188,29 @@ def affine_act(x, scale, shift, relu=False, out=None):
     return _put(out, y)
 
 
-def bn_bwd(dy, y, raw, mean, invstd, gamma, count, relu, gscale, want_param_grads=True, allreduce=None):
-    N, Cc, H, W, _ = nhwc_info(dy)
+def _dz_xhat(dy, y, raw, mean, invstd, relu):
     dz = dy.float()
     if relu:
         dz = dz * (y.float() > 0)
     v = lambda t: t.detach().float().view(1, -1, 1, 1)
-    xhat = (raw.float() - v(mean)) * v(invstd)
-    sums = torch.cat([dz.sum((0, 2, 3)), (dz * xhat).sum((0, 2, 3))])
-    local = sums.clone()
-    if allreduce is not None:
-        sums = allreduce(sums)
+    return dz, (raw.float() - v(mean)) * v(invstd)
+
+
+def bn_bwd_sums(dy, y, raw, mean, invstd, relu):
+    nhwc_info(dy)
+    dz, xhat = _dz_xhat(dy, y, raw, mean, invstd, relu)
+    return torch.cat([dz.sum((0, 2, 3)), (dz * xhat).sum((0, 2, 3))])
+
+
+def bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads=True):
+    N, Cc, H, W, _ = nhwc_info(dy)
+    dz, xhat = _dz_xhat(dy, y, raw, mean, invstd, relu)
+    v = lambda t: t.detach().float().view(1, -1, 1, 1)
     draw = v(gamma) * v(invstd) * (dz - v(sums[:Cc]) / count - xhat * v(sums[Cc:]) / count)
     out = _put(_empty(N, Cc, H, W, dy.device), draw)
     if not want_param_grads:
         return out, None, None
-    return out, local[Cc:] / gscale, local[:Cc] / gscale
+    return out, sums[Cc:] / gscale, sums[:Cc] / gscale
 
 
 def relu_bwd(dy, y):
@@ -304,7 +311,8 @@ def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta
 def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale):
     N, Cout, Ho, Wo, _ = nhwc_info(dy)
     mean, invstd = vec[4 * Cout:5 * Cout], vec[5 * Cout:6 * Cout]
-    draw, dg, db = bn_bwd(dy, y, raw, mean, invstd, gamma, N * Ho * Wo, relu, gscale)
+    sums = bn_bwd_sums(dy, y, raw, mean, invstd, relu)
+    draw, dg, db = bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, N * Ho * Wo, relu, gscale)
     off = (d.off_h, d.off_w)
     dx = conv_dgrad(draw, w, (N, d.Cin, d.H, d.W), d.Cin, Cout, d.ksize, d.stride, d.pad, off=off) if need_dx else None
     if dw_accum is not None:
@@ -313,7 +321,7 @@ def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need
 
 
 _PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold", "conv_fwd", "stem_conv_nchw", "bilinear",
-            "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd", "relu_bwd",
+            "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd_sums", "bn_bwd_apply", "relu_bwd",
             "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
             "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd")
 
