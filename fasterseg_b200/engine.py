@@ -24,11 +24,12 @@ def packed_weight(conv: nn.Conv2d, ci: int, co: int) -> torch.Tensor:
     """fp16 packed copy of conv.weight[:co, :ci] (USConv2d slice, slimmable_ops.py:42), cached."""
     cache = conv.__dict__.setdefault("_fsb_wcache", {})
     key = (ci, co)
-    ver = _versions(conv.weight)
+    weight = conv.weight
+    ver = (weight._version, weight.data_ptr())
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
-    w = conv.weight.detach()
+    w = weight.detach()
     if w.dtype != torch.float32:
         w = w.float()
     packed = F_.pack_conv_weight(w, ci, co, conv.kernel_size[0])

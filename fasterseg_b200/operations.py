@@ -96,7 +96,7 @@ class _Primitive(nn.Module):
 
     def _set_pairs(self, ratio, convs_bns):
         assert len(ratio) == 2
-        self.ratio = ratio
+        self.__dict__["ratio"] = ratio   # plain attribute on the per-step hot path: bypass nn.Module.__setattr__
         first = True
         for conv, bn in convs_bns:
             conv.set_ratio(ratio if first else (ratio[1], ratio[1]))
@@ -127,7 +127,7 @@ class ConvNorm(_Primitive):
     def set_ratio(self, ratio):
         assert self.slimmable
         assert len(ratio) == 2
-        self.ratio = ratio
+        self.__dict__["ratio"] = ratio
         self.conv[0].set_ratio(ratio)
         self.conv[1].set_ratio(ratio[1])
 
@@ -292,7 +292,7 @@ class FactorizedReduce(_Primitive):
 
     def set_ratio(self, ratio):
         assert len(ratio) == 2
-        self.ratio = ratio
+        self.__dict__["ratio"] = ratio
         if self.stride == 1:
             self.conv1.set_ratio(ratio)
             self.bn.set_ratio(ratio[1])

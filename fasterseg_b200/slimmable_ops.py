@@ -28,7 +28,8 @@ class _WidthSwitch:
     against the module's `width_mult_list` at use time (the reference asserts inside forward)."""
 
     def set_ratio(self, ratio):
-        self.ratio = ratio
+        # plain attribute, written ~20 k times per supernet step: skip nn.Module.__setattr__'s Parameter / Module bookkeeping
+        self.__dict__["ratio"] = ratio
 
     def _checked(self, fraction):
         assert fraction in self.width_mult_list, str(fraction) + " in? " + str(self.width_mult_list)
@@ -50,11 +51,17 @@ class USConv2d(_WidthSwitch, nn.Conv2d):
     def _resolve_channels(self):
         """(c_in, c_out) for the current ratio.  Like the reference's forward this also overwrites `in_channels`,
         `out_channels` and `groups`, which callers (and thop's counters) read afterwards."""
-        fractions = [self._checked(r) for r in self.ratio]
-        active = [make_divisible(full * r) for full, r in zip((self.in_channels_max, self.out_channels_max), fractions)]
-        self.in_channels, self.out_channels = active
-        self.groups = active[0] if self.depthwise else 1
-        return tuple(active)
+        ratio = self.ratio if type(self.ratio) is tuple else tuple(self.ratio)
+        known = self.__dict__.setdefault("_corner_cache", {})
+        active = known.get(ratio)
+        if active is None:
+            fractions = [self._checked(r) for r in ratio]
+            active = tuple(make_divisible(full * r) for full, r in zip((self.in_channels_max, self.out_channels_max), fractions))
+            known[ratio] = active
+        state = self.__dict__     # in_channels / out_channels / groups are plain attributes of nn.Conv2d
+        state["in_channels"], state["out_channels"] = active
+        state["groups"] = active[0] if self.depthwise else 1
+        return active
 
     def forward(self, input):
         return engine.conv_bn_act(input, self, None, relu=False)
