@@ -28,21 +28,31 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device(t: torch.Tensor) -> bool:
+    """Every tensor handed to the library must live on the GPU (there is no CPU path).  One predicate, so that the host-side
+    tests can run the wrappers' marshalling against a fake library with CPU tensors (tests/test_marshalling_cpu.py)."""
+    return t.is_cuda
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
 def empty_nhwc(N, Cc, H, W, device, dtype=torch.float16) -> torch.Tensor:
     """(N, C, H, W)-shaped view of a fresh NHWC buffer; the pixel stride is rounded up to 8 channels so that
-    every pixel starts on a 16-byte boundary (vector stores, TMA strides)."""
+    every pixel starts on a 16-byte boundary (vector stores, TMA strides).  Called ~15 k times per supernet step:
+    when no padding is needed the strided tensor is created in ONE torch call (no permute / slice objects)."""
     cpad = (Cc + 7) // 8 * 8
-    buf = torch.empty((N, H, W, cpad), device=device, dtype=dtype).permute(0, 3, 1, 2)
-    return buf if cpad == Cc else buf[:, :Cc]
+    if cpad == Cc:
+        return torch.empty_strided((N, Cc, H, W), (H * W * Cc, 1, W * Cc, Cc), device=device, dtype=dtype)
+    # padded: allocate the full (N, H, W, cpad) block -- the pad lanes of the last pixel must belong to the allocation,
+    # vector stores touch them -- and hand out the first Cc channels
+    return torch.empty((N, H, W, cpad), device=device, dtype=dtype).permute(0, 3, 1, 2)[:, :Cc]
 
 
 def nhwc_info(t: torch.Tensor, dtype=torch.float16) -> Tuple[int, int, int, int, int]:
     """-> (N, C, H, W, channel_stride); raises unless `t` is a channels-last addressable CUDA tensor of `dtype`."""
-    if t.dtype != dtype or t.dim() != 4 or not t.is_cuda:
+    if t.dtype != dtype or t.dim() != 4 or not _on_device(t):
         raise ValueError("expected a 4-D CUDA %s tensor, got %s %s" % (dtype, t.dtype, tuple(t.shape)))
     N, Cc, H, W = t.shape
     sn, sc, sh, sw = t.stride()
@@ -68,7 +78,7 @@ def to_nhwc_half(x: torch.Tensor) -> torch.Tensor:
     """Reference-layout tensor (NCHW fp32/fp16 contiguous) -> NHWC fp16 via our layout kernel."""
     if is_nhwc_half(x):
         return x
-    if x.dim() != 4 or not x.is_cuda or x.dtype not in (torch.float32, torch.float16):
+    if x.dim() != 4 or not _on_device(x) or x.dtype not in (torch.float32, torch.float16):
         raise ValueError("expected a CUDA NCHW fp32/fp16 tensor")
     x = x.contiguous()
     N, Cc, H, W = x.shape
@@ -103,7 +113,7 @@ def make_conv_desc(N, H, W, Cin, Cout, ksize, stride, pad, x_cstride, y_cstride,
 
 def pack_conv_weight(w: torch.Tensor, Cin: int, Cout: int, ksize: int) -> torch.Tensor:
     """fp32 OIHW master weight (possibly max-width; only [:Cout, :Cin] is read) -> packed fp16 buffer."""
-    assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] == ksize and w.shape[3] == ksize
+    assert _on_device(w) and w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] == ksize and w.shape[3] == ksize
     assert w.stride(3) == 1 and w.stride(2) == ksize
     d = ConvDesc(1, 8, 8, Cin, Cout, ksize, 1, 0, 1, 0, 0, 8, 8, Cin, Cout, 0)
     nbytes = _lib.lib().fsb_conv_packed_bytes(C.byref(d))
@@ -147,7 +157,7 @@ def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=
 
 def stem_conv_nchw(x, w, scale, shift, relu=True, out=None):
     """3x3 s2 p1 RGB stem on the caller's NCHW fp32/fp16 tensor."""
-    assert x.dim() == 4 and x.shape[1] == 3 and x.is_cuda and x.is_contiguous()
+    assert x.dim() == 4 and x.shape[1] == 3 and _on_device(x) and x.is_contiguous()
     assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (3, 3, 3)
     N, _, H, W = x.shape
     Cout = w.shape[0]
@@ -405,8 +415,8 @@ def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta
     Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
     cpad = (Cout + 7) // 8 * 8
     dev = x.device
-    raw = torch.empty((N, Ho, Wo, cpad), device=dev, dtype=torch.float32)
-    y = torch.empty((N, Ho, Wo, cpad), device=dev, dtype=torch.float16)
+    raw = empty_nhwc(N, Cout, Ho, Wo, dev, torch.float32)    # views at offset 0 of their buffers, pixel stride cpad
+    y = empty_nhwc(N, Cout, Ho, Wo, dev)
     vec = torch.empty(6 * Cout, device=dev, dtype=torch.float32)
     d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, cpad, 0)
     check(_lib.lib().fsb_conv_bn_act_train_fwd(C.byref(d), x.data_ptr(), wpacked.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
@@ -416,11 +426,7 @@ def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta
                                                None if num_batches_tracked is None else num_batches_tracked.data_ptr(),
                                                raw.data_ptr(), cpad, y.data_ptr(), cpad, vec.data_ptr(), int(relu), _stream()),
           "fsb_conv_bn_act_train_fwd")
-    yv = y.permute(0, 3, 1, 2)
-    rv = raw.permute(0, 3, 1, 2)
-    if cpad != Cout:
-        yv, rv = yv[:, :Cout], rv[:, :Cout]
-    return yv, rv, vec, d
+    return y, raw, vec, d
 
 
 def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale):
@@ -428,17 +434,14 @@ def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need
     N, Cout, Ho, Wo, dcs = nhwc_info(dy)
     dev = dy.device
     cpad = d.y_cstride
-    draw = torch.empty((N, Ho, Wo, cpad), device=dev, dtype=torch.float16)
+    draw = empty_nhwc(N, Cout, Ho, Wo, dev)
+    assert draw.stride(3) == cpad
     vb = torch.empty(4 * Cout, device=dev, dtype=torch.float32)
     dx = None
     xcs = 0
     if need_dx:
-        cin_pad = (d.Cin + 7) // 8 * 8
-        dxb = torch.empty((N, d.H, d.W, cin_pad), device=dev, dtype=torch.float16)
-        dx = dxb.permute(0, 3, 1, 2)
-        if cin_pad != d.Cin:
-            dx = dx[:, :d.Cin]
-        xcs = cin_pad
+        dx = empty_nhwc(N, d.Cin, d.H, d.W, dev)
+        xcs = dx.stride(3)
     check(_lib.lib().fsb_conv_bn_act_train_bwd(C.byref(d), x.data_ptr(), dy.data_ptr(), dcs, y.data_ptr(), y.stride(3), raw.data_ptr(),
                                                raw.stride(3), vec.data_ptr(), gamma.data_ptr(), int(relu),
                                                None if wpacked_t is None else wpacked_t.data_ptr(), w.data_ptr(), w.stride(0),

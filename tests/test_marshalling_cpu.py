@@ -1,0 +1,227 @@
+"""The ctypes boundary without a GPU: every tensor-level wrapper of `fasterseg_b200.functional` is driven with CPU tensors
+against a FAKE library whose entry points are `ctypes.CFUNCTYPE` callbacks built from the same signature table the real
+binding uses (`_lib._SIGS`).  ctypes therefore converts / type-checks every argument exactly as it would for libfsb200.so
+(wrong arity, a float where the header has an int, a tensor instead of a pointer -> the call raises), and the callbacks
+record what arrived, so the tests can assert that descriptors, pointers, channel strides, counts and flags are the ones the
+tensors imply.  No arithmetic happens; outputs are whatever `torch.empty` returned."""
+import ctypes as C
+
+import pytest
+import torch
+
+from fasterseg_b200 import _lib
+from fasterseg_b200 import functional as F_
+from tests import cpu_backend
+
+
+class FakeLib:
+    def __init__(self):
+        self.calls = []
+        self._keep = []
+        for name, (res, args) in _lib._SIGS.items():
+            proto = C.CFUNCTYPE(res, *args)
+
+            def recorder(*a, _name=name, _res=res):
+                vals = []
+                for v in a:
+                    if isinstance(v, C.POINTER(_lib.ConvDesc)):
+                        d = v.contents
+                        vals.append({f: getattr(d, f) for f, _ in _lib.ConvDesc._fields_})
+                    else:
+                        vals.append(v)
+                self.calls.append((_name, vals))
+                if _name in ("fsb_conv_packed_bytes", "fsb_conv_packed_dgrad_bytes"):
+                    return 4096
+                if _name == "fsb_abi_version":
+                    return 1
+                return None if _res is C.c_char_p else 0
+
+            cb = proto(recorder)
+            self._keep.append(cb)
+            setattr(self, name, cb)
+
+    def last(self, name):
+        for n, vals in reversed(self.calls):
+            if n == name:
+                return vals
+        raise AssertionError("%s was not called; calls: %s" % (name, [n for n, _ in self.calls]))
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    lib = FakeLib()
+    monkeypatch.setattr(_lib, "lib", lambda: lib)
+    monkeypatch.setattr(F_, "_stream", lambda: 0)
+    monkeypatch.setattr(F_, "_on_device", lambda t: True)         # the product insists on CUDA tensors; everything else is real
+    return lib
+
+
+def act(N, C_, H, W, dtype=torch.float16, wide=0):
+    """NHWC activation view; `wide` extra channels make it a slice of a wider (concat) buffer"""
+    t = F_.empty_nhwc(N, C_ + wide, H, W, "cpu", dtype=dtype)
+    return t[:, :C_] if wide else t
+
+
+def test_empty_nhwc_layout():
+    for C_ in (19, 32, 1, 8):
+        t = F_.empty_nhwc(2, C_, 5, 7, "cpu")
+        N, Cc, H, W, cs = cpu_backend.nhwc_info(t)
+        assert (N, Cc, H, W) == (2, C_, 5, 7) and cs == (C_ + 7) // 8 * 8 and t.dtype == torch.float16
+        assert t.stride() == (5 * 7 * cs, 1, 7 * cs, cs)
+        # the padded lanes of the LAST pixel belong to the allocation too (vector stores touch them)
+        assert t.untyped_storage().nbytes() >= 2 * 5 * 7 * cs * 2
+
+
+def test_conv_fwd_marshalling(fake):
+    x = act(2, 32, 12, 20, wide=16)
+    wp = torch.empty(2048, dtype=torch.float16)
+    scale, shift = torch.empty(24), torch.empty(24)
+    out = act(2, 24, 6, 10, wide=8)
+    y = F_.conv_fwd(x, wp, 24, 3, 2, 1, scale, shift, relu=True, out=out)
+    d, px, pw, ps, psh, py, pst, stream = fake.last("fsb_conv_fwd")
+    assert y is out
+    assert (d["N"], d["H"], d["W"], d["Cin"], d["Cout"], d["ksize"], d["stride"], d["pad"], d["Ho"], d["Wo"]) == (2, 12, 20, 32, 24, 3, 2, 1, 6, 10)
+    assert d["x_cstride"] == 48 and d["y_cstride"] == 32
+    assert d["flags"] == _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE
+    assert (px, pw, ps, psh, py, pst) == (x.data_ptr(), wp.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(), None)
+    # training flavour: fp32 raw output + statistics, shifted origin (FactorizedReduce's second conv)
+    stats = torch.zeros(48)
+    raw = F_.conv_fwd(x, wp, 24, 1, 2, 0, off=(1, 1), stats=stats, out_f32=True)
+    d, _, _, ps, psh, py, pst, _ = fake.last("fsb_conv_fwd")
+    assert raw.dtype == torch.float32 and tuple(raw.shape) == (2, 24, 6, 10)
+    assert (d["off_h"], d["off_w"], d["Ho"], d["Wo"]) == (1, 1, 6, 10)
+    assert d["flags"] == _lib.FSB_CONV_STATS | _lib.FSB_CONV_OUT_F32 and (ps, psh) == (None, None)
+    assert (py, pst) == (raw.data_ptr(), stats.data_ptr()) and d["y_cstride"] == raw.stride(3)
+
+
+def test_fused_training_unit_marshalling(fake):
+    x = act(2, 32, 12, 20)
+    wp = torch.empty(2048, dtype=torch.float16)
+    gamma, beta, rm, rv = torch.empty(20), torch.empty(20), torch.empty(20), torch.empty(20)
+    nbt = torch.zeros((), dtype=torch.int64)
+    y, raw, vec, d = F_.conv_bn_act_train_fwd(x, wp, 20, 3, 1, 1, (0, 0), gamma, beta, 1e-5, 0.1, rm, rv, nbt, True)
+    a = fake.last("fsb_conv_bn_act_train_fwd")
+    desc = a[0]
+    assert (desc["N"], desc["Cin"], desc["Cout"], desc["Ho"], desc["Wo"], desc["x_cstride"], desc["y_cstride"]) == (2, 32, 20, 12, 20, 32, 24)
+    assert a[1:5] == [x.data_ptr(), wp.data_ptr(), gamma.data_ptr(), beta.data_ptr()]
+    assert a[5] == pytest.approx(1e-5) and a[6] == pytest.approx(0.1)
+    assert a[7:10] == [rm.data_ptr(), rv.data_ptr(), nbt.data_ptr()]
+    assert a[10] == raw.data_ptr() and a[11] == raw.stride(3) == 24 and raw.dtype == torch.float32
+    assert a[12] == y.data_ptr() and a[13] == y.stride(3) == 24 and y.dtype == torch.float16
+    assert a[14] == vec.data_ptr() and vec.numel() == 6 * 20 and a[15] == 1
+    assert tuple(y.shape) == tuple(raw.shape) == (2, 20, 12, 20)
+    cpu_backend.nhwc_info(y), cpu_backend.nhwc_info(raw, torch.float32)
+    # backward
+    dy = act(2, 20, 12, 20)
+    w = torch.empty(40, 48, 3, 3)[:20, :32]            # active corner of a max-width master weight
+    wt = torch.empty(2048, dtype=torch.float16)
+    acc = torch.zeros(40, 48, 3, 3)
+    dx, dg, db = F_.conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, True, wt, w, True, acc, 1024.0)
+    b = fake.last("fsb_conv_bn_act_train_bwd")
+    assert b[1:4] == [x.data_ptr(), dy.data_ptr(), dy.stride(3)]
+    assert b[4:8] == [y.data_ptr(), y.stride(3), raw.data_ptr(), raw.stride(3)]
+    assert b[8:11] == [vec.data_ptr(), gamma.data_ptr(), 1]
+    assert b[11:15] == [wt.data_ptr(), w.data_ptr(), w.stride(0), w.stride(1)] and (w.stride(0), w.stride(1)) == (48 * 9, 9)
+    assert b[16] == 24 and b[15] is not None and b[17] is not None        # draw (stride = padded Cout) and the 4C scratch vector
+    assert tuple(dx.shape) == (2, 32, 12, 20) and b[18] == dx.data_ptr() and b[19] == dx.stride(3)
+    assert b[20] == acc.data_ptr() and b[21] == pytest.approx(1024.0)
+    assert dg.numel() == db.numel() == 20 and dg.data_ptr() != db.data_ptr()
+    # no dx wanted (first layer): null pointer, no allocation
+    dx, _, _ = F_.conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, True, None, w, False, acc, 1024.0)
+    b = fake.last("fsb_conv_bn_act_train_bwd")
+    assert dx is None and b[18] is None and b[11] is None
+
+
+def test_bn_backward_marshalling(fake):
+    dy, y = act(2, 24, 6, 10), act(2, 24, 6, 10)
+    raw = act(2, 24, 6, 10, dtype=torch.float32)
+    mean, invstd, gamma = torch.empty(24), torch.empty(24), torch.empty(24)
+    draw, dg, db = F_.bn_bwd(dy, y, raw, mean, invstd, gamma, 120, True, 1024.0)
+    r = fake.last("fsb_bn_bwd_reduce")
+    assert r[0] == 2 * 6 * 10 and r[1] == 24 and r[2] == dy.data_ptr() and r[4] == y.data_ptr() and r[6] == raw.data_ptr()
+    assert r[8] == 1 and r[11] == 1      # raw is fp32, relu mask on
+    a = fake.last("fsb_bn_bwd_apply")
+    assert a[12] == r[12] and a[13] == pytest.approx(120.0)   # same sums buffer, count
+    assert a[15] == draw.data_ptr() and a[17] == dg.data_ptr() and a[18] == db.data_ptr()
+    # SyncBN composition: the apply kernel gets the all-reduced buffer and no gamma/beta outputs
+    seen = {}
+
+    def allreduce(s):
+        seen["in"] = s
+        return s
+    draw, dg, db = F_.bn_bwd(dy, y, raw, mean, invstd, gamma, 240, True, 1024.0, allreduce=allreduce)
+    a = fake.last("fsb_bn_bwd_apply")
+    assert a[12] == seen["in"].data_ptr() and a[17] is None and a[18] is None and a[13] == pytest.approx(240.0)
+    assert dg.numel() == db.numel() == 24
+
+
+def test_conv_backward_marshalling(fake):
+    dy = act(2, 24, 6, 10)
+    w = torch.empty(40, 48, 3, 3)[:24, :32]
+    wt = torch.empty(2048, dtype=torch.float16)
+    dx = F_.conv_dgrad(dy, w, (2, 32, 12, 20), 32, 24, 3, 2, 1, wpacked_t=wt)
+    a = fake.last("fsb_conv_dgrad")
+    assert (a[0]["H"], a[0]["W"], a[0]["Ho"], a[0]["Wo"], a[0]["stride"]) == (12, 20, 6, 10, 2)
+    assert a[1:3] == [dy.data_ptr(), dy.stride(3)] and a[3] == wt.data_ptr() and a[4:7] == [w.data_ptr(), 48 * 9, 9]
+    assert a[7:9] == [dx.data_ptr(), dx.stride(3)] and tuple(dx.shape) == (2, 32, 12, 20)
+    x = act(2, 32, 12, 20)
+    acc = torch.zeros(40, 48, 3, 3)
+    F_.conv_wgrad(x, dy, acc, 32, 24, 3, 2, 1, 1024.0, accumulate_into=acc)
+    a = fake.last("fsb_conv_wgrad")
+    assert a[1:4] == [x.data_ptr(), dy.data_ptr(), dy.stride(3)] and a[4:8] == [acc.data_ptr(), 48 * 9, 9, 1]
+    dw = F_.conv_wgrad(x, dy, acc, 32, 24, 3, 2, 1, 1024.0)
+    a = fake.last("fsb_conv_wgrad")
+    assert a[7] == 0 and dw.shape == acc.shape and float(dw.abs().sum()) == 0.0   # partial corner: zero-filled full tensor
+
+
+def test_resize_concat_and_layout_marshalling(fake):
+    x = act(1, 32, 8, 16)
+    cat = F_.empty_nhwc(1, 48, 16, 32, "cpu")
+    F_.bilinear(x, (16, 32), out=cat[:, :32])
+    a = fake.last("fsb_bilinear_fwd")
+    assert a[:6] == [1, 32, 8, 16, 16, 32] and a[6:10] == [x.data_ptr(), 32, cat.data_ptr(), 48]
+    skip = act(1, 16, 16, 32)
+    F_.copy_channels(skip, cat[:, 32:])
+    a = fake.last("fsb_copy_channels")
+    assert a[:2] == [16 * 32, 16] and a[2:6] == [skip.data_ptr(), 16, cat.data_ptr() + 32 * 2, 48]
+    logits = act(1, 19, 8, 16)
+    out = F_.upsample_logits(logits, (64, 128), dtype=torch.float16)
+    a = fake.last("fsb_upsample_logits_nchw")
+    assert a[:6] == [1, 19, 8, 16, 64, 128] and a[7] == 24 and a[9] == 0 and out.is_contiguous()
+    lab = F_.upsample_argmax(logits, (64, 128))
+    assert lab.dtype == torch.uint8 and tuple(lab.shape) == (1, 64, 128)
+    img = torch.empty(1, 3, 16, 32)
+    xh = F_.to_nhwc_half(img)
+    a = fake.last("fsb_nchw_to_nhwc_f16")
+    assert a[:4] == [1, 3, 16, 32] and a[5] == 1 and a[7] == 8 and tuple(xh.shape) == (1, 3, 16, 32)
+    back = F_.to_nchw(x)
+    assert back.dtype == torch.float32 and back.is_contiguous()
+
+
+def test_weighted_sum_marshalling(fake):
+    xs = [act(1, 16, 4, 6) for _ in range(5)]
+    wts = torch.empty(5)
+    out = F_.wsum_fwd(xs, wts)
+    a = fake.last("fsb_wsum_fwd")
+    assert a[:3] == [5, 24, 16] and a[5] == wts.data_ptr() and a[6] == out.data_ptr()
+    dxs, dw = F_.wsum_bwd(out, xs, wts, [True, False, True, True, True], True, 1024.0)
+    assert dxs[1] is None and all(d is not None for i, d in enumerate(dxs) if i != 1) and dw.numel() == 5
+
+
+def test_weight_packing_and_stem_marshalling(fake):
+    w = torch.empty(40, 48, 3, 3)
+    packed = F_.pack_conv_weight(w, 32, 24, 3)
+    a = fake.last("fsb_pack_conv_weight")
+    assert (a[0]["Cin"], a[0]["Cout"], a[0]["ksize"]) == (32, 24, 3) and a[1:4] == [w.data_ptr(), 48 * 9, 9]
+    assert packed.dtype == torch.float16 and packed.numel() == 2048 and a[4] == packed.data_ptr()
+    img = torch.empty(2, 3, 32, 64)
+    ws = torch.empty(32, 3, 3, 3)
+    scale, shift = torch.empty(32), torch.empty(32)
+    y = F_.stem_conv_nchw(img, ws, scale, shift)
+    a = fake.last("fsb_stem_conv_nchw")
+    assert a[:4] == [2, 32, 64, 32] and a[4] == img.data_ptr() and a[5] == 1 and a[9] == y.data_ptr() and a[10] == 32
+    assert tuple(y.shape) == (2, 32, 16, 32) and a[11] == _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE
+    with pytest.raises(ValueError):
+        F_.nhwc_info(torch.empty(2, 8, 4, 4, dtype=torch.float16))          # NCHW-contiguous: not NHWC-addressable
+    with pytest.raises(C.ArgumentError):
+        fake.fsb_conv_fwd(None, torch.empty(1), None, None, None, None, None, None)   # a tensor is not a pointer
