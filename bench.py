@@ -251,6 +251,24 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def frame_sigma_roofline(model, x, frame_us):
+    """Whole-frame efficiency: sum over the frame's launches of max(FLOPs / tensor peak, algorithmic bytes / HBM peak) at the
+    measured peaks, divided by the measured frame time.  The launch list comes from one eager forward
+    with the wrappers instrumented (fasterseg_b200/roofline.py); extra key only."""
+    try:
+        from fasterseg_b200 import roofline as RL
+        with torch.no_grad():
+            recs = RL.trace_launches(lambda: model(x))
+        torch.cuda.synchronize()
+        pk = measured_peaks()
+        s = RL.sigma_roofline(recs, pk["tflops"], pk["hbm_gbs"])
+        return {"sum_us": round(s["sum_us"], 1), "frame_us": round(frame_us, 1), "frac": round(s["sum_us"] / frame_us, 4),
+                "launches": s["launches"], "tensor_bound_launches": s["tensor_bound_launches"], "gflop": round(s["gflop"], 2),
+                "algorithmic_mbytes": round(s["mbytes"], 1), "peak_source": pk["source"]}
+    except Exception as e:  # noqa: BLE001 -- analysis key, reported not raised
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def supernet_step_metric():
     """Second half of BASELINE.json's metric: supernet pretrain step (configs[2], 3x3x256x512 per GPU, 16 layers, 252 M
     parameters: 4 forwards + backward + clip + SGD) through the reference-facing classes.  Extra key only -- it never fails
@@ -382,6 +400,7 @@ def main():
         "roofline": roof,
         "frame_tflops": round(STUDENT_GFLOP * value / world / 1000.0, 2),
     }
+    line["frame_roofline"] = frame_sigma_roofline(model, pool[0], ms_total / args.steps * 1000.0 )
     if world == 1 and not args.no_supernet_step:
         line["supernet_step"] = supernet_step_metric()
     if world == 1 and not args.no_cpu_baseline:
