@@ -48,6 +48,8 @@ struct ConvTcParams {
   const float* shift;
   __half* y;
   float* stats;
+  int m_tiles;  // persistent kernel only: spatial tiles (tiles_w * tiles_h * N) ...
+  int n_tiles;  // ... x output-channel tiles; a CTA walks tile = blockIdx.x, += gridDim.x (n fastest)
 };
 
 template <int BK>
@@ -282,6 +284,215 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K1p: persistent variant (EXPERIMENTAL, enabled with FSB_CONV_PERSIST=1; inference epilogue only).
+//
+// The per-tile kernel above pays its prologue (barrier init, TMEM allocation, descriptor prefetch, first TMA round trip) and
+// its epilogue (TMEM -> registers -> smem -> TMA store) once per 128-pixel tile, serially with a main loop that lasts only
+// 72 MMAs for the student's largest layers -- the tensor pipe idles most of a tile's life.  Here one CTA per SM walks
+// tiles tile = blockIdx.x, += gridDim.x with
+//   * the TMA producer running ahead across tile boundaries (one continuous stage ring),
+//   * TWO accumulators in TMEM: the MMA issuer fills buffer (t & 1) while the epilogue warps drain buffer ((t - 1) & 1),
+//   * a dedicated staging buffer for the TMA store, released by cp.async.bulk.wait_group.read before it is rewritten.
+// Barriers: full/empty per stage (as above), tmem_full[2] (MMA -> epilogue, tcgen05.commit), tmem_empty[2] (epilogue ->
+// MMA, one arrival per epilogue warp after its last tcgen05.ld of the tile).
+// ------------------------------------------------------------------------------------------
+constexpr int kPersistMaxCout = 512;
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_persistent_kernel(const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[kPersistMaxCout];
+  __shared__ float s_shift[kPersistMaxCout];
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kABytes = kTileM * BK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * BK * 2;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;  // stage_bytes is a multiple of 1024
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.k_chunks;
+  const uint32_t acc_cols = p.tmem_cols >> 1;  // columns of ONE accumulator (the allocation holds two)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a[0]);
+    tma_prefetch_desc(&p.tmap_b);
+    tma_prefetch_desc(&p.tmap_y[0]);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  for (int c = threadIdx.x; c < kPersistMaxCout; c += kThreads) {
+    const bool ok = c < p.Cout;
+    s_scale[c] = (ok && (p.flags & FSB_CONV_AFFINE) && p.scale) ? p.scale[c] : 1.0f;
+    s_shift[c] = (ok && (p.flags & FSB_CONV_AFFINE) && p.shift) ? p.shift[c] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer: one ring across all tiles of this CTA =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * p.n_tile;
+        int t = tile / p.n_tiles;
+        const int w0 = (t % p.tiles_w) * p.tw;
+        t /= p.tiles_w;
+        const int h0 = (t % p.tiles_h) * p.th;
+        const int img = t / p.tiles_h;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
+          const int cw = w0 + p.tap_dw[tap];
+          const int chh = h0 + p.tap_dh[tap];
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            const int s = it % p.stages;
+            const int round = it / p.stages;
+            if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+            uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+            tma_load_4d(sa, ma, &full_bar[s], kc * BK, cw, chh, img);
+            tma_load_3d(sb, &p.tmap_b, &full_bar[s], kc * BK, n0, p.tap_widx[tap]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: alternates between the two TMEM accumulators =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(p.n_tile));
+      int it = 0;
+      int lt = 0;  // tiles done by this CTA
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const int use = lt >> 1;  // how often this accumulator has been used before
+        if (use > 0) mbar_wait(&tmem_empty_bar[buf], (use - 1) & 1);  // epilogue of its previous tile has drained it
+        tc_fence_after();
+        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
+        for (int ki = 0; ki < k_iters; ++ki, ++it) {
+          const int s = it % p.stages;
+          const int round = it / p.stages;
+          mbar_wait(&full_bar[s], round & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = umma_desc_kmajor(sa, BK * 2);
+          const uint64_t db = umma_desc_kmajor(sb, BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5: drain accumulator (t & 1) while the MMA warp fills the other =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const bool relu = (p.flags & FSB_CONV_RELU) != 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int use = lt >> 1;
+      const int n0 = (tile % p.n_tiles) * p.n_tile;
+      int t = tile / p.n_tiles;
+      const int w0 = (t % p.tiles_w) * p.tw;
+      t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * p.th;
+      const int img = t / p.tiles_h;
+      mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc_fence_after();
+      if (lt > 0) {
+        // the staging buffer still feeds the previous tile's bulk stores until they have READ it
+        if (warp == 2 && lane == 0) tma_store_wait_read();
+        named_bar_sync(1, 128);
+      }
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
+        uint32_t vv[4][16];
+        const int nb = min(4, (p.n_tile - c0) >> 4);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b < nb) tmem_ld16(taddr + c0 + 16 * b, vv[b]);
+        tmem_ld_wait();
+        if (c0 + 64 >= p.n_tile) {
+          // last TMEM read of this tile by this warp: hand the accumulator back to the MMA issuer
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        uint8_t* slab = staging + static_cast<size_t>(c0 >> 6) * (kTileM * 128);
+        const bool full_slab = (p.n_tile - c0) >= 64;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b >= nb) break;
+          const int c = c0 + 16 * b;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = __uint_as_float(vv[b][j]) * s_scale[n0 + c + j] + s_shift[n0 + c + j];
+            f[j] = relu ? fmaxf(x, 0.f) : x;
+          }
+          uint4 o0, o1;
+          o0.x = pack_half2(f[0], f[1]);
+          o0.y = pack_half2(f[2], f[3]);
+          o0.z = pack_half2(f[4], f[5]);
+          o0.w = pack_half2(f[6], f[7]);
+          o1.x = pack_half2(f[8], f[9]);
+          o1.y = pack_half2(f[10], f[11]);
+          o1.z = pack_half2(f[12], f[13]);
+          o1.w = pack_half2(f[14], f[15]);
+          const int ch16 = (c - c0) >> 3;
+          if (full_slab) {
+            *reinterpret_cast<uint4*>(slab + m * 128 + ((ch16 ^ (m & 7)) << 4)) = o0;
+            *reinterpret_cast<uint4*>(slab + m * 128 + (((ch16 + 1) ^ (m & 7)) << 4)) = o1;
+          } else {
+            uint8_t* row = slab + m * (p.tail_w * 2) + (ch16 << 4);
+            *reinterpret_cast<uint4*>(row) = o0;
+            *reinterpret_cast<uint4*>(row + 16) = o1;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 2 && lane == 0) {
+          tma_store_4d(&p.tmap_y[full_slab ? 0 : 1], slab, n0 + c0, w0, h0, img);
+          tma_store_commit();
+        }
+      }
+    }
+    if (warp == 2 && lane == 0) tma_store_wait_read();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static int encode_tiled(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -477,8 +688,44 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
     int rc = encode_tiled(&p.tmap_b, wpacked, 3, dims, str, boxB, g.bk * 2);
     if (rc) return rc;
   }
-  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
   cudaError_t e;
+  // ---- experimental persistent variant (see K1p above): inference epilogue, plain taps, several tiles per SM ----
+  static const bool persist_on = [] { const char* v = getenv("FSB_CONV_PERSIST"); return v && v[0] == '1'; }();
+  if (persist_on && !cu && p.tma_store && d->Cout <= kPersistMaxCout && !(d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS)) &&
+      m_tiles * n_tiles > sms && cols <= 256) {
+    const size_t staging = static_cast<size_t>((n_tile + 63) / 64) * kTileM * 128;
+    const size_t budget = 200 * 1024;
+    int pst = static_cast<int>((budget - staging) / stage_bytes);
+    if (pst > kMaxStages) pst = kMaxStages;
+    if (pst >= 2) {
+      p.m_tiles = m_tiles;
+      p.n_tiles = n_tiles;
+      p.tmem_cols = cols * 2;  // two accumulators
+      p.stages = pst;
+      const size_t psmem = stage_bytes * pst + staging + 1024;
+      const unsigned ctas = static_cast<unsigned>(m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms);
+      if (g.bk == 64) {
+        static bool pattr64 = false;
+        if (!pattr64) {
+          e = cudaFuncSetAttribute(conv_tc_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+          if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_persistent<64>)");
+          pattr64 = true;
+        }
+        e = launch_kernel(conv_tc_persistent_kernel<64>, dim3(ctas), dim3(kThreads), psmem, stream, p);
+      } else {
+        static bool pattr32 = false;
+        if (!pattr32) {
+          e = cudaFuncSetAttribute(conv_tc_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+          if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_persistent<32>)");
+          pattr32 = true;
+        }
+        e = launch_kernel(conv_tc_persistent_kernel<32>, dim3(ctas), dim3(kThreads), psmem, stream, p);
+      }
+      if (e != cudaSuccess) return set_cuda_error(e, "conv_tc persistent launch");
+      return FSB_OK;
+    }
+  }
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
   if (g.bk == 64) {
     static bool attr64 = false;
     if (!attr64) {
