@@ -735,3 +735,12 @@ def ohem_cross_entropy(pred, target, ignore_label=255, thresh=0.7, min_kept=256)
             valid = valid & kept
     t = t.masked_fill(~valid, ignore_label).view(b, h, w)
     return F.cross_entropy(pred, t, ignore_index=ignore_label)
+
+
+def distill_kl(student_logits, teacher_logits):
+    """Distillation term of train/train.py:64,260: nn.KLDivLoss() (reduction 'mean' = mean over ALL elements) of
+    log(softmax(student)) against softmax(teacher), both over the class dimension."""
+    log_p = F.softmax(student_logits, dim=1).log()
+    q = F.softmax(teacher_logits, dim=1)
+    return (q * (q.log() - log_p)).mean()
+
