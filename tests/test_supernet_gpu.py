@@ -10,7 +10,7 @@ from oracle import fasterseg_oracle as orc
 from oracle import supernet_oracle as sno
 from tests import helpers as H
 from tests.test_boundary_cpu import _build_supernet
-from tests.test_supernet_oracle import CASE, FWD, META, cfg, inputs, make_sd
+from tests.test_supernet_oracle import CASE, FWD, META, cfg, inputs, make_sd, oracle_loss_and_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -65,16 +65,8 @@ def test_supernet_loss_backward(tag, pretrain, np_seed, torch_seed):
     crit = nn.CrossEntropyLoss(ignore_index=255)
 
     def run_oracle(emulate):
-        sd = make_sd(requires_grad=True)
-        np.random.seed(np_seed)
-        torch.manual_seed(torch_seed)
-        orc.EMULATE_FP16["on"] = emulate
-        try:
-            loss = sno.supernet_loss(x, tgt, sd, cfg(), crit, pretrain)
-            loss.backward()
-        finally:
-            orc.EMULATE_FP16["on"] = False
-        return float(loss.detach()), {k: v.grad.numpy() for k, v in sd.items() if v.requires_grad and v.grad is not None}
+        loss, sd = oracle_loss_and_grads(pretrain, np_seed, torch_seed, emulate)
+        return float(loss), {k: v.grad.numpy() for k, v in sd.items() if v.requires_grad and v.grad is not None}
 
     l32, g32 = run_oracle(False)
     l16, g16 = run_oracle(True)

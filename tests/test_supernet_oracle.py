@@ -63,15 +63,32 @@ def test_supernet_forward_matches_reference(tag, arch_idx, mode, train, np_seed,
                 np.testing.assert_allclose(sd[k.split("after:")[1]].numpy(), z[k], rtol=2e-4, atol=2e-6)
 
 
+_ORACLE_LOSS_CACHE = {}
+
+
+def oracle_loss_and_grads(pretrain, np_seed, torch_seed, emulate_fp16=False):
+    """(loss tensor (detached), state dict with .grad populated) of the oracle's `_loss` + backward for the golden case;
+    cached per process: the GPU parity test, the CPU host-logic test and the oracle-vs-reference test all need it."""
+    key = (repr(pretrain), np_seed, torch_seed, bool(emulate_fp16))
+    if key not in _ORACLE_LOSS_CACHE:
+        sd = make_sd(requires_grad=True)
+        x, tgt = inputs()
+        np.random.seed(np_seed)
+        torch.manual_seed(torch_seed)
+        orc.EMULATE_FP16["on"] = bool(emulate_fp16)
+        try:
+            loss = sno.supernet_loss(x, tgt, sd, cfg(), nn.CrossEntropyLoss(ignore_index=255), pretrain)
+            loss.backward()
+        finally:
+            orc.EMULATE_FP16["on"] = False
+        _ORACLE_LOSS_CACHE[key] = (loss.detach(), sd)
+    return _ORACLE_LOSS_CACHE[key]
+
+
 @pytest.mark.parametrize("tag,pretrain,np_seed,torch_seed", [("loss.pretrain", True, 11, 12), ("loss.search", "some-dir", 13, 14)])
 def test_supernet_loss_and_grads_match_reference(tag, pretrain, np_seed, torch_seed):
     z = H.load_npz("supernet.npz")
-    sd = make_sd(requires_grad=True)
-    x, tgt = inputs()
-    np.random.seed(np_seed)
-    torch.manual_seed(torch_seed)
-    loss = sno.supernet_loss(x, tgt, sd, cfg(), nn.CrossEntropyLoss(ignore_index=255), pretrain)
-    loss.backward()
+    loss, sd = oracle_loss_and_grads(pretrain, np_seed, torch_seed)
     assert abs(float(loss) - float(z[tag + "/loss"][0])) < 1e-4 * abs(float(z[tag + "/loss"][0]))
     n = 0
     for k in z.files:
