@@ -1,0 +1,17 @@
+#!/usr/bin/env bash
+# First GPU session of the next round: validate and measure the persistent conv kernel (FSB_CONV_PERSIST=1) against the
+# per-tile kernel.  Everything lands in gpurun_out/.  Usage (from the repo root, on the GPU box):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/r2_first_session.sh'
+set -u
+mkdir -p gpurun_out
+# 1. parity of the whole GPU suite with the persistent kernel enabled
+FSB_CONV_PERSIST=1 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_persist.log 2>&1
+tail -3 gpurun_out/r2_pytest_persist.log
+# 2. per-layer timings, per-tile vs persistent (the table prints the student's conv shapes)
+timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_pertile.log 2>&1
+FSB_CONV_PERSIST=1 timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_persist.log 2>&1
+tail -45 gpurun_out/r2_conv_bench_persist.log
+# 3. headline metric both ways (no CPU baseline / supernet step: kernel comparison only)
+timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_pertile.json 2> gpurun_out/r2_bench_pertile.err
+FSB_CONV_PERSIST=1 timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_persist.json 2> gpurun_out/r2_bench_persist.err
+cut -c1-400 gpurun_out/r2_bench_pertile.json; echo; cut -c1-400 gpurun_out/r2_bench_persist.json
