@@ -21,10 +21,23 @@ from fasterseg_b200 import functional as F_  # noqa: E402
 from fasterseg_b200._lib import ConvDesc  # noqa: E402
 
 CALLS = {}
+WORK = {"flops": 0.0, "bytes": 0.0, "roof_s": 0.0}   # algorithmic work of the launches the stubs stand for
+PEAK_TFLOPS, PEAK_GBS = 1694.0, 6568.7               # MEASURED_PEAKS.json of this pool's B200s
 
 
 def _count(name):
     CALLS[name] = CALLS.get(name, 0) + 1
+
+
+def _work(flops, nbytes):
+    """one launch (or fused group of launches) worth `flops` and `nbytes` of algorithmic traffic"""
+    WORK["flops"] += flops
+    WORK["bytes"] += nbytes
+    WORK["roof_s"] += max(flops / (PEAK_TFLOPS * 1e12), nbytes / (PEAK_GBS * 1e9))
+
+
+def _numel(t):
+    return float(t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3])
 
 
 def _e(N, C, H, W, dtype=torch.float16):
@@ -45,8 +58,9 @@ def install_null_backend():
     def conv_fwd(x, wp, Cout, k, s, p, scale=None, shift=None, relu=False, out=None, off=(0, 0), stats=None, force_direct=False,
                  out_f32=False):
         _count("conv_fwd")
-        N, _, H, W = x.shape
+        N, Cin, H, W = x.shape
         Ho, Wo = F_.conv_out_size(H, W, k, s, p, 1, off[0], off[1])
+        _work(2.0 * k * k * Cin * Cout * N * Ho * Wo, 2 * _numel(x) + (4 if out_f32 else 2) * N * Cout * Ho * Wo + 2 * k * k * Cin * Cout)
         return out if out is not None else _e(N, Cout, Ho, Wo, torch.float32 if out_f32 else torch.float16)
 
     def stem_conv_nchw(x, w, scale, shift, relu=True, out=None):
@@ -55,6 +69,7 @@ def install_null_backend():
 
     def bilinear(x, size, relu=False, out=None):
         _count("bilinear")
+        _work(0.0, 2 * _numel(x) + 2.0 * x.shape[0] * x.shape[1] * int(size[0]) * int(size[1]))
         return out if out is not None else _e(x.shape[0], x.shape[1], int(size[0]), int(size[1]))
 
     def train_fwd(x, wp, Cout, k, s, p, off, gamma, beta, eps, momentum, rm, rv, nbt, relu):
@@ -62,11 +77,19 @@ def install_null_backend():
         N, Cin, H, W = x.shape
         Ho, Wo = F_.conv_out_size(H, W, k, s, p, 1, off[0], off[1])
         d = ConvDesc(N, H, W, Cin, Cout, k, s, p, 1, off[0], off[1], Ho, Wo, x.stride(3), (Cout + 7) // 8 * 8, 0)
+        px = float(N * Cout * Ho * Wo)
+        # conv (x in, fp32 raw out, weights) + apply (raw in, fp16 y out)
+        _work(2.0 * k * k * Cin * Cout * N * Ho * Wo, 2 * _numel(x) + 4 * px + 2 * k * k * Cin * Cout + 4 * px + 2 * px)
         return _e(N, Cout, Ho, Wo), _e(N, Cout, Ho, Wo, torch.float32), torch.empty(6 * Cout), d
 
     def train_bwd(d, x, dy, y, raw, vec, gamma, relu, wt, w, need_dx, dw_acc, gscale):
         _count("conv_bn_act_train_bwd")
         Cout = dy.shape[1]
+        px, kk = _numel(dy), d.ksize * d.ksize
+        gemm = 2.0 * kk * d.Cin * Cout * dy.shape[0] * dy.shape[2] * dy.shape[3]
+        # BN backward: two passes over (dy, y, raw) + draw out; dgrad: draw + weights in, dx out; wgrad: x + draw in, dW out
+        _work((2.0 if need_dx else 1.0) * gemm,
+              2 * (2 + 2 + 4) * px + 2 * px + (2 * px + 2 * _numel(x) if need_dx else 0) + 2 * _numel(x) + 2 * px + 6 * kk * d.Cin * Cout)
         dx = _e(dy.shape[0], d.Cin, d.H, d.W) if need_dx else None
         return dx, torch.empty(Cout), torch.empty(Cout)
 
@@ -77,10 +100,12 @@ def install_null_backend():
 
     def wsum_bwd(dout, xs, wts, need_dx, need_dw, gscale):
         _count("wsum_bwd")
+        _work(0.0, 2 * _numel(dout) * (1 + len(xs) + sum(1 for n in need_dx if n)))
         return [_e(*dout.shape) if n else None for n in need_dx], (torch.empty(len(xs)) if need_dw else None)
 
     def conv_wgrad(x, dy, w_like, Cin, Cout, k, s, p, gscale, off=(0, 0), accumulate_into=None, force_direct=False):
         _count("conv_wgrad")
+        _work(2.0 * k * k * Cin * Cout * dy.shape[0] * dy.shape[2] * dy.shape[3], 2 * _numel(x) + 2 * _numel(dy) + 4 * k * k * Cin * Cout)
         return accumulate_into if accumulate_into is not None else torch.empty_like(w_like)
 
     simple = {
@@ -106,7 +131,17 @@ def install_null_backend():
     for name, fn in simple.items():
         def wrapped(*a, _fn=fn, _name=name, **k):
             _count(_name)
-            return _fn(*a, **k)
+            res = _fn(*a, **k)
+            # elementwise / layout kernels: every 4-D tensor argument read once, every 4-D result written once
+            touched = [t for t in list(a) + (list(res) if isinstance(res, tuple) else [res]) if isinstance(t, torch.Tensor) and t.dim() == 4]
+            if _name == "conv_dgrad":
+                dy, w, xs, ci, co, kk = a[0], a[1], a[2], a[3], a[4], a[5]
+                _work(2.0 * kk * kk * ci * co * dy.shape[0] * dy.shape[2] * dy.shape[3], 2 * _numel(dy) + 2.0 * xs[0] * xs[1] * xs[2] * xs[3] + 2 * kk * kk * ci * co)
+            elif _name == "wsum_fwd":
+                _work(0.0, 2 * _numel(a[0][0]) * (len(a[0]) + 1))
+            elif _name not in ("pack_conv_weight", "pack_conv_weight_dgrad", "bn_fold", "bn_finalize"):
+                _work(0.0, sum(t.element_size() * _numel(t) for t in touched))
+            return res
         setattr(F_, name, wrapped)
     for name, fn in (("nhwc_info", nhwc_info), ("to_nhwc_half", to_nhwc_half), ("conv_fwd", conv_fwd), ("stem_conv_nchw", stem_conv_nchw),
                      ("bilinear", bilinear), ("conv_bn_act_train_fwd", train_fwd), ("conv_bn_act_train_bwd", train_bwd),
@@ -142,6 +177,8 @@ def main():
 
     step()  # warm-up: weight-pack caches, grad buffers
     CALLS.clear()
+    for k_ in WORK:
+        WORK[k_] = 0.0
     prof = cProfile.Profile() if args.profile else None
     times = []
     for _ in range(args.steps):
@@ -155,6 +192,8 @@ def main():
     n_calls = sum(CALLS.values()) // args.steps
     print("mode %s layers %d: host time per step (forward x4 + backward, null backend) median %.0f ms, min %.0f ms; %d backend calls/step -> %.1f us of Python per call"
           % (args.mode, args.layers, 1e3 * sorted(times)[len(times) // 2], 1e3 * min(times), n_calls, 1e6 * min(times) / max(n_calls, 1)))
+    print("algorithmic work per step: %.2f TFLOP, %.1f GB -> sum over launches of max(FLOPs / %.0f TFLOP/s, bytes / %.0f GB/s) = %.1f ms"
+          % (WORK["flops"] / args.steps / 1e12, WORK["bytes"] / args.steps / 1e9, PEAK_TFLOPS, PEAK_GBS, 1e3 * WORK["roof_s"] / args.steps))
     print("calls/step:", {k: v // args.steps for k, v in sorted(CALLS.items(), key=lambda kv: -kv[1])})
     if prof:
         pstats.Stats(prof).sort_stats("tottime").print_stats(28)
