@@ -64,6 +64,12 @@ _SIGS = {
                                             C.c_int, _P, C.c_int, _P]),
     "fsb_conv_bn_act_train_bwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P,
                                             C.c_int64, C.c_int64, _P, C.c_int, _P, _P, C.c_int, _P, C.c_float, _P]),
+    "fsb_dp_unique_id": (C.c_int, [_P]),
+    "fsb_dp_init": (C.c_int, [_P, C.c_int, C.c_int]),
+    "fsb_dp_world": (C.c_int, []),
+    "fsb_dp_enable": (C.c_int, [C.c_int]),
+    "fsb_dp_allreduce_f32": (C.c_int, [_P, C.c_int64, _P]),
+    "fsb_dp_shutdown": (C.c_int, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -69,8 +69,9 @@ def _conv_backward(ctx_conv, x, draw, ci, co, off, need_dx, need_dw):
 
 class ConvBnActFn(torch.autograd.Function):
     """act(BN_train(conv(x))): conv with fused per-channel statistics -> finalize (running-stat update) -> apply.
-    Single process: one fused C-ABI call per direction (csrc/train_fused.cu); with SyncBN the statistics are all-reduced
-    between the stages, so the separate entry points are used."""
+    One fused C-ABI call per direction (csrc/train_fused.cu) for a single process and for data parallelism with the
+    library's own communicator (csrc/dp.cu: the statistics are all-reduced on the stream inside the call); with SyncBN over
+    torch.distributed the statistics are all-reduced between the stages from here, so the separate entry points are used."""
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, conv, bn, relu, ci, co, off):
@@ -78,7 +79,7 @@ class ConvBnActFn(torch.autograd.Function):
         wp = engine.packed_weight(conv, ci, co)
         momentum = bn.momentum if bn.momentum is not None else 0.1
         ctx.conv, ctx.relu, ctx.ci, ctx.co, ctx.off = conv, relu, ci, co, off
-        if engine.dp_world_size() == 1:
+        if engine.dp_world_size() == 1 or engine.dp_native():
             track = bn.track_running_stats
             y, raw, vec, d = F_.conv_bn_act_train_fwd(x, wp, co, k, s, p, off, gamma, beta, bn.eps, momentum,
                                                       bn.running_mean if track else None, bn.running_var if track else None,

@@ -14,6 +14,19 @@ int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const 
                         const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t);
 int conv_dgrad_launch(const fsb_conv_desc*, const void*, int, const void*, const float*, int64_t, int64_t, void*, int, cudaStream_t);
 int conv_wgrad_launch(const fsb_conv_desc*, const void*, const void*, int, float*, int64_t, int64_t, int, float, cudaStream_t);
+int dp_world();                                        // dp.cu: 1 unless fsb_dp_init created a communicator
+int dp_allreduce_f32(float*, int64_t, cudaStream_t);   // in-place sum over ranks on the stream
+
+// dgamma = sum(dz * xhat) / gscale, dbeta = sum(dz) / gscale from the rank-LOCAL sums (the data-parallel gradient average
+// divides by the world size afterwards, so these must not come from the all-reduced buffer)
+__global__ void local_param_grads_kernel(int C, const float* __restrict__ sums, float inv_gscale, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    dbeta[c] = sums[c] * inv_gscale;
+    dgamma[c] = sums[C + c] * inv_gscale;
+  }
+}
 
 }  // namespace fsb
 
@@ -37,7 +50,12 @@ int fsb_conv_bn_act_train_fwd(const fsb_conv_desc* d, const void* x, const void*
                                                                        : conv_tc_dispatch(&c, x, wpacked, nullptr, nullptr, raw_f32, vec, st);
   if (rc) return rc;
   const int64_t pixels = static_cast<int64_t>(d->N) * d->Ho * d->Wo;
-  rc = bn_finalize_launch(C, vec, static_cast<double>(pixels), gamma, beta, eps, momentum, running_mean, running_var, vec + 2 * C,
+  const int world = dp_world();
+  if (world > 1) {  // SyncBN: the statistics of all ranks, exchanged on the stream between the two kernels
+    rc = dp_allreduce_f32(vec, 2 * C, st);
+    if (rc) return rc;
+  }
+  rc = bn_finalize_launch(C, vec, static_cast<double>(pixels) * world, gamma, beta, eps, momentum, running_mean, running_var, vec + 2 * C,
                           vec + 3 * C, vec + 4 * C, vec + 5 * C, st, num_batches_tracked);
   if (rc) return rc;
   return affine_act_launch(pixels, C, raw_f32, raw_cstride, vec + 2 * C, vec + 3 * C, y, y_cstride,
@@ -59,8 +77,20 @@ int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void*
   int rc = bn_bwd_reduce_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, relu,
                                 vec_bwd, st);
   if (rc) return rc;
-  rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
-                           static_cast<double>(pixels), relu, draw, draw_cstride, vec_bwd + 2 * C, vec_bwd + 3 * C, gscale, st);
+  const int world = dp_world();
+  if (world > 1) {
+    // SyncBN backward: gamma / beta gradients from the LOCAL sums, dx from the GLOBAL sums and the global pixel count
+    local_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, vec_bwd, 1.0f / gscale, vec_bwd + 2 * C, vec_bwd + 3 * C);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "conv_bn_act_train_bwd: local_param_grads launch");
+    rc = dp_allreduce_f32(vec_bwd, 2 * C, st);
+    if (rc) return rc;
+    rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
+                             static_cast<double>(pixels) * world, relu, draw, draw_cstride, nullptr, nullptr, gscale, st);
+  } else {
+    rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
+                             static_cast<double>(pixels), relu, draw, draw_cstride, vec_bwd + 2 * C, vec_bwd + 3 * C, gscale, st);
+  }
   if (rc) return rc;
   if (dx) {
     rc = conv_dgrad_launch(d, draw, draw_cstride, wpacked_t, w, so, si, dx, dx_cstride, st);

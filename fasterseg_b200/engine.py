@@ -120,18 +120,27 @@ def conv_bn_act_train_nograd(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
 # ----------------------------------------------------------------------------------------------
 # data-parallel hooks (SyncBN statistics); identity when torch.distributed is not initialised
 # ----------------------------------------------------------------------------------------------
-_SYNC_BN = {"enabled": False, "group": None}
+_SYNC_BN = {"enabled": False, "group": None, "native": False}
 
 
 def enable_sync_bn(enabled=True, group=None):
     _SYNC_BN["enabled"] = enabled
     _SYNC_BN["group"] = group
+    if _SYNC_BN["native"]:   # the library's own communicator follows the switch (a rank-0-only reference run must not all-reduce)
+        from . import _lib
+        _lib.check(_lib.lib().fsb_dp_enable(1 if enabled else 0), "fsb_dp_enable")
 
 
 def dp_world_size():
     if _SYNC_BN["enabled"] and torch.distributed.is_available() and torch.distributed.is_initialized():
         return torch.distributed.get_world_size(_SYNC_BN["group"])
     return 1
+
+
+def dp_native():
+    """True when the library owns a NCCL communicator (parallel.init_native_dp): the fused training units then exchange
+    their BatchNorm statistics themselves, on the stream, and stay on the one-call-per-unit path under data parallelism."""
+    return _SYNC_BN["native"] and _SYNC_BN["enabled"]
 
 
 def dp_allreduce_stats(stats):

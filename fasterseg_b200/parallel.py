@@ -38,7 +38,30 @@ def init_from_env(backend: Optional[str] = None, sync_bn: bool = True):
             dist.init_process_group(backend)
     if sync_bn:
         engine.enable_sync_bn(world > 1)
+    if world > 1 and os.environ.get("FSB_NATIVE_DP", "0") == "1" and torch.cuda.is_available():
+        init_native_dp()   # EXPERIMENTAL (default off): SyncBN exchange inside the fused training units
     return rank, local_rank, world
+
+
+def init_native_dp(group=None):
+    """Give libfsb200 its own NCCL communicator over the ranks of `group`: rank 0 creates the 128-byte id, it travels through
+    torch.distributed, every rank joins with its current device.  Afterwards `engine.dp_native()` is True and the fused
+    training units all-reduce their BatchNorm statistics themselves (no host work per unit)."""
+    import ctypes
+
+    from . import _lib
+    lib = _lib.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (ctypes.c_char * 128)()
+    if rank == 0:
+        _lib.check(lib.fsb_dp_unique_id(buf), "fsb_dp_unique_id")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    carrier = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+    dist.broadcast(carrier, src=0, group=group)
+    ident = bytes(carrier.cpu().tolist())
+    _lib.check(lib.fsb_dp_init(ident, rank, world), "fsb_dp_init")
+    engine._SYNC_BN["native"] = True
+    return world
 
 
 def seed_all_ranks_identically(seed: int = 12345):

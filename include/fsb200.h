@@ -204,7 +204,9 @@ int fsb_wsum_bwd(int K, int64_t pixels, int C, const void* dout, int dout_cstrid
  *            -> fsb_affine_act.   vec: fp32[6*Cout] = [sum | sumsq | scale | shift | mean | invstd] (zeroed by the call).
  * backward = fsb_bn_bwd_reduce -> fsb_bn_bwd_apply -> fsb_conv_dgrad (if dx) -> fsb_conv_wgrad accumulate (if dw).
  *            vec_bwd: fp32[4*Cout] = [sum dz | sum dz*xhat | dgamma | dbeta] (zeroed by the call); draw: fp16 NHWC scratch.
- * Single-process only: with SyncBN the statistics need an all-reduce between the stages, use the separate entry points. */
+ * Data parallel: once fsb_dp_init() has created a communicator, both calls all-reduce their 2*Cout statistics over the ranks
+ * on `stream` between the stages (SyncBN: global count, gamma/beta gradients from the rank-local sums); without it they are
+ * single-process and SyncBN callers use the separate entry points with their own exchange. */
 int fsb_conv_bn_act_train_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* gamma, const float* beta,
                               float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
                               void* raw_f32, int raw_cstride, void* y, int y_cstride, float* vec, int relu, void* stream);
@@ -215,6 +217,19 @@ int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void*
 
 /* y (+)= x elementwise over a channel-slice view (gradient accumulation when a tensor feeds several consumers) */
 int fsb_add_inplace(int64_t pixels, int C, const void* x, int x_cstride, void* y, int y_cstride, void* stream);
+
+/* ---- data-parallel exchange (replaces the SyncBN / gradient all-reduce a DDP port of
+ * search/train_search.py:215-256 and train/train.py:219-271 would issue through torch.distributed) --------------------------
+ * One process per GPU.  Rank 0 obtains a 128-byte NCCL id (fsb_dp_unique_id), the launcher broadcasts it by any means,
+ * every rank calls fsb_dp_init(id, rank, world) with its device current (collective).  From then on the fused training
+ * units exchange their BatchNorm statistics themselves and fsb_dp_allreduce_f32 sums fp32 buffers (gradient buckets) in
+ * place on the given stream.  NCCL is loaded with dlopen at first use; fsb_dp_world() is 1 until fsb_dp_init succeeded. */
+int fsb_dp_unique_id(void* out128);
+int fsb_dp_init(const void* id128, int rank, int world);
+int fsb_dp_world(void);
+int fsb_dp_enable(int on); /* 0: keep the communicator but behave single-process (fsb_dp_world() == 1) until re-enabled */
+int fsb_dp_allreduce_f32(void* buf, int64_t n, void* stream);
+int fsb_dp_shutdown(void);
 
 #ifdef __cplusplus
 }

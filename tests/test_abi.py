@@ -53,3 +53,19 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.FsbError):
         _lib.lib()
+
+
+def test_native_dp_api_is_inert_until_initialised():
+    """csrc/dp.cu: NCCL is resolved with dlopen on first use; before fsb_dp_init the library is single-process."""
+    import ctypes
+
+    from fasterseg_b200 import engine
+    lib = _lib.lib()
+    assert lib.fsb_dp_world() == 1 and not engine.dp_native()
+    assert lib.fsb_dp_allreduce_f32(None, 0, None) == 0            # no communicator: a no-op, not an error
+    assert lib.fsb_dp_init(bytes(128), 0, 1) == 0 and lib.fsb_dp_world() == 1   # world 1: nothing to create
+    assert lib.fsb_dp_init(bytes(128), 2, 2) != 0 and b"bad arguments" in lib.fsb_last_error_string()
+    assert lib.fsb_dp_enable(0) == 0 and lib.fsb_dp_enable(1) == 0 and lib.fsb_dp_shutdown() == 0
+    ident = (ctypes.c_char * 128)()
+    if lib.fsb_dp_unique_id(ident) == 0:      # needs libnccl.so.2 (bundled with torch); no GPU required for the id
+        assert any(bytes(ident))
