@@ -57,9 +57,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_native_dp_api_is_inert_until_initialised():
     """csrc/dp.cu: NCCL is resolved with dlopen on first use; before fsb_dp_init the library is single-process."""
-    import ctypes
-
-    from fasterseg_b200 import engine
+    from fasterseg_b200 import _lib, engine
     lib = _lib.lib()
     assert lib.fsb_dp_world() == 1 and not engine.dp_native()
     assert lib.fsb_dp_allreduce_f32(None, 0, None) == 0            # no communicator: a no-op, not an error
