@@ -196,3 +196,42 @@ def test_supernet_loss_backward_wiring(tag, pretrain, np_seed, torch_seed):
     print("%s: %d gradients, median err vs fp32 oracle ours %.3e | emulation %.3e" % (tag, len(e_ours), med_ours, med_emu))
     assert len(e_ours) > 300
     assert med_ours <= 1.5 * med_emu + 1e-2
+
+
+def test_weight_and_bn_caches_follow_parameter_updates():
+    """Packed-weight / folded-BN caches are keyed by the tensors' version counters and storage: an optimizer step, an
+    in-place edit, a `.data` swap and `load_state_dict` must all be visible to the next forward (train/train.py:262-264
+    steps the optimizer between forwards; train_search.py:73 loads checkpoints partially)."""
+    model, g = _build_student(1)
+    model = model.eval()
+    _load_seeded(model, g, 2024)
+    x = orc.random_input((1, 3, 64, 128), seed=5)
+
+    def fresh_output():
+        twin, _ = _build_student(1)
+        twin = twin.eval()
+        twin.load_state_dict(model.state_dict())
+        for a, b in zip(model.modules(), twin.modules()):
+            if isinstance(a, nn.BatchNorm2d):
+                b.eps, b.momentum = a.eps, a.momentum
+        with torch.no_grad():
+            return twin(x)
+
+    with torch.no_grad():
+        y0 = model(x)
+        assert torch.equal(y0, fresh_output())
+        # 1. optimizer-style in-place update of every parameter
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        for p in model.parameters():
+            p.grad = torch.ones_like(p) * 0.01
+        opt.step()
+        y1 = model(x)
+        assert not torch.equal(y1, y0) and torch.equal(y1, fresh_output())
+        # 2. running statistics edited in place (BN fold cache), one conv weight replaced through .data
+        model.stem[1].bn1.running_var.mul_(1.5)
+        model.heads8.conv_3x3.conv.weight.data = model.heads8.conv_3x3.conv.weight.data * 0.9
+        y2 = model(x)
+        assert not torch.equal(y2, y1) and torch.equal(y2, fresh_output())
+        # 3. load_state_dict back to the original weights reproduces the original output bit for bit
+        _load_seeded(model, g, 2024)
+        assert torch.equal(model(x), y0)
