@@ -70,3 +70,36 @@ def test_reference_architect_steps_our_supernet(shadowed, monkeypatch, latency_w
             # the latency term reaches the student's betas (they only enter through forward_latency's mixing weights
             # when a beta row has no live gradient from the loss) and its width logits
             assert model.ratio_1_0.grad is not None and float(model.ratio_1_0.grad.abs().sum()) > 0
+
+
+def test_reference_init_weight_and_ohem_loss_accept_our_modules(shadowed):
+    """train_search.py:77 / train.py:122 initialise the networks with the reference's `init_weight`, which picks modules by
+    isinstance(nn.Conv2d / nn.BatchNorm2d) -- our slimmable classes must still qualify -- and train.py:250-258 feeds our
+    logits to the reference's ProbOhemCrossEntropy2d."""
+    from fasterseg_b200.model_search import Network_Multi_Path
+    from fasterseg_b200.slimmable_ops import USBatchNorm2d, USConv2d
+    from oracle import ref_harness
+    spec = importlib.util.spec_from_file_location("ref_init_func", "/root/reference/tools/utils/init_func.py")
+    init_func = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(init_func)
+    wml = [4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.]
+    model = Network_Multi_Path(19, 5, nn.CrossEntropyLoss(ignore_index=255), Fch=12, width_mult_list=wml,
+                               prun_modes=['max', 'arch_ratio'], stem_head_width=[(1, 1), (8. / 12, 8. / 12)])
+    for p in model.parameters():
+        nn.init.constant_(p, 7.0)
+    init_func.init_weight(model, nn.init.kaiming_normal_, nn.BatchNorm2d, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+    convs = [m for m in model.modules() if isinstance(m, USConv2d)]
+    bns = [m for m in model.modules() if isinstance(m, USBatchNorm2d)]
+    assert len(convs) > 100 and len(bns) > 100
+    assert all(float(m.weight.std()) > 0 and abs(float(m.weight.mean())) < 1.0 for m in convs)      # re-initialised
+    assert all(m.eps == 1e-5 and m.momentum == 0.1 and float(m.weight.min()) == 1.0 for m in bns)   # the (unused) own affine
+    assert all(float(b.weight.min()) == 1.0 and float(b.bias.abs().max()) == 0.0 for m in bns for b in m.bn)  # per-width BNs
+    ns = ref_harness.load_reference("train", "seg_opr.loss_opr")
+    crit = ns.modules["seg_opr.loss_opr"].ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=64, use_weight=False)
+    with cpu_backend.installed():
+        model.train()
+        model.prun_mode, model.arch_idx = "max", 0
+        logits = model(torch.randn(2, 3, 64, 128))
+        loss = sum(crit(l, torch.randint(0, 19, (2, 8, 16))) for l in logits)
+        loss.backward()
+    assert torch.isfinite(loss.detach()) and model.stem[0][0].conv[0].weight.grad is not None
