@@ -1,0 +1,43 @@
+"""bench.py contract without a GPU: the reference arm prints ONE JSON line with the agreed keys (same metric / unit / workload
+as our arm), ranks other than 0 stay silent, and our arm refuses to run without a CUDA device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, "bench.py"] + args, cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_json_line():
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fasterseg_student_fps_1024x2048" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "1x3x1024x2048" in d["config"]["workload"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD          # same workload string as our arm
+
+
+def test_reference_arm_other_ranks_are_silent():
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_our_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = _run(["--steps", "3", "--warmup", "3"])
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
