@@ -95,7 +95,11 @@ def golden_supernet(golden_dir):
                  "refine32.1.3.conv.0.weight", "cells.5.1._op._ops.1.conv1.weight"]
         for k in keep:
             if grads.get(k) is not None:
-                rec["%s/grad:%s" % (tag, k)] = _np(grads[k]).astype(np.float32)
+                g = _np(grads[k]).astype(np.float32)
+                if g.ndim == 4 and g.nbytes > 200_000:   # large weight gradients: every 4th output / input channel
+                    rec["%s/grad.s4:%s" % (tag, k)] = np.ascontiguousarray(g[::4, ::4])
+                else:
+                    rec["%s/grad:%s" % (tag, k)] = g
         # global gradient norm over the SGD parameter groups (clip_grad_norm_ input, train_search.py:249)
         sq = sum(float((g.double() ** 2).sum()) for g in grads.values() if g is not None)
         rec[tag + "/grad_norm"] = np.array([sq ** 0.5], dtype=np.float64)

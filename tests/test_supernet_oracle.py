@@ -92,12 +92,14 @@ def test_supernet_loss_and_grads_match_reference(tag, pretrain, np_seed, torch_s
     assert abs(float(loss) - float(z[tag + "/loss"][0])) < 1e-4 * abs(float(z[tag + "/loss"][0]))
     n = 0
     for k in z.files:
-        if k.startswith(tag + "/grad:"):
-            key = k.split("grad:")[1]
+        if k.startswith(tag + "/grad:") or k.startswith(tag + "/grad.s4:"):
+            strided = "/grad.s4:" in k
+            key = k.split("grad.s4:" if strided else "grad:")[1]
             assert sd[key].grad is not None, key
             # train-mode BN chains are ill-conditioned: two fp32 CPU evaluations that differ only in summation order
             # (ATen conv of the sliced weight view vs our restatement) already disagree at the 5e-3 level on alpha grads
-            assert H.rel_err(sd[key].grad.numpy(), z[k]) < 3e-2, (key, H.rel_err(sd[key].grad.numpy(), z[k]))
+            got = sd[key].grad.numpy()[::4, ::4] if strided else sd[key].grad.numpy()
+            assert H.rel_err(got, z[k]) < 3e-2, (key, H.rel_err(got, z[k]))
             n += 1
     assert n >= 12
     no_grad = sorted(k for k, v in sd.items() if v.requires_grad and v.grad is None)
