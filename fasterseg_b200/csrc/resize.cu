@@ -259,10 +259,140 @@ upsample_logits_tiled_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// EXPERIMENTAL (FSB_UPSAMPLE_V2=1, default off): same tiling idea without the per-row barriers.
+// The tiled kernel above synchronises twice per output row (build the vertically interpolated line in smem, consume it),
+// i.e. 8 barriers for 78 KB of stores -- it reaches 2.4 TB/s of the 6.6 TB/s the 80 MB logits write could stream at.
+// For upsampling factors >= 8 the 8 consecutive output columns of a thread read at most 3 consecutive source columns, so
+// a thread can interpolate them vertically in registers (6 smem loads per (row, class)) and needs no shared line at all:
+// one barrier per block (after staging the source window), 8 output rows per block.
+// Arithmetic is expression-for-expression the one of the kernel above: (1 - lh) * top + lh * bottom, then x0 + lw * (x1 - x0).
+// ------------------------------------------------------------------------------------------
+constexpr int kUp2Rows = 8;
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+upsample_logits_rows_kernel(int N, int C, int Hi, int Wi, int Ho, int Wo, const __half* __restrict__ x, int xcs,
+                            TOut* __restrict__ y, float sh, float sw, int max_rows, int max_cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_up[];  // [max_rows][C][max_cols] source window as fp32
+  const int n = blockIdx.z;
+  const int ho0 = blockIdx.y * kUp2Rows;
+  const int wo0 = blockIdx.x * kUpCols;
+  const int ho_last = min(ho0 + kUp2Rows, Ho) - 1;
+  const int wo_last = min(wo0 + kUpCols, Wo) - 1;
+  int hs0, hs1, ws0, ws1, tmp;
+  float ftmp;
+  src_index(ho0, sh, Hi, hs0, tmp, ftmp);
+  src_index(ho_last, sh, Hi, tmp, hs1, ftmp);
+  src_index(wo0, sw, Wi, ws0, tmp, ftmp);
+  src_index(wo_last, sw, Wi, tmp, ws1, ftmp);
+  const int nrows = hs1 - hs0 + 1;  // <= max_rows by construction on the host
+  const int ncols = ws1 - ws0 + 1;  // <= max_cols
+  float* win = s_up;
+  const int cvec = (C + 7) >> 3;
+  const int items = nrows * ncols * cvec;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int cv = i % cvec;
+    const int col = (i / cvec) % ncols;
+    const int row = i / (cvec * ncols);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * Hi + hs0 + row) * Wi + ws0 + col) * xcs + cv * 8);
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cv * 8 + j;
+      if (c < C) win[(static_cast<size_t>(row) * C + c) * max_cols + col] = __half2float(hv[j]);
+    }
+  }
+  __syncthreads();
+  constexpr int kVecs = kUpCols / 8;  // 64 column vectors per block row
+  const int v = threadIdx.x % kVecs;
+  const int cg = threadIdx.x / kVecs;  // class group 0..3
+  const int cgs = blockDim.x / kVecs;
+  const int wo = wo0 + v * 8;
+  if (wo > wo_last) return;  // no barrier below this point
+  // horizontal taps of the 8 columns, relative to the first source column this thread touches (span <= 3 columns)
+  int rel0[8], rel1[8];
+  float lwj[8];
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int w0, w1;
+    src_index(min(wo + j, Wo - 1), sw, Wi, w0, w1, lwj[j]);
+    if (j == 0) base = w0;
+    rel0[j] = w0 - base;
+    rel1[j] = w1 - base;
+  }
+  const int col0 = base - ws0;
+  const int k1 = min(col0 + 1, ncols - 1) - col0;  // clamp the 2nd / 3rd column into the staged window
+  const int k2 = min(col0 + 2, ncols - 1) - col0;
+  const size_t plane = static_cast<size_t>(Ho) * Wo;
+  for (int ho = ho0; ho <= ho_last; ++ho) {
+    int h0, h1;
+    float lh;
+    src_index(ho, sh, Hi, h0, h1, lh);
+    const float* r0 = win + static_cast<size_t>(h0 - hs0) * C * max_cols + col0;
+    const float* r1 = win + static_cast<size_t>(h1 - hs0) * C * max_cols + col0;
+    for (int c = cg; c < C; c += cgs) {
+      const float* p0 = r0 + c * max_cols;
+      const float* p1 = r1 + c * max_cols;
+      const float s0 = (1.f - lh) * p0[0] + lh * p1[0];
+      const float s1 = (1.f - lh) * p0[k1] + lh * p1[k1];
+      const float s2 = (1.f - lh) * p0[k2] + lh * p1[k2];
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = rel0[j] == 0 ? s0 : (rel0[j] == 1 ? s1 : s2);
+        const float x1 = rel1[j] == 0 ? s0 : (rel1[j] == 1 ? s1 : s2);
+        o[j] = x0 + lwj[j] * (x1 - x0);
+      }
+      TOut* dst = y + (static_cast<size_t>(n) * C + c) * plane + static_cast<size_t>(ho) * Wo + wo;
+      if (wo + 8 <= Wo && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (sizeof(TOut) == 2) {
+          uint4 pk;
+          pk.x = pack_half2(o[0], o[1]);
+          pk.y = pack_half2(o[2], o[3]);
+          pk.z = pack_half2(o[4], o[5]);
+          pk.w = pack_half2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dst) = pk;
+        } else {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          d4[0] = make_float4(o[0], o[1], o[2], o[3]);
+          d4[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (wo + j < Wo) dst[j] = static_cast<TOut>(o[j]);
+      }
+    }
+  }
+}
+
 int upsample_logits_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x, int xcs, void* y, int out_dtype,
                            cudaStream_t stream) {
   // tiled path: upsampling only, source window must fit in shared memory, 16-byte addressable source pixels
   const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  static const bool v2_on = [] { const char* e = getenv("FSB_UPSAMPLE_V2"); return e && e[0] == '1'; }();
+  // v2 needs the 8 columns of a thread to span <= 3 source columns: 7 * sw + 1 < 2  <=>  upsampling factor > 7
+  if (v2_on && sh <= 1.f && sw * 7.f < 0.999f && xcs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && xcs >= (C + 7) / 8 * 8) {
+    const int max_rows = static_cast<int>(sh * (kUp2Rows - 1)) + 3;
+    const int max_cols = static_cast<int>(sw * (kUpCols - 1)) + 3;
+    const size_t smem = static_cast<size_t>(max_rows) * C * max_cols * sizeof(float);
+    if (smem <= 48 * 1024) {
+      dim3 grid((Wo + kUpCols - 1) / kUpCols, (Ho + kUp2Rows - 1) / kUp2Rows, N);
+      if (out_dtype == 0)
+        FSB_LAUNCH(upsample_logits_rows_kernel<__half>, grid, dim3(256), smem, stream, N, C, Hi, Wi, Ho, Wo,
+                   static_cast<const __half*>(x), xcs, static_cast<__half*>(y), sh, sw, max_rows, max_cols);
+      else
+        FSB_LAUNCH(upsample_logits_rows_kernel<float>, grid, dim3(256), smem, stream, N, C, Hi, Wi, Ho, Wo,
+                   static_cast<const __half*>(x), xcs, static_cast<float*>(y), sh, sw, max_rows, max_cols);
+      cudaError_t e3 = last_launch_error();
+      if (e3 != cudaSuccess) return set_cuda_error(e3, "upsample_logits_rows launch");
+      return FSB_OK;
+    }
+  }
   if (sh <= 1.f && sw <= 1.f && xcs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && xcs >= (C + 7) / 8 * 8) {
     const int max_rows = static_cast<int>(sh * (kUpRows - 1)) + 3;
     const int max_cols = static_cast<int>(sw * (kUpCols - 1)) + 3;

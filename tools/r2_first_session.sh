@@ -11,6 +11,11 @@ tail -3 gpurun_out/r2_pytest_persist.log
 timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_pertile.log 2>&1
 FSB_CONV_PERSIST=1 timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_persist.log 2>&1
 tail -45 gpurun_out/r2_conv_bench_persist.log
+# 2b. barrier-free logits upsample (FSB_UPSAMPLE_V2=1): parity of everything that upsamples logits, then its time in the frame
+FSB_UPSAMPLE_V2=1 timeout 200 python -m pytest tests/test_kernels_gpu.py tests/test_student_gpu.py -x -q -k "upsample or logits or eval" > gpurun_out/r2_pytest_upsample_v2.log 2>&1
+tail -2 gpurun_out/r2_pytest_upsample_v2.log
+FSB_UPSAMPLE_V2=1 timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_upsample_v2.json 2> gpurun_out/r2_bench_upsample_v2.err
+cut -c1-200 gpurun_out/r2_bench_upsample_v2.json; echo
 # 3. headline metric both ways (no CPU baseline / supernet step: kernel comparison only)
 timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_pertile.json 2> gpurun_out/r2_bench_pertile.err
 FSB_CONV_PERSIST=1 timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_persist.json 2> gpurun_out/r2_bench_persist.err
