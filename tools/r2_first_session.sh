@@ -20,3 +20,6 @@ cut -c1-200 gpurun_out/r2_bench_upsample_v2.json; echo
 timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_pertile.json 2> gpurun_out/r2_bench_pertile.err
 FSB_CONV_PERSIST=1 timeout 150 python bench.py --no-cpu-baseline --no-supernet-step > gpurun_out/r2_bench_persist.json 2> gpurun_out/r2_bench_persist.err
 cut -c1-400 gpurun_out/r2_bench_pertile.json; echo; cut -c1-400 gpurun_out/r2_bench_persist.json
+# 4. N3: per-operator latency table of this GPU (667 entries, fast protocol)
+timeout 300 python tools/build_latency_table.py --out gpurun_out/latency_lookup_table_b200.npy > gpurun_out/r2_latency_table.log 2>&1
+tail -2 gpurun_out/r2_latency_table.log
