@@ -694,16 +694,22 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   if (persist_on && !cu && p.tma_store && d->Cout <= kPersistMaxCout && !(d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS)) &&
       m_tiles * n_tiles > sms && cols <= 256) {
     const size_t staging = static_cast<size_t>((n_tile + 63) / 64) * kTileM * 128;
-    const size_t budget = 200 * 1024;
-    int pst = static_cast<int>((budget - staging) / stage_bytes);
+    // tuning knobs for the first measurements: CTAs per SM (1 = whole shared memory for one pipeline, 2 = two issuers
+    // sharing the tensor core, TMEM 2 x 2 x cols <= 512) and a cap on the pipeline depth
+    static const int occ_env = [] { const char* v = getenv("FSB_PERSIST_OCC"); return (v && v[0] == '2') ? 2 : 1; }();
+    static const int stages_env = [] { const char* v = getenv("FSB_PERSIST_STAGES"); return v ? atoi(v) : 0; }();
+    const int occ = (occ_env == 2 && cols * 4 <= 512) ? 2 : 1;
+    const size_t budget = (occ == 2 ? 100 : 200) * 1024;
+    int pst = budget > staging ? static_cast<int>((budget - staging) / stage_bytes) : 0;
     if (pst > kMaxStages) pst = kMaxStages;
+    if (stages_env >= 2 && pst > stages_env) pst = stages_env;
     if (pst >= 2) {
       p.m_tiles = m_tiles;
       p.n_tiles = n_tiles;
       p.tmem_cols = cols * 2;  // two accumulators
       p.stages = pst;
       const size_t psmem = stage_bytes * pst + staging + 1024;
-      const unsigned ctas = static_cast<unsigned>(m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms);
+      const unsigned ctas = static_cast<unsigned>(m_tiles * n_tiles < sms * occ ? m_tiles * n_tiles : sms * occ);
       if (g.bk == 64) {
         static bool pattr64 = false;
         if (!pattr64) {

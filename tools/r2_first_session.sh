@@ -10,7 +10,8 @@ tail -3 gpurun_out/r2_pytest_persist.log
 # 2. per-layer timings, per-tile vs persistent (the table prints the student's conv shapes)
 timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_pertile.log 2>&1
 FSB_CONV_PERSIST=1 timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_persist.log 2>&1
-tail -45 gpurun_out/r2_conv_bench_persist.log
+FSB_CONV_PERSIST=1 FSB_PERSIST_OCC=2 timeout 120 python tools/conv_bench.py > gpurun_out/r2_conv_bench_persist_occ2.log 2>&1
+tail -30 gpurun_out/r2_conv_bench_persist.log; tail -30 gpurun_out/r2_conv_bench_persist_occ2.log
 # 2b. barrier-free logits upsample (FSB_UPSAMPLE_V2=1): parity of everything that upsamples logits, then its time in the frame
 FSB_UPSAMPLE_V2=1 timeout 200 python -m pytest tests/test_kernels_gpu.py tests/test_student_gpu.py -x -q -k "upsample or logits or eval" > gpurun_out/r2_pytest_upsample_v2.log 2>&1
 tail -2 gpurun_out/r2_pytest_upsample_v2.log
