@@ -57,6 +57,47 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
+def _lazy_worker(rank, world, port, q):
+    """`launch.install_data_parallel()` as the unmodified drivers get it: parameters are discovered lazily at the first
+    backward (the script builds its model AFTER the launcher ran), gradients are averaged over the ranks."""
+    sys.path.insert(0, ROOT)
+    os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank),
+                       "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+    from fasterseg_b200 import launch
+    sync = launch.install_data_parallel()
+    try:
+        assert sync is not None and sync.params == []
+        net = nn.Sequential(nn.Linear(6, 5), nn.ReLU(), nn.Linear(5, 3))          # built after the hooks, like the drivers do
+        frozen = nn.Linear(3, 3).requires_grad_(False)
+        full_x, full_y = torch.randn(8, 6), torch.randn(8, 3)                      # identical on both ranks (lock-step seed)
+        idx = slice(rank * 4, rank * 4 + 4)
+        ((frozen(net(full_x[idx])) - full_y[idx]) ** 2).mean().backward()
+        ref = nn.Sequential(nn.Linear(6, 5), nn.ReLU(), nn.Linear(5, 3))
+        ref.load_state_dict(net.state_dict())
+        # reference gradients through torch.autograd.grad: Tensor.backward is hooked process-wide
+        want = torch.autograd.grad(((frozen(ref(full_x)) - full_y) ** 2).mean(), list(ref.parameters()))
+        ok = all(torch.allclose(a.grad, b, atol=1e-6) for a, b in zip(net.parameters(), want))
+        ok = ok and sync.syncs == 1 and len(sync.params) >= 4 and all(p.requires_grad for p in sync.params)
+        q.put((rank, bool(ok)))
+    finally:
+        sync.uninstall()
+        dist.destroy_process_group()
+
+
+def test_launcher_data_parallel_hooks_discover_parameters_lazily():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_lazy_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
 def _run(mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
