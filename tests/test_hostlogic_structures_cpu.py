@@ -68,3 +68,51 @@ def test_eval_logits_match_the_reference_on_random_structures(reference_net, see
     agree = float((labels.long() == want.argmax(1)).float().mean())
     agree16 = float((half.argmax(1) == want.argmax(1)).float().mean())
     assert agree >= agree16 - 0.02
+
+
+@pytest.mark.parametrize("seed,lasts", [(1003, [0, 1, 2]), (1010, [2, 0]), (1017, [1]), (1045, [2, 1]), (1052, [1, 2])])
+def test_train_mode_auxiliary_heads_match_the_reference_on_random_structures(reference_net, seed, lasts):
+    """Train-mode build (auxiliary 1/16 and 1/32 heads, model_seg.py:217-226,298-335) for `lasts` combinations the shipped
+    genotypes do not cover: which features feed heads16 / heads32, in which order, and which predictions are None."""
+    from fasterseg_b200.model_seg import Network_Multi_Path_Infer
+
+    def build(Net):
+        alphas, betas, ratios = mk.clone_params(case)
+        m = Net(alphas, betas, ratios, num_classes=19, layers=case["layers"], Fch=12, width_mult_list=mk.WML,
+                stem_head_width=case["stem_head_width"], ignore_skip=case["ignore_skip"])
+        m.train()
+        m.build_structure(list(lasts))
+        return m
+
+    case = mk.draw_case(seed)
+    ref = build(reference_net)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        for mod in ref.modules():
+            if isinstance(mod, nn.Conv2d):
+                nn.init.kaiming_normal_(mod.weight, mode="fan_in", nonlinearity="relu")
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.weight.normal_(1.0, 0.1)
+                mod.bias.normal_(0, 0.1)
+    ours = build(Network_Multi_Path_Infer)
+    assert list(ours.state_dict()) == list(ref.state_dict())
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 3, 128, 256)
+    with torch.no_grad():
+        want = ref(x)
+        half = copy.deepcopy(ref)
+        half.load_state_dict(ours.state_dict())        # running stats as before the reference's forward touched them
+        half = half.half()
+        got16 = half(x.half())
+        with cpu_backend.installed():
+            got = ours(x)
+    assert len(got) == len(want) == 3
+    for name, g, w, h in zip(("pred8", "pred16", "pred32"), got, want, got16):
+        assert (g is None) == (w is None), name
+        if w is None:
+            continue
+        assert g.shape == w.shape
+        err = float((g.float() - w).norm() / w.norm())
+        err16 = float((h.float() - w).norm() / w.norm())
+        print("seed %d lasts %s %s: ours %.3e | reference in fp16 %.3e" % (seed, lasts, name, err, err16))
+        assert err <= 1.5 * err16 + 5e-3, name
