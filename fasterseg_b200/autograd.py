@@ -31,6 +31,135 @@ def set_grad_scale(v: float):
     GRAD_SCALE = float(v)
 
 
+# ----------------------------------------------------------------------------------------------
+# EXPERIMENTAL (FSB_TAPE=1, default off): one torch.autograd node per network forward.
+#
+# The supernet step is bound by Python time per unit, and a large share of that is
+# torch.autograd.Function.apply itself (ctx construction, functorch bookkeeping, engine dispatch: ~30 us forward + ~30 us
+# backward per node, ~5 400 nodes per step).  With the tape enabled a whole forward pass runs inside ONE autograd node:
+# every unit below is executed through `call()`, which runs `Fn.forward` on a minimal context object and appends it to a
+# list; the node's backward replays the list in reverse, accumulating activation gradients with our add kernel.  The
+# scalar plumbing on the architecture parameters (softmax, gumbel sampling, weight * width-score products) stays ordinary
+# torch autograd: it runs under enable_grad inside the node and is differentiated at the end of the replay.
+# The Function classes are unchanged -- the tape only replaces who calls their forward / backward.
+# ----------------------------------------------------------------------------------------------
+TAPE_ENABLED = _os.environ.get("FSB_TAPE", "0") == "1"
+_TAPE = None
+
+
+class _NodeCtx:
+    """what our Function.forward / backward use of autograd's ctx: save_for_backward, saved_tensors, needs_input_grad and
+    free-form attributes"""
+    saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+class Tape:
+    def __init__(self):
+        self.nodes = []        # (Function class, ctx, args, output) in execution order
+        self.tracked = set()   # ids of tape-produced tensors that need a gradient
+        self.keep = []         # every tape-produced tensor stays alive until backward, so ids are unique
+
+    def needs(self, t):
+        return isinstance(t, torch.Tensor) and (t.requires_grad or id(t) in self.tracked)
+
+    def record(self, fn, args):
+        ctx = _NodeCtx()
+        ctx.needs_input_grad = tuple(self.needs(a) for a in args)
+        prev = torch.is_grad_enabled()
+        torch._C._set_grad_enabled(False)          # like Function.forward
+        try:
+            out = fn.forward(ctx, *args)
+        finally:
+            torch._C._set_grad_enabled(prev)
+        if any(ctx.needs_input_grad):
+            self.tracked.add(id(out))
+            self.nodes.append((fn, ctx, args, out))
+        self.keep.append(out)
+        return out
+
+    def backward(self, out_grads):
+        """out_grads: {id(output tensor): gradient}.  Returns {id: (leaf tensor, gradient)} for everything that is not a
+        tape intermediate: parameters and tensors of the surrounding torch autograd graph (the scalar plumbing)."""
+        grads = dict(out_grads)
+        leaves = {}
+        for fn, ctx, args, out in reversed(self.nodes):
+            g = grads.pop(id(out), None)
+            if g is None:
+                continue
+            res = fn.backward(ctx, g)
+            if not isinstance(res, tuple):
+                res = (res,)
+            for a, need, ga in zip(args, ctx.needs_input_grad, res):
+                if ga is None or not need:
+                    continue
+                key = id(a)
+                if key in self.tracked:
+                    have = grads.get(key)
+                    grads[key] = ga if have is None else F_.add_inplace(ga, have)   # have += ga on our kernel
+                else:
+                    have = leaves.get(key)
+                    leaves[key] = (a, ga) if have is None else (a, have[1] + ga)
+        return leaves
+
+
+def call(fn, *args):
+    """Execute one unit: as its own torch.autograd node (default) or on the active tape."""
+    if _TAPE is None:
+        return fn.apply(*args)
+    return _TAPE.record(fn, args)
+
+
+class TapedForwardFn(torch.autograd.Function):
+    """forward(body, n_inputs, *inputs, *parameters): runs `body(*inputs)` with a tape active and returns its tuple of
+    output tensors; backward replays the tape and hands every parameter its gradient."""
+
+    @staticmethod
+    def forward(ctx, body, n_inputs, *tensors):
+        global _TAPE
+        assert _TAPE is None, "nested taped forwards are not supported"
+        tape = Tape()
+        _TAPE = tape
+        try:
+            with torch.enable_grad():      # scalar plumbing on the architecture parameters builds a normal torch graph
+                outs = body(*tensors[:n_inputs])
+        finally:
+            _TAPE = None
+        outs = tuple(outs) if isinstance(outs, (tuple, list)) else (outs,)
+        ctx.tape = tape
+        ctx.out_ids = [id(o) for o in outs]
+        ctx.params = tensors[n_inputs:]
+        ctx.n_inputs = n_inputs
+        ctx.mark_non_differentiable(*[o for o in outs if id(o) not in tape.tracked])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        leaves = ctx.tape.backward({oid: g for oid, g in zip(ctx.out_ids, gouts) if g is not None})
+        result = {}
+        plumbing, plumbing_grads = [], []
+        for t, g in leaves.values():
+            if t.grad_fn is not None:          # produced by torch ops from the architecture parameters
+                plumbing.append(t)
+                plumbing_grads.append(g.to(t.dtype).reshape(t.shape))
+            else:
+                result[id(t)] = g
+        if plumbing:
+            # differentiate the scalar plumbing: accumulates straight into the .grad of the architecture parameters, which is
+            # what the outer engine would do with returned gradients (re-entrant autograd is allowed inside a backward)
+            torch.autograd.backward(plumbing, plumbing_grads)
+        ctx.tape = None
+        return (None, None) + (None,) * ctx.n_inputs + tuple(result.get(id(p)) for p in ctx.params)
+
+
+def run_taped(module, body, *inputs):
+    """One autograd node for `body(*inputs)`; all parameters of `module` that require a gradient are its inputs."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    return TapedForwardFn.apply(body, len(inputs), *inputs, *params)
+
+
 def _dy(t):
     """Incoming gradient as an NHWC fp16 view (autograd may hand us a differently-strided tensor after accumulation)."""
     if F_.is_nhwc_half(t):
@@ -290,43 +419,45 @@ class CatFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 def conv_bn_act_train(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
     assert conv.bias is None, "conv bias followed by train-mode BN is not on the hot path"
-    y = ConvBnActFn.apply(x, conv.weight, bn.weight, bn.bias, conv, bn, relu, ci, co, off)
+    y = call(ConvBnActFn, x, conv.weight, bn.weight, bn.bias, conv, bn, relu, ci, co, off)
     if out is not None:  # autograd-visible copy into a caller-provided slot (training path does not use zero-copy concat)
         raise RuntimeError("out= is an inference-only fast path")
     return y
 
 
 def conv_bias_act(x, conv, relu, ci, co):
-    return ConvBiasFn.apply(x, conv.weight, conv.bias, conv, relu, ci, co)
+    return call(ConvBiasFn, x, conv.weight, conv.bias, conv, relu, ci, co)
 
 
 def factorized_reduce_train(op, x, bn, ci, co_half, out=None):
     if out is not None:
         raise RuntimeError("out= is an inference-only fast path")
-    return FactorizedReduceFn.apply(x, op.conv1.weight, op.conv2.weight, bn.weight, bn.bias, op, bn, ci, co_half)
+    return call(FactorizedReduceFn, x, op.conv1.weight, op.conv2.weight, bn.weight, bn.bias, op, bn, ci, co_half)
 
 
 def bilinear(x, size, relu=False):
-    return BilinearFn.apply(x, (int(size[0]), int(size[1])), relu)
+    return call(BilinearFn, x, (int(size[0]), int(size[1])), relu)
 
 
 def upsample_logits(x, size, dtype=torch.float32):
-    return UpsampleLogitsFn.apply(x, (int(size[0]), int(size[1])), dtype)
+    return call(UpsampleLogitsFn, x, (int(size[0]), int(size[1])), dtype)
 
 
 def to_nchw(x, dtype=torch.float32):
-    return ToNCHWFn.apply(x, dtype)
+    return call(ToNCHWFn, x, dtype)
 
 
 def weighted_sum(wts, xs):
-    return WsumFn.apply(wts, *xs)
+    return call(WsumFn, wts, *xs)
 
 
 def cat_channels(xs):
     xs = [F_.to_nhwc_half(t) for t in xs]
-    return xs[0] if len(xs) == 1 else CatFn.apply(*xs)
+    return xs[0] if len(xs) == 1 else call(CatFn, *xs)
 
 
 def grad_mode(*tensors):
     """True when an autograd graph must be recorded for these inputs."""
+    if _TAPE is not None:
+        return any(_TAPE.needs(t) for t in tensors)
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)

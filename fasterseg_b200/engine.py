@@ -83,7 +83,8 @@ def conv_bn_act(x: torch.Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], 
     wp = packed_weight(conv, ci, co)
     bn = active_bn(bn) if bn is not None else None
     training = bn is not None and (bn.training or bn.running_mean is None)
-    want_grad = torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)
+    from . import autograd as AG
+    want_grad = AG.grad_mode(x, conv.weight)
     if not training:
         if want_grad and bn is None:
             from .autograd import conv_bias_act  # conv (+bias) with backward, e.g. Head.conv_1x1

@@ -80,7 +80,7 @@ def _resolve_ratio(r, width_mult_list):
 
 
 def _needs_graph(*tensors):
-    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+    return AG.grad_mode(*tensors)
 
 
 class MixedOp(nn.Module):
@@ -276,6 +276,11 @@ class Network_Multi_Path(nn.Module):
     # execution
     # ---------------------------------------------------------------------------------------------------------
     def forward(self, input):
+        if AG.TAPE_ENABLED and AG._TAPE is None and self.training and torch.is_grad_enabled():
+            return AG.run_taped(self, self._forward, input)   # EXPERIMENTAL: the whole pass as one autograd node
+        return self._forward(input)
+
+    def _forward(self, input):
         idx = self.arch_idx
         refine16, refine32 = self.refine16[idx], self.refine32[idx]
         alphas, betas = self._distributions()
@@ -413,7 +418,7 @@ class Network_Multi_Path(nn.Module):
 
 # ------------------------------------------------------------------------------------------------------------
 def _grad(*ts):
-    return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
+    return AG.grad_mode(*ts)
 
 
 def _cat(tensors):

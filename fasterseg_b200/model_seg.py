@@ -216,8 +216,8 @@ class Network_Multi_Path_Infer(nn.Module):
         """arm 1x1 -> bilinear to skip's size -> cat([up, skip]) -> refine 3x3, with the concat done by writing both
         producers into one buffer (model_seg.py:304-307, 309-312, 316-319)."""
         a = arm(coarse)
-        if torch.is_grad_enabled() and a.requires_grad:
-            from . import autograd as AG
+        from . import autograd as AG
+        if AG.grad_mode(a):
             up = AG.bilinear(a, (skip.shape[2], skip.shape[3]))
             return refine(AG.cat_channels([up, skip]))
         N, c_up = a.shape[0], a.shape[1]
@@ -270,7 +270,8 @@ class Network_Multi_Path_Infer(nn.Module):
         if fused_in is None:
             ref = outputs8[0]
             fused_in = F_.empty_nhwc(ref.shape[0], f8 * self._branch, ref.shape[2], ref.shape[3], ref.device)  # cat(pred8)
-        grad = torch.is_grad_enabled() and any(t.requires_grad for t in outputs8 + outputs16 + outputs32)
+        from . import autograd as AG
+        grad = AG.grad_mode(*(outputs8 + outputs16 + outputs32))
         aux = {16: [], 32: []}          # train mode: inputs of the auxiliary heads, in branch order
         at8 = []
         for tail in self._tails:
@@ -307,6 +308,18 @@ class Network_Multi_Path_Infer(nn.Module):
         return self.agg_ffm(outputs8, outputs16, outputs32, ctx)
 
     def forward(self, input):
+        from . import autograd as AG
+        if AG.TAPE_ENABLED and AG._TAPE is None and self.training and torch.is_grad_enabled():
+            # EXPERIMENTAL: the whole pass as one autograd node; absent auxiliary predictions come back as None
+            live = [0] + ([1] if any(last in (1, 2) for last in self.lasts) else []) + ([2] if 2 in self.lasts else [])
+            outs = AG.run_taped(self, lambda x: tuple(p for p in self._forward(x) if p is not None), input)
+            full = [None, None, None]
+            for i, o in zip(live, outs):
+                full[i] = o
+            return tuple(full)
+        return self._forward(input)
+
+    def _forward(self, input):
         if not self.training:
             pred8 = self._features(input)
             return F_.upsample_logits(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), dtype=self.logits_dtype)
@@ -401,8 +414,8 @@ class _BranchCtx:
 
 
 def _upsample_logits(x, size, dtype):
-    if torch.is_grad_enabled() and x.requires_grad:
-        from . import autograd as AG
+    from . import autograd as AG
+    if AG.grad_mode(x):
         return AG.upsample_logits(x, size, dtype)
     return F_.upsample_logits(x, size, dtype=dtype)
 
@@ -412,8 +425,8 @@ def _cat_channels(tensors):
     tensors = [F_.to_nhwc_half(t) for t in tensors]
     if len(tensors) == 1:
         return tensors[0]
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-        from . import autograd as AG
+    from . import autograd as AG
+    if AG.grad_mode(*tensors):
         return AG.cat_channels(tensors)
     N, _, H, W = tensors[0].shape
     total = sum(t.shape[1] for t in tensors)

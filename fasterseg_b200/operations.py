@@ -229,9 +229,8 @@ class _Residual(_Primitive):
             return x
         x = F_.to_nhwc_half(x)
         H, W = int(x.size(2)), int(x.size(3))
-        grad = torch.is_grad_enabled() and (x.requires_grad or self.conv1.weight.requires_grad)
-        if grad:
-            from . import autograd as AG
+        from . import autograd as AG
+        if AG.grad_mode(x, self.conv1.weight):
             y = AG.bilinear(x, (H // 2, W // 2))
             for i, (conv, bn) in enumerate(stages):
                 last = i == len(stages) - 1
@@ -345,7 +344,8 @@ def _factorized_reduce_s2(op, x, out):
     N, _, H, W = x.shape
     assert H % 2 == 0 and W % 2 == 0, "FactorizedReduce needs even H, W (the reference's cat fails otherwise)"
     co = 2 * co_half
-    if bn.training and torch.is_grad_enabled() and (x.requires_grad or op.conv1.weight.requires_grad):
+    from .autograd import grad_mode
+    if bn.training and grad_mode(x, op.conv1.weight):
         from .autograd import factorized_reduce_train
         return factorized_reduce_train(op, x, bn, ci, co_half, out)
     if out is None:

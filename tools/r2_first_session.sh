@@ -24,3 +24,9 @@ cut -c1-400 gpurun_out/r2_bench_pertile.json; echo; cut -c1-400 gpurun_out/r2_be
 # 4. N3: per-operator latency table of this GPU (667 entries, fast protocol)
 timeout 300 python tools/build_latency_table.py --out gpurun_out/latency_lookup_table_b200.npy > gpurun_out/r2_latency_table.log 2>&1
 tail -2 gpurun_out/r2_latency_table.log
+# 5. tape mode (FSB_TAPE=1: one autograd node per forward pass): training parity, then the step time both ways
+FSB_TAPE=1 timeout 300 python -m pytest tests/test_supernet_gpu.py tests/test_student_gpu.py tests/test_ops_gpu.py -x -q > gpurun_out/r2_pytest_tape.log 2>&1
+tail -2 gpurun_out/r2_pytest_tape.log
+timeout 120 python tools/search_step_bench.py --mode pretrain --steps 5 --warmup 2 > gpurun_out/r2_pretrain_step.log 2>&1; tail -1 gpurun_out/r2_pretrain_step.log
+FSB_TAPE=1 timeout 120 python tools/search_step_bench.py --mode pretrain --steps 5 --warmup 2 > gpurun_out/r2_pretrain_step_tape.log 2>&1; tail -1 gpurun_out/r2_pretrain_step_tape.log
+FSB_TAPE=1 timeout 120 python tools/search_step_bench.py --mode search --steps 3 --warmup 1 > gpurun_out/r2_search_step_tape.log 2>&1; tail -1 gpurun_out/r2_search_step_tape.log
