@@ -272,20 +272,35 @@ def frame_sigma_roofline(model, x, frame_us):
 def supernet_step_metric():
     """Second half of BASELINE.json's metric: supernet pretrain step (configs[2], 3x3x256x512 per GPU, 16 layers, 252 M
     parameters: 4 forwards + backward + clip + SGD) through the reference-facing classes.  Extra key only -- it never fails
-    the headline line.  Multi-GPU numbers for it come from `torchrun ... tools/search_step_bench.py` (profiles/)."""
+    the headline line.  Measured per-unit (the default autograd wiring) and, if that works on this box, with the
+    experimental tape mode (FSB_TAPE: one autograd node per forward pass, same kernels, same work); the tape number is only
+    reported when its loss agrees with the per-unit run.  Multi-GPU numbers come from `torchrun ... tools/search_step_bench.py`."""
     try:
         import importlib.util
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "search_step_bench.py")
         spec = importlib.util.spec_from_file_location("search_step_bench", path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        res = mod.measure("pretrain", 16, steps=3, warmup=2)
+        res = mod.measure("pretrain", 16, steps=3, warmup=2, tape=False)
         res["timing"] = "host wall clock around step + synchronize, median of 3 (the step is host-launch-bound: ~20 k launches)"
+        try:
+            taped = mod.measure("pretrain", 16, steps=3, warmup=2, tape=True)
+            same = abs(taped["loss"] - res["loss"]) <= 2e-2 * abs(res["loss"])   # same seeds, same data; chaotic net -> loose
+            res["tape_mode"] = {"value": taped["value"], "min_ms": taped["min_ms"], "loss": taped["loss"], "loss_agrees": bool(same),
+                                "what": "FSB_TAPE=1 (experimental, default off): one torch.autograd node per forward pass"}
+        except Exception as e:  # noqa: BLE001
+            res["tape_mode"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        finally:
+            from fasterseg_b200 import autograd as AG
+            AG.TAPE_ENABLED = os.environ.get("FSB_TAPE", "0") == "1"
         return res
     except Exception as e:  # noqa: BLE001 -- secondary metric, reported not raised
         return {"error": "%s: %s" % (type(e).__name__, e)}
     finally:
-        torch.cuda.empty_cache()
+        try:
+            torch.cuda.empty_cache()
+        except Exception:  # noqa: BLE001 -- a poisoned context must not take the headline line down
+            pass
 
 
 def main():

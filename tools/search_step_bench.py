@@ -45,8 +45,12 @@ def weight_params(m):
     return ps
 
 
-def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1):
-    """Time `steps` optimizer steps; returns the result dict (identical on every rank)."""
+def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape=None):
+    """Time `steps` optimizer steps; returns the result dict (identical on every rank).
+    tape: None = whatever FSB_TAPE says; True / False = force the experimental one-node-per-forward autograd mode."""
+    from fasterseg_b200 import autograd as AG
+    if tape is not None:
+        AG.TAPE_ENABLED = bool(tape)
     args = argparse.Namespace(mode=mode, layers=layers, steps=steps, warmup=warmup)
     parallel.seed_all_ranks_identically(12345)   # identical weights + lock-step width sampling / gumbel noise on every rank
     model = build(args.layers)
@@ -97,7 +101,7 @@ def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1):
         sync.uninstall()
     return {"metric": "supernet_%s_step_ms" % args.mode, "value": round(dt * 1e3, 1), "min_ms": round(tmin * 1e3, 1),
             "max_ms": round(tmax * 1e3, 1), "unit": "ms/step", "n_gpus": world, "layers": args.layers, "steps": args.steps,
-            "warmup": args.warmup, "batch_per_gpu": [B, 3, H, W], "images_per_s": round(B * world / dt, 2),
+            "warmup": args.warmup, "autograd": "tape" if AG.TAPE_ENABLED else "per-unit", "batch_per_gpu": [B, 3, H, W], "images_per_s": round(B * world / dt, 2),
             "grad_syncs": sync.syncs if sync else 0, "loss": float(loss.detach()),
             "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
             "mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
