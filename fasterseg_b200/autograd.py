@@ -67,7 +67,8 @@ class Tape:
 
     def record(self, fn, args):
         ctx = _NodeCtx()
-        ctx.needs_input_grad = tuple(self.needs(a) for a in args)
+        tracked, tensor = self.tracked, torch.Tensor
+        ctx.needs_input_grad = tuple(isinstance(a, tensor) and (a.requires_grad or id(a) in tracked) for a in args)
         prev = torch.is_grad_enabled()
         torch._C._set_grad_enabled(False)          # like Function.forward
         try:
