@@ -222,7 +222,7 @@ class ConvBnActFn(torch.autograd.Function):
             ctx.fused, ctx.desc = True, d
             ctx.save_for_backward(x, raw, y, vec, gamma)
             return y
-        stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
+        stats = F_.conv_stats_buffer(x, co, k, s, p, off=off)
         raw = F_.conv_fwd(x, wp, co, k, s, p, relu=False, off=off, stats=stats, out_f32=True)
         N, _, Ho, Wo = raw.shape
         stats = engine.dp_allreduce_stats(stats)
@@ -304,11 +304,10 @@ class FactorizedReduceFn(torch.autograd.Function):
         p1 = engine.packed_weight(op.conv1, ci, co_half)
         p2 = engine.packed_weight(op.conv2, ci, co_half)
         raw = F_.empty_nhwc(N, co, H // 2, W // 2, x.device, dtype=torch.float32)
-        s1 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
-        s2 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
-        F_.conv_fwd(x, p1, co_half, 1, 2, 0, out=raw[:, :co_half], stats=s1, out_f32=True)
-        F_.conv_fwd(x, p2, co_half, 1, 2, 0, out=raw[:, co_half:], off=(1, 1), stats=s2, out_f32=True)
-        stats = torch.cat([s1[:co_half], s2[:co_half], s1[co_half:], s2[co_half:]])
+        # both halves write their columns of ONE statistics buffer (rows are per spatial tile, identical for the two convs)
+        stats = F_.conv_stats_buffer(x, co_half, 1, 2, 0, total_C=co)
+        F_.conv_fwd(x, p1, co_half, 1, 2, 0, out=raw[:, :co_half], stats=stats, out_f32=True)
+        F_.conv_fwd(x, p2, co_half, 1, 2, 0, out=raw[:, co_half:], off=(1, 1), stats=stats, stats_off=co_half, out_f32=True)
         stats = engine.dp_allreduce_stats(stats)
         count = N * (H // 2) * (W // 2) * engine.dp_world_size()
         scale, shift, mean, invstd = F_.bn_finalize(stats, count, gamma, beta, bn.eps, 0.1 if bn.momentum is None else bn.momentum,

@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface of libfsb200.so (declared in include/fsb200.h).
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -37,6 +38,47 @@ int sm_count() {
   return n;
 }
 
+static const char* const kOptNames[OPT_COUNT] = {"FSB_CONV_TC2", "FSB_TC2_R", "FSB_TC2_ASTAGES", "FSB_NO_TMA_STORE",
+                                                 "FSB_DGRAD_S2_DIRECT", "FSB_WGRAD_TC", "FSB_CONV_PERSIST", "FSB_PERSIST_OCC",
+                                                 "FSB_PERSIST_STAGES", "FSB_UPSAMPLE_V2", "FSB_DETERMINISTIC", "FSB_CONV_TC3"};
+static int g_opts[OPT_COUNT];
+static std::once_flag g_opts_once;
+static void load_opts() {
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    const char* e = getenv(kOptNames[i]);
+    g_opts[i] = (e && e[0]) ? atoi(e) : -1;
+  }
+}
+int opt(Opt o) {
+  std::call_once(g_opts_once, load_opts);
+  return g_opts[o];
+}
+
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
+  struct Entry { const void* k; unsigned long long mask; };
+  static Entry table[32];
+  static int n = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDevice");
+  const unsigned long long bit = 1ull << (dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* hit = nullptr;
+  for (int i = 0; i < n; ++i)
+    if (table[i].k == kernel) hit = &table[i];
+  if (hit && (hit->mask & bit)) return FSB_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  if (!hit && n < 32) {
+    table[n].k = kernel;
+    table[n].mask = 0;
+    hit = &table[n++];
+  }
+  if (hit) hit->mask |= bit;
+  return FSB_OK;
+}
+
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
   static std::once_flag once;
@@ -62,14 +104,20 @@ int nhwc_to_nchw_launch(int, int, int, int, const void*, int, void*, int, cudaSt
 int copy_channels_launch(int64_t, int, const void*, int, void*, int, cudaStream_t);
 int bn_fold_launch(int, const float*, const float*, const float*, const float*, float, const float*, float*, float*, cudaStream_t);
 int bn_stats_launch(int64_t, int, const void*, int, int, float*, cudaStream_t);
-int bn_finalize_launch(int, const float*, double, const float*, const float*, float, float, float*, float*, float*, float*,
-                       float*, float*, cudaStream_t, long long* = nullptr);
+int stat_rows(int64_t);
+int wsum_rows(int64_t, int);
+int rowsum_launch(int, const float*, int, int, float*, cudaStream_t);
+int conv_tc_m_tiles(const fsb_conv_desc*);
+int conv_tc2_ctas(const fsb_conv_desc*);
+int bn_finalize_launch(int, const float*, int, int, double, const float*, const float*, float, float, float*, float*, float*, float*,
+                       float*, float*, cudaStream_t, long long* = nullptr, const fsb_bn_sel* = nullptr, const int* = nullptr);
 int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t);
 
 int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*, int,
                          float*, cudaStream_t);
 int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
-                        const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t);
+                        const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t, int = 1,
+                        const fsb_bn_sel* = nullptr, const int* = nullptr);
 int relu_bwd_launch(int64_t, int, const void*, int, const void*, int, void*, int, cudaStream_t);
 fsb_conv_desc dgrad_as_fwd_desc(const fsb_conv_desc*, int, int);
 int pack_dgrad_launch(const fsb_conv_desc*, const float*, int64_t, int64_t, void*, cudaStream_t);
@@ -116,6 +164,37 @@ const char* fsb_last_error_string(void) { return g_err; }
 int fsb_set_pdl(int enabled) {
   g_pdl = enabled ? 1 : 0;
   return FSB_OK;
+}
+
+static int find_opt(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptNames[i]) == 0) return i;
+  return -1;
+}
+int fsb_set_option(const char* name, int value) {
+  const int i = find_opt(name);
+  if (i < 0) return set_error(FSB_ERR_INVALID, "fsb_set_option: unknown option");
+  opt(static_cast<Opt>(i));  // make sure the environment has been read, then override
+  g_opts[i] = value;
+  return FSB_OK;
+}
+int fsb_get_option(const char* name) {
+  const int i = find_opt(name);
+  return i < 0 ? -1 : opt(static_cast<Opt>(i));
+}
+
+int fsb_conv_stats_rows(const fsb_conv_desc* d) {
+  if (check_desc(d)) return 0;
+  if ((d->flags & FSB_CONV_FORCE_DIRECT) || !conv_tc_supported(d)) return stat_rows(static_cast<int64_t>(d->N) * d->Ho * d->Wo);
+  if (conv_tc2_supported(d)) return conv_tc2_ctas(d);
+  return conv_tc_m_tiles(d);
+}
+int fsb_stat_rows(int64_t pixels) { return stat_rows(pixels); }
+int fsb_wsum_rows(int64_t pixels, int C) { return wsum_rows(pixels, C); }
+int fsb_rowsum(int L, const float* src, int rows, int stride, float* out, void* stream) {
+  if (L <= 0 || rows <= 0 || !src || !out || stride < L) return set_error(FSB_ERR_INVALID, "rowsum: bad argument");
+  return rowsum_launch(L, src, rows, stride, out, static_cast<cudaStream_t>(stream));
 }
 
 int fsb_debug_set_buffer(void* dev_u64x128) {
@@ -204,11 +283,11 @@ int fsb_bn_stats(int64_t pixels, int C, const void* x, int xcs, float* stats, vo
   if (pixels <= 0 || C <= 0 || !x || !stats) return set_error(FSB_ERR_INVALID, "bn_stats: bad argument");
   return bn_stats_launch(pixels, C, x, xcs, 0, stats, static_cast<cudaStream_t>(stream));
 }
-int fsb_bn_finalize(int C, const float* stats, double count, const float* gamma, const float* beta, float eps, float momentum,
-                    float* running_mean, float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
-                    void* stream) {
-  if (C <= 0 || !stats || count <= 0) return set_error(FSB_ERR_INVALID, "bn_finalize: bad argument");
-  return bn_finalize_launch(C, stats, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
+int fsb_bn_finalize(int C, const float* stats, int rows, int SC, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, void* stream) {
+  if (C <= 0 || !stats || count <= 0 || rows <= 0 || SC < C) return set_error(FSB_ERR_INVALID, "bn_finalize: bad argument");
+  return bn_finalize_launch(C, stats, rows, SC, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
                             save_invstd, static_cast<cudaStream_t>(stream));
 }
 int fsb_affine_act(int64_t pixels, int C, const void* x, int xcs, const float* scale, const float* shift, void* y, int ycs,
@@ -227,11 +306,11 @@ int fsb_bn_bwd_reduce(int64_t pixels, int C, const void* dy, int dcs, const void
 }
 int fsb_bn_bwd_apply(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
                      int raw_is_f32, const float* mean, const float* invstd, const float* gamma, const float* sums, double count, int relu,
-                     void* draw, int ocs, float* dgamma, float* dbeta, float gscale, void* stream) {
+                     void* draw, int ocs, float* dgamma, float* dbeta, float gscale, int accumulate, void* stream) {
   if (pixels <= 0 || C <= 0 || !dy || !raw || !mean || !invstd || !sums || !draw || count <= 0 || gscale <= 0 || (relu && !y))
     return set_error(FSB_ERR_INVALID, "bn_bwd_apply: bad argument");
   return bn_bwd_apply_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, gamma, sums, count, relu, draw, ocs,
-                             dgamma, dbeta, gscale, static_cast<cudaStream_t>(stream));
+                             dgamma, dbeta, gscale, static_cast<cudaStream_t>(stream), accumulate);
 }
 int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, void* dx, int xcs, void* stream) {
   if (pixels <= 0 || C <= 0 || !dy || !y || !dx) return set_error(FSB_ERR_INVALID, "relu_bwd: bad argument");

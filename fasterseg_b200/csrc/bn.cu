@@ -29,12 +29,51 @@ int bn_fold_launch(int C, const float* gamma, const float* beta, const float* me
   return FSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Deterministic statistics.  No kernel of this library accumulates BatchNorm statistics with floating-point atomics
+// (their arrival order changes from run to run, and a chain of BatchNorm layers amplifies the last-bit differences into
+// percent-level gradient differences).  Instead every producer CTA writes ONE partial row
+//     row[r][0 .. SC)  = per-channel sum,   row[r][SC .. 2*SC) = per-channel sum of squares   (row stride 2*SC floats)
+// and the consumer adds the rows in index order (bn_finalize folds that in; rowsum_kernel is the stand-alone form).
+// ------------------------------------------------------------------------------------------
+int stat_rows(int64_t pixels) {
+  int64_t b = (pixels + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 2) b = 148 * 2;
+  return static_cast<int>(b);
+}
+
+// out[c] = sum_r rows[r * stride + c], r ascending, accumulated in double: one block = 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) rowsum_kernel(int L, const float* __restrict__ rows, int P, int stride, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double sh[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double acc = 0.0;
+  if (c < L)
+    for (int r = ty; r < P; r += 8) acc += static_cast<double>(rows[static_cast<size_t>(r) * stride + c]);
+  sh[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < L) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    out[c] = static_cast<float>(t);
+  }
+}
+int rowsum_launch(int L, const float* rows, int P, int stride, float* out, cudaStream_t stream) {
+  FSB_LAUNCH(rowsum_kernel, dim3((L + 31) / 32), dim3(256), 0, stream, L, rows, P, stride, out);
+  cudaError_t e = last_launch_error();
+  if (e != cudaSuccess) return set_cuda_error(e, "rowsum launch");
+  return FSB_OK;
+}
+
 // per-channel sum / sumsq of an fp16 NHWC tensor.  Block = 256 threads = (256 / cvec_lanes) pixel rows x channel
 // vectors; each thread owns 8 channels (one 16-byte load per pixel), accumulates in fp32 registers, then the block
-// reduces through shared memory and issues one atomicAdd per channel.  Warp-shuffle is not needed for the cross-pixel
-// reduction because a thread's 8 channels never change; the smem tree adds the pixel-row partials.
+// reduces through shared memory in a fixed order and writes its partial row (blockIdx.x).
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(int64_t pixels, int C, const __half* __restrict__ x, int xcs, float* __restrict__ stats) {
+bn_stats_kernel(int64_t pixels, int C, const __half* __restrict__ x, int xcs, float* __restrict__ rows_out, int SC) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];  // [rows][C*2]
@@ -65,20 +104,21 @@ bn_stats_kernel(int64_t pixels, int C, const __half* __restrict__ x, int xcs, fl
     }
   }
   __syncthreads();
+  float* out = rows_out + static_cast<size_t>(blockIdx.x) * 2 * SC;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int r = 0; r < rows; ++r) {
       a += red[(r * C + c) * 2 + 0];
       b += red[(r * C + c) * 2 + 1];
     }
-    atomicAdd(&stats[c], a);
-    atomicAdd(&stats[C + c], b);
+    out[c] = a;
+    out[SC + c] = b;
   }
 }
 // generic (any C / stride) fallback: block = 32 channels x 8 pixel rows
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_stats_generic_kernel(int64_t pixels, int C, const T* __restrict__ x, int xcs, float* __restrict__ stats) {
+bn_stats_generic_kernel(int64_t pixels, int C, const T* __restrict__ x, int xcs, float* __restrict__ rows_out, int SC) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[8][32][2];
@@ -99,22 +139,22 @@ bn_stats_generic_kernel(int64_t pixels, int C, const T* __restrict__ x, int xcs,
       s += red[r][threadIdx.x][0];
       q += red[r][threadIdx.x][1];
     }
-    atomicAdd(&stats[c], s);
-    atomicAdd(&stats[C + c], q);
+    float* out = rows_out + static_cast<size_t>(blockIdx.x) * 2 * SC;
+    out[c] = s;
+    out[SC + c] = q;
   }
 }
 
-int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* stats, cudaStream_t stream) {
+// writes stat_rows(pixels) partial rows (row stride 2*SC; `rows` already points at the channel offset of this tensor)
+int bn_stats_rows_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* rows, int SC, cudaStream_t stream) {
+  const int P = stat_rows(pixels);
   if (x_is_f32 || C % 8 || xcs % 8 || C > 2048 || (reinterpret_cast<uintptr_t>(x) & 15)) {
-    int64_t gx = (pixels + 63) / 64;
-    if (gx > 148 * 2) gx = 148 * 2;
-    if (gx < 1) gx = 1;
     if (x_is_f32)
-      FSB_LAUNCH(bn_stats_generic_kernel<float>, dim3(static_cast<unsigned>(gx), (C + 31) / 32), dim3(256), 0, stream, pixels, C,
-                 static_cast<const float*>(x), xcs, stats);
+      FSB_LAUNCH(bn_stats_generic_kernel<float>, dim3(static_cast<unsigned>(P), (C + 31) / 32), dim3(256), 0, stream, pixels, C,
+                 static_cast<const float*>(x), xcs, rows, SC);
     else
-      FSB_LAUNCH(bn_stats_generic_kernel<__half>, dim3(static_cast<unsigned>(gx), (C + 31) / 32), dim3(256), 0, stream, pixels, C,
-                 static_cast<const __half*>(x), xcs, stats);
+      FSB_LAUNCH(bn_stats_generic_kernel<__half>, dim3(static_cast<unsigned>(P), (C + 31) / 32), dim3(256), 0, stream, pixels, C,
+                 static_cast<const __half*>(x), xcs, rows, SC);
     cudaError_t e0 = last_launch_error();
     if (e0 != cudaSuccess) return set_cuda_error(e0, "bn_stats_generic launch");
     return FSB_OK;
@@ -122,27 +162,73 @@ int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32,
   const int cvec = C / 8;
   const int threads = 256;
   if (cvec > threads) return set_error(FSB_ERR_INVALID, "bn_stats: C too large");
-  const int rows = threads / cvec;
-  int64_t blocks = (pixels + rows * 8 - 1) / (rows * 8);
-  if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  const size_t smem = static_cast<size_t>(rows) * C * 2 * sizeof(float);
-  FSB_LAUNCH(bn_stats_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, pixels, C, static_cast<const __half*>(x), xcs, stats);
+  const int rows_per = threads / cvec;
+  const size_t smem = static_cast<size_t>(rows_per) * C * 2 * sizeof(float);
+  FSB_LAUNCH(bn_stats_kernel, dim3(static_cast<unsigned>(P)), dim3(threads), smem, stream, pixels, C, static_cast<const __half*>(x), xcs, rows, SC);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_stats launch");
   return FSB_OK;
 }
+// buf: (1 + stat_rows(pixels)) rows of 2*C floats; row 0 receives the totals
+int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* buf, cudaStream_t stream) {
+  int rc = bn_stats_rows_launch(pixels, C, x, xcs, x_is_f32, buf + 2 * C, C, stream);
+  if (rc) return rc;
+  return rowsum_launch(2 * C, buf + 2 * C, stat_rows(pixels), 2 * C, buf, stream);
+}
 
-__global__ void bn_finalize_kernel(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
-                                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                                   float* save_mean, float* save_invstd, long long* num_batches_tracked) {
+// One block = 32 channels x 16 row lanes: adds the partial rows in index order (double), then finalises.
+// sel != nullptr ("selected" mode, used by the captured training graphs): the BatchNorm parameter set of this launch is
+// chosen ON THE DEVICE -- sel[*width_idx] -- and channels >= its active width get scale = shift = 0, i.e. the unit runs at
+// its maximum width with the inactive tail forced to zero (USBatchNorm2d / USConv2d semantics, search/slimmable_ops.py:36-69).
+__global__ void __launch_bounds__(512)
+bn_finalize_kernel(int C, const float* __restrict__ stats, int P, int SC, double count, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                   float* save_mean, float* save_invstd, long long* num_batches_tracked, const fsb_bn_sel* sel, const int* width_idx) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double sh[16][32][2];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  int active = C;
+  if (sel) {
+    const fsb_bn_sel s = sel[*width_idx];
+    gamma = s.gamma;
+    beta = s.beta;
+    running_mean = s.running_mean;
+    running_var = s.running_var;
+    num_batches_tracked = s.num_batches_tracked;
+    active = s.C;
+  }
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const size_t stride = 2 * static_cast<size_t>(SC);
+    for (int r = ty; r < P; r += 16) {
+      s += static_cast<double>(stats[r * stride + c]);
+      q += static_cast<double>(stats[r * stride + SC + c]);
+    }
+  }
+  sh[ty][tx][0] = s;
+  sh[ty][tx][1] = q;
+  __syncthreads();
+  if (ty != 0) return;
   if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (c >= C) return;
-  const double mean = static_cast<double>(stats[c]) / count;
-  double var = static_cast<double>(stats[C + c]) / count - mean * mean;
+  s = 0.0;
+  q = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    s += sh[k][tx][0];
+    q += sh[k][tx][1];
+  }
+  if (c >= active) {  // inactive tail of a slimmable unit running at max width
+    if (scale) scale[c] = 0.f;
+    if (shift) shift[c] = 0.f;
+    if (save_mean) save_mean[c] = 0.f;
+    if (save_invstd) save_invstd[c] = 0.f;
+    return;
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
   if (var < 0) var = 0;
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float g = gamma ? gamma[c] : 1.f;
@@ -157,11 +243,12 @@ __global__ void bn_finalize_kernel(int C, const float* stats, double count, cons
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
-int bn_finalize_launch(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
+int bn_finalize_launch(int C, const float* stats, int P, int SC, double count, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
-                       float* save_invstd, cudaStream_t stream, long long* num_batches_tracked) {
-  FSB_LAUNCH(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, C, stats, count, gamma, beta, eps, momentum, running_mean,
-                                                         running_var, scale, shift, save_mean, save_invstd, num_batches_tracked);
+                       float* save_invstd, cudaStream_t stream, long long* num_batches_tracked, const fsb_bn_sel* sel,
+                       const int* width_idx) {
+  FSB_LAUNCH(bn_finalize_kernel, dim3((C + 31) / 32), dim3(512), 0, stream, C, stats, P, SC, count, gamma, beta, eps, momentum,
+             running_mean, running_var, scale, shift, save_mean, save_invstd, num_batches_tracked, sel, width_idx);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_finalize launch");
   return FSB_OK;

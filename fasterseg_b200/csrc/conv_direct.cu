@@ -10,7 +10,7 @@
 
 namespace fsb {
 
-int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* stats, cudaStream_t stream);
+int bn_stats_rows_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32, float* rows, int SC, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int64_t so, int64_t si, int taps, int Cout, int Cin,
@@ -93,10 +93,6 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
     const int ch = cg * 8 + j;
     if (ch >= d.Cout) break;
     float v = acc[j];
-    if ((d.flags & FSB_CONV_STATS) && p.stats) {
-      atomicAdd(&p.stats[ch], v);
-      atomicAdd(&p.stats[d.Cout + ch], v * v);
-    }
     if (d.flags & FSB_CONV_AFFINE) v = v * (p.scale ? p.scale[ch] : 1.f) + (p.shift ? p.shift[ch] : 0.f);
     if (d.flags & FSB_CONV_RELU) v = fmaxf(v, 0.f);
     if (d.flags & FSB_CONV_OUT_F32)
@@ -119,7 +115,7 @@ int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacke
   p.scale = scale;
   p.shift = shift;
   p.y = static_cast<__half*>(y);
-  // per-element atomics would serialise on Cout addresses: take the statistics in a second pass over the (fp16) output
+  // the statistics are taken in a second pass over the output (partial rows, no atomics: bn.cu)
   const bool want_stats = (d->flags & FSB_CONV_STATS) && stats;
   p.stats = nullptr;
   p.d.flags &= ~FSB_CONV_STATS;
@@ -130,8 +126,9 @@ int conv_direct_launch(const fsb_conv_desc* d, const void* x, const void* wpacke
   if (e != cudaSuccess) return set_cuda_error(e, "conv_direct launch");
   if (want_stats) {
     if (d->flags & (FSB_CONV_AFFINE | FSB_CONV_RELU)) return set_error(FSB_ERR_INVALID, "conv_direct: STATS needs a raw (no epilogue) output");
-    return bn_stats_launch(static_cast<int64_t>(d->N) * d->Ho * d->Wo, d->Cout, y, d->y_cstride,
-                           (d->flags & FSB_CONV_OUT_F32) ? 1 : 0, stats, stream);
+    const int SC = d->stats_C > 0 ? d->stats_C : d->Cout;
+    return bn_stats_rows_launch(static_cast<int64_t>(d->N) * d->Ho * d->Wo, d->Cout, y, d->y_cstride,
+                                (d->flags & FSB_CONV_OUT_F32) ? 1 : 0, stats + d->stats_off, SC, stream);
   }
   return FSB_OK;
 }

@@ -47,7 +47,9 @@ struct ConvTcParams {
   const float* scale;
   const float* shift;
   __half* y;
-  float* stats;
+  float* stats;   // partial rows (one per spatial tile = blockIdx.x), see bn.cu "Deterministic statistics"
+  int stats_C;    // row half-width (row stride = 2 * stats_C floats)
+  int stats_off;  // channel offset of this conv's output inside a row
   int m_tiles;  // persistent kernel only: spatial tiles (tiles_w * tiles_h * N) ...
   int n_tiles;  // ... x output-channel tiles; a CTA walks tile = blockIdx.x, += gridDim.x (n fastest)
 };
@@ -169,6 +171,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // per-warp channel statistics of this tile: [4 warps][sum | sumsq][n_tile] in the (now idle) pipeline buffers
+    float* s_stat = reinterpret_cast<float*>(smem);
     // TMEM loads are latency-bound (~250 ns per dependent tcgen05.ld + wait): issue up to four 16-column loads, wait once
     for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
       uint32_t vv[4][16];
@@ -195,9 +199,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
           }
-          if (lane == 0 && n0 + c + j < p.Cout) {
-            atomicAdd(&p.stats[n0 + c + j], a);
-            atomicAdd(&p.stats[p.Cout + n0 + c + j], b);
+          if (lane == 0) {
+            s_stat[(q * 2 + 0) * p.n_tile + c + j] = a;
+            s_stat[(q * 2 + 1) * p.n_tile + c + j] = b;
           }
         }
       }
@@ -274,6 +278,23 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       }
     }  // 64-column batch
     if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_read();  // smem must outlive the bulk reads
+    if (do_stats) {
+      // no atomics: the four warp partials are added in warp order and written as this tile's partial row; the consumer
+      // (bn_finalize / rowsum) adds the rows in index order, so the statistics are bit-reproducible run to run
+      named_bar_sync(2, 128);
+      float* row = p.stats + static_cast<size_t>(blockIdx.x) * 2 * p.stats_C + p.stats_off;
+      for (int ch = static_cast<int>(threadIdx.x) - 64; ch < p.n_tile; ch += 128) {
+        if (n0 + ch >= p.Cout) continue;
+        float a = s_stat[0 * p.n_tile + ch], b = s_stat[1 * p.n_tile + ch];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          a += s_stat[(w * 2 + 0) * p.n_tile + ch];
+          b += s_stat[(w * 2 + 1) * p.n_tile + ch];
+        }
+        row[n0 + ch] = a;
+        row[p.stats_C + n0 + ch] = b;
+      }
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -542,6 +563,12 @@ ConvGeom conv_geom(const fsb_conv_desc* d) {
   return g;
 }
 
+// spatial tiles (= CTAs along M = partial statistic rows) of the per-tap kernel
+int conv_tc_m_tiles(const fsb_conv_desc* d) {
+  const int tw = d->Wo >= 16 ? 16 : 8, th = kTileM / tw;
+  return ((d->Wo + tw - 1) / tw) * ((d->Ho + th - 1) / th) * d->N;
+}
+
 int conv_tc_supported(const fsb_conv_desc* d) {
   if (d->Cin < 16 || (d->x_cstride % 8) != 0) return 0;
   if (!(d->ksize == 1 || d->ksize == 3) || !(d->stride == 1 || d->stride == 2)) return 0;
@@ -585,6 +612,10 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   p.shift = shift;
   p.y = static_cast<__half*>(y);
   p.stats = stats;
+  p.stats_C = d->stats_C > 0 ? d->stats_C : d->Cout;
+  p.stats_off = d->stats_off;
+  if ((d->flags & FSB_CONV_STATS) && stats && (d->stats_off < 0 || d->stats_off + d->Cout > p.stats_C))
+    return set_error(FSB_ERR_INVALID, "conv_tc: stats_off + Cout exceeds stats_C");
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(n_tile)) cols <<= 1;
   p.tmem_cols = cols;
@@ -601,8 +632,8 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   size_t smem_bytes = stage_bytes * stages + 1024;
   // ---- TMA-store epilogue: fp16 output whose pixels start on 16 B and whose channel count is a multiple of 8 ----
   p.tma_store = 0;
-  if (!(d->flags & FSB_CONV_OUT_F32) && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      n_tile % 8 == 0 && (cu || !getenv("FSB_NO_TMA_STORE"))) {
+  if (!(d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS)) && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+      n_tile % 8 == 0 && (cu || opt(OPT_NO_TMA_STORE) <= 0)) {
     const uint64_t ycs = static_cast<uint64_t>(d->y_cstride) * 2;
     uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->Wo), static_cast<uint64_t>(d->Ho),
                         static_cast<uint64_t>(d->N)};
@@ -690,14 +721,14 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   }
   cudaError_t e;
   // ---- experimental persistent variant (see K1p above): inference epilogue, plain taps, several tiles per SM ----
-  static const bool persist_on = [] { const char* v = getenv("FSB_CONV_PERSIST"); return v && v[0] == '1'; }();
+  const bool persist_on = opt(OPT_CONV_PERSIST) == 1;
   if (persist_on && !cu && p.tma_store && d->Cout <= kPersistMaxCout && !(d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS)) &&
       m_tiles * n_tiles > sms && cols <= 256) {
     const size_t staging = static_cast<size_t>((n_tile + 63) / 64) * kTileM * 128;
     // tuning knobs for the first measurements: CTAs per SM (1 = whole shared memory for one pipeline, 2 = two issuers
     // sharing the tensor core, TMEM 2 x 2 x cols <= 512) and a cap on the pipeline depth
-    static const int occ_env = [] { const char* v = getenv("FSB_PERSIST_OCC"); return (v && v[0] == '2') ? 2 : 1; }();
-    static const int stages_env = [] { const char* v = getenv("FSB_PERSIST_STAGES"); return v ? atoi(v) : 0; }();
+    const int occ_env = opt(OPT_PERSIST_OCC) == 2 ? 2 : 1;
+    const int stages_env = opt(OPT_PERSIST_STAGES) > 0 ? opt(OPT_PERSIST_STAGES) : 0;
     const int occ = (occ_env == 2 && cols * 4 <= 512) ? 2 : 1;
     const size_t budget = (occ == 2 ? 100 : 200) * 1024;
     int pst = budget > staging ? static_cast<int>((budget - staging) / stage_bytes) : 0;
@@ -711,20 +742,10 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
       const size_t psmem = stage_bytes * pst + staging + 1024;
       const unsigned ctas = static_cast<unsigned>(m_tiles * n_tiles < sms * occ ? m_tiles * n_tiles : sms * occ);
       if (g.bk == 64) {
-        static bool pattr64 = false;
-        if (!pattr64) {
-          e = cudaFuncSetAttribute(conv_tc_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-          if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_persistent<64>)");
-          pattr64 = true;
-        }
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_persistent_kernel<64>), 216 * 1024, "cudaFuncSetAttribute(conv_tc_persistent<64>)")) return rc;
         e = launch_kernel(conv_tc_persistent_kernel<64>, dim3(ctas), dim3(kThreads), psmem, stream, p);
       } else {
-        static bool pattr32 = false;
-        if (!pattr32) {
-          e = cudaFuncSetAttribute(conv_tc_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-          if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_persistent<32>)");
-          pattr32 = true;
-        }
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_persistent_kernel<32>), 216 * 1024, "cudaFuncSetAttribute(conv_tc_persistent<32>)")) return rc;
         e = launch_kernel(conv_tc_persistent_kernel<32>, dim3(ctas), dim3(kThreads), psmem, stream, p);
       }
       if (e != cudaSuccess) return set_cuda_error(e, "conv_tc persistent launch");
@@ -733,20 +754,10 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   }
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
   if (g.bk == 64) {
-    static bool attr64 = false;
-    if (!attr64) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc<64>)");
-      attr64 = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel<64>), 220 * 1024, "cudaFuncSetAttribute(conv_tc<64>)")) return rc;
     e = launch_kernel(conv_tc_kernel<64>, grid, dim3(kThreads), smem_bytes, stream, p);
   } else {
-    static bool attr32 = false;
-    if (!attr32) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc<32>)");
-      attr32 = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel<32>), 220 * 1024, "cudaFuncSetAttribute(conv_tc<32>)")) return rc;
     e = launch_kernel(conv_tc_kernel<32>, grid, dim3(kThreads), smem_bytes, stream, p);
   }
   if (e != cudaSuccess) return set_cuda_error(e, "conv_tc launch");

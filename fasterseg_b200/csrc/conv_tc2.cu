@@ -40,7 +40,8 @@ struct ConvTc2Params {
   const float* scale;
   const float* shift;
   __half* y;
-  float* stats;
+  float* stats;   // partial rows, one per CTA (bn.cu "Deterministic statistics")
+  int stats_C, stats_off;
   unsigned long long* dbg;  // optional timeline buffer (fsb_debug_set_buffer): 64 stamps per traced CTA
 };
 
@@ -179,6 +180,12 @@ conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) T2_STAMP(41);
+    // per-warp channel statistics [4 warps][sum | sumsq][n_tile], accumulated over the R rows in row order (lane 0 only)
+    float* s_stat = reinterpret_cast<float*>(smem);
+    if (do_stats) {
+      for (int i = lane; i < 2 * p.n_tile; i += 32) s_stat[q * 2 * p.n_tile + i] = 0.f;
+      __syncwarp();
+    }
     for (int j = 0; j < p.R; ++j) {
       const int oh = h0 + j;
       const bool pix_ok = (oh < p.Ho) && (ow < p.Wo);
@@ -212,9 +219,9 @@ conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
               a += __shfl_xor_sync(0xffffffffu, a, o);
               b += __shfl_xor_sync(0xffffffffu, b, o);
             }
-            if (lane == 0 && c + i < p.Cout) {
-              atomicAdd(&p.stats[c + i], a);
-              atomicAdd(&p.stats[p.Cout + c + i], b);
+            if (lane == 0) {
+              s_stat[(q * 2 + 0) * p.n_tile + c + i] += a;
+              s_stat[(q * 2 + 1) * p.n_tile + c + i] += b;
             }
           }
         }
@@ -258,6 +265,21 @@ conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
         }
       }
     }
+    if (do_stats) {
+      named_bar_sync(2, 128);
+      float* row = p.stats + static_cast<size_t>(blockIdx.x) * 2 * p.stats_C + p.stats_off;
+      for (int ch = static_cast<int>(threadIdx.x) - 64; ch < p.n_tile; ch += 128) {
+        if (ch >= p.Cout) continue;
+        float a = s_stat[0 * p.n_tile + ch], b = s_stat[1 * p.n_tile + ch];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          a += s_stat[(w * 2 + 0) * p.n_tile + ch];
+          b += s_stat[(w * 2 + 1) * p.n_tile + ch];
+        }
+        row[ch] = a;
+        row[p.stats_C + ch] = b;
+      }
+    }
     tc_fence_before();
     if (threadIdx.x == 64) T2_STAMP(42);
   }
@@ -278,15 +300,44 @@ int conv_tc2_supported(const fsb_conv_desc* d) {
   if (d->ksize != 3 || d->stride != 1 || d->dil != 1 || d->pad != 1 || d->off_h || d->off_w) return 0;
   if (d->Cin < 32 || (d->x_cstride % 8) != 0 || d->Cout > 256) return 0;
   if (d->Wo < 96) return 0;  // strips are 128 output columns wide
-  const char* e = getenv("FSB_CONV_TC2");
-  if (e && e[0] == '0') return 0;
-  if (e && e[0] == '2') return 1;  // force (tests / tuning)
+  const int mode = opt(OPT_CONV_TC2);
+  if (mode == 0) return 0;
+  if (mode == 2) return 1;  // force (tests / tuning)
   // Measured on B200 (profiles/r1_conv_bench_v3.log): with 1-CTA SS-mode MMAs both kernels are bound by the tensor pipe's
   // operand fetch (~130 cycles per 128x128x16 MMA); the row-strip layout only wins where the per-tap kernel's L2->SM
   // traffic is the limiter: narrow N (<= 64 output channels) on maps large enough for >= 1 wave of 8-row strips.
   if (d->Cout > 64 || d->Cin % 64 != 0) return 0;
   if (static_cast<int64_t>(d->N) * d->Ho * d->Wo < 98304) return 0;
   return 1;
+}
+
+// rows per CTA: as many as TMEM (R * N <= 512) and shared memory allow while still producing >= ~0.8 waves of CTAs
+int conv_tc2_rows_per_cta(const fsb_conv_desc* d) {
+  const ConvGeom g = conv_geom(d);
+  const int n_tile = g.npad;
+  const int strips = (d->Wo + kT2Cols - 1) / kT2Cols;
+  const int pix_bytes = g.bk * 2;
+  const int rowb = (kT2Halo * pix_bytes + 1023) / 1024 * 1024;
+  const int b_bytes = n_tile * pix_bytes;
+  const int sms = sm_count();
+  const int smem_cap = 200 * 1024;
+  int bestR = 1;
+  for (int R = 8; R >= 1; R >>= 1) {
+    if (R * n_tile > 512) continue;
+    const int a_stage = (R + 2) * rowb;
+    if (a_stage + 2 * b_bytes > smem_cap) continue;
+    const int tiles = ((d->Ho + R - 1) / R) * strips * d->N;
+    bestR = R;
+    if (tiles * 10 >= sms * 8) break;  // enough CTAs: stop shrinking R
+  }
+  const int R = opt(OPT_TC2_R);  // tuning override
+  if (R >= 1 && R <= 8 && R * n_tile <= 512 && (R + 2) * rowb + 2 * b_bytes <= smem_cap) bestR = R;
+  return bestR;
+}
+// CTAs (= partial statistic rows) of the row-strip kernel
+int conv_tc2_ctas(const fsb_conv_desc* d) {
+  const int R = conv_tc2_rows_per_cta(d);
+  return ((d->Wo + kT2Cols - 1) / kT2Cols) * ((d->Ho + R - 1) / R) * d->N;
 }
 
 int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift, void* y,
@@ -308,30 +359,17 @@ int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
   p.shift = shift;
   p.y = static_cast<__half*>(y);
   p.stats = stats;
+  p.stats_C = d->stats_C > 0 ? d->stats_C : d->Cout;
+  p.stats_off = d->stats_off;
   p.dbg = g_dbg_buffer;
   const int b_bytes = p.n_tile * pix_bytes;
-  const int sms = sm_count();
   const int smem_cap = 200 * 1024;
-  // rows per CTA: as many as TMEM (R * N <= 512) and shared memory allow while still producing >= ~0.8 waves of CTAs
-  int bestR = 1;
-  for (int R = 8; R >= 1; R >>= 1) {
-    if (R * p.n_tile > 512) continue;
-    const int a_stage = (R + 2) * p.rowb;
-    if (a_stage + 2 * b_bytes > smem_cap) continue;
-    const int tiles = ((d->Ho + R - 1) / R) * p.strips * d->N;
-    bestR = R;
-    if (tiles * 10 >= sms * 8) break;  // enough CTAs: stop shrinking R
-  }
-  if (const char* e = getenv("FSB_TC2_R")) {  // tuning override
-    const int R = atoi(e);
-    if (R >= 1 && R <= 8 && R * p.n_tile <= 512 && (R + 2) * p.rowb + 2 * b_bytes <= smem_cap) bestR = R;
-  }
+  const int bestR = conv_tc2_rows_per_cta(d);
   p.R = bestR;
   p.row_groups = (d->Ho + p.R - 1) / p.R;
   const int a_stage = (p.R + 2) * p.rowb;
   // one A stage + a deep weight ring beats two A stages + a shallow ring: the weight tiles are the latency-critical stream
-  int want_a = 1;
-  if (const char* e = getenv("FSB_TC2_ASTAGES")) want_a = atoi(e) == 2 ? 2 : 1;
+  const int want_a = opt(OPT_TC2_ASTAGES) == 2 ? 2 : 1;
   p.a_stages = (want_a == 2 && p.k_chunks > 1 && 2 * a_stage + 2 * b_bytes <= smem_cap) ? 2 : 1;
   int bst = (smem_cap - p.a_stages * a_stage) / b_bytes;
   if (bst > kT2MaxB) bst = kT2MaxB;
@@ -360,20 +398,11 @@ int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
   }
   dim3 grid(static_cast<unsigned>(p.strips * p.row_groups * d->N));
   cudaError_t e;
-  static bool attr_done[2] = {false, false};
   if (g.bk == 64) {
-    if (!attr_done[0]) {
-      e = cudaFuncSetAttribute(conv_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc2<64>)");
-      attr_done[0] = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc2_kernel<64>), 220 * 1024, "cudaFuncSetAttribute(conv_tc2<64>)")) return rc;
     e = launch_kernel(conv_tc2_kernel<64>, grid, dim3(kT2Threads), smem_bytes, stream, p);
   } else {
-    if (!attr_done[1]) {
-      e = cudaFuncSetAttribute(conv_tc2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc2<32>)");
-      attr_done[1] = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc2_kernel<32>), 220 * 1024, "cudaFuncSetAttribute(conv_tc2<32>)")) return rc;
     e = launch_kernel(conv_tc2_kernel<32>, grid, dim3(kT2Threads), smem_bytes, stream, p);
   }
   if (e != cudaSuccess) return set_cuda_error(e, "conv_tc2 launch");

@@ -31,6 +31,28 @@ ConvGeom conv_geom(const fsb_conv_desc* d);
 bool pdl_enabled();
 int sm_count();
 
+// Tuning / validation switches.  Read from the environment ONCE (first use) and settable through fsb_set_option(); never a
+// getenv() on the launch path.  -1 = unset.
+enum Opt {
+  OPT_CONV_TC2 = 0,      // FSB_CONV_TC2: 0 = never use the row-strip kernel, 2 = force it wherever it is supported
+  OPT_TC2_R,             // FSB_TC2_R: rows per CTA override
+  OPT_TC2_ASTAGES,       // FSB_TC2_ASTAGES
+  OPT_NO_TMA_STORE,      // FSB_NO_TMA_STORE
+  OPT_DGRAD_S2_DIRECT,   // FSB_DGRAD_S2_DIRECT
+  OPT_WGRAD_TC,          // FSB_WGRAD_TC: 0 = CUDA-core weight gradient
+  OPT_CONV_PERSIST,      // FSB_CONV_PERSIST
+  OPT_PERSIST_OCC,       // FSB_PERSIST_OCC
+  OPT_PERSIST_STAGES,    // FSB_PERSIST_STAGES
+  OPT_UPSAMPLE_V2,       // FSB_UPSAMPLE_V2
+  OPT_DETERMINISTIC,     // FSB_DETERMINISTIC: 1 = weight gradients without split-K atomics (bit-reproducible steps)
+  OPT_CONV_TC3,          // FSB_CONV_TC3: 0 = never use the channel-major 128x256 kernel, 2 = force it wherever it is supported
+  OPT_COUNT
+};
+int opt(Opt o);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember it per (kernel, device), not per process
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what);
+
 // Launch with (optionally) the programmatic-dependent-launch attribute; every kernel of this library calls
 // pdl_launch_dependents() at entry and pdl_wait() before its first dependent global access.
 template <typename... KArgs, typename... Args>
@@ -77,9 +99,14 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
 int conv_tc2_supported(const fsb_conv_desc* d);
 int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                     void* y, float* stats, cudaStream_t stream);
-// picks the row-strip kernel for wide 3x3 stride-1 convs, the per-tap kernel otherwise
+int conv_tc3_supported(const fsb_conv_desc* d, const void* y);
+int conv_tc3_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift, void* y,
+                    cudaStream_t stream);
+// picks the channel-major 128x256 kernel for wide-Cout inference / dgrad convs, the row-strip kernel for wide 3x3 stride-1
+// convs with few output channels, the per-tap kernel otherwise
 inline int conv_tc_dispatch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                             void* y, float* stats, cudaStream_t stream) {
+  if (!stats && conv_tc3_supported(d, y)) return conv_tc3_launch(d, x, wpacked, scale, shift, y, stream);
   if (conv_tc2_supported(d)) return conv_tc2_launch(d, x, wpacked, scale, shift, y, stats, stream);
   return conv_tc_launch(d, x, wpacked, scale, shift, y, stats, stream);
 }

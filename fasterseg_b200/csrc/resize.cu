@@ -374,7 +374,7 @@ int upsample_logits_launch(int N, int C, int Hi, int Wi, int Ho, int Wo, const v
                            cudaStream_t stream) {
   // tiled path: upsampling only, source window must fit in shared memory, 16-byte addressable source pixels
   const float sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
-  static const bool v2_on = [] { const char* e = getenv("FSB_UPSAMPLE_V2"); return e && e[0] == '1'; }();
+  const bool v2_on = opt(OPT_UPSAMPLE_V2) == 1;
   // v2 needs the 8 columns of a thread to span <= 3 source columns: 7 * sw + 1 < 2  <=>  upsampling factor > 7
   if (v2_on && sh <= 1.f && sw * 7.f < 0.999f && xcs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && xcs >= (C + 7) / 8 * 8) {
     const int max_rows = static_cast<int>(sh * (kUp2Rows - 1)) + 3;

@@ -74,7 +74,7 @@ template <typename TR>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dcs, const __half* __restrict__ y, int ycs,
                      const TR* __restrict__ raw, int rcs, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     int relu, float* __restrict__ sums) {
+                     int relu, float* __restrict__ rows_out) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];
@@ -109,14 +109,16 @@ bn_bwd_reduce_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int d
     }
   }
   __syncthreads();
+  // this block's partial row (fixed intra-block order; the rows are added in index order by rowsum_kernel)
+  float* out = rows_out + static_cast<size_t>(blockIdx.x) * 2 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int r = 0; r < rows; ++r) {
       a += red[(r * C + c) * 2 + 0];
       b += red[(r * C + c) * 2 + 1];
     }
-    atomicAdd(&sums[c], a);
-    atomicAdd(&sums[C + c], b);
+    out[c] = a;
+    out[C + c] = b;
   }
 }
 
@@ -125,14 +127,23 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dcs, const __half* __restrict__ y, int ycs,
                     const TR* __restrict__ raw, int rcs, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int relu,
-                    __half* __restrict__ draw, int ocs, float* __restrict__ dgamma, float* __restrict__ dbeta, float inv_gscale) {
+                    __half* __restrict__ draw, int ocs, float* __restrict__ dgamma, float* __restrict__ dbeta, float inv_gscale,
+                    int accumulate, const fsb_bn_sel* sel, const int* width_idx) {
   pdl_launch_dependents();
   pdl_wait();
   const int cvec = C >> 3;
+  int active = C;
+  if (sel) {  // parameter set chosen on the device (see bn_finalize_kernel); channels >= its width have invstd = 0 -> draw = 0
+    const fsb_bn_sel sl = sel[*width_idx];
+    gamma = sl.gamma;
+    dgamma = sl.dgamma;
+    dbeta = sl.dbeta;
+    active = sl.C;
+  }
   if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] += sums[c] * inv_gscale;
-      if (dgamma) dgamma[c] += sums[C + c] * inv_gscale;
+    for (int c = threadIdx.x; c < active; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sums[c] * inv_gscale;
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sums[C + c] * inv_gscale;
     }
   }
   const int64_t total = pixels * cvec;
@@ -149,7 +160,7 @@ bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dc
       const int c = cv * 8 + j;
       const float dz = (relu && !(yy[j] > 0.f)) ? 0.f : d[j];
       const float xh = (r[j] - mean[c]) * invstd[c];
-      const float g = gamma ? gamma[c] : 1.f;
+      const float g = (gamma && c < active) ? gamma[c] : (c < active ? 1.f : 0.f);
       o[j] = g * invstd[c] * (dz - sums[c] * inv_count - xh * sums[C + c] * inv_count);
     }
     *reinterpret_cast<uint4*>(draw + p * ocs + cv * 8) = pack8(o);
@@ -183,6 +194,10 @@ static inline unsigned grid_for(int64_t total, int threads) {
   return static_cast<unsigned>(b);
 }
 
+int stat_rows(int64_t pixels);
+int rowsum_launch(int L, const float* rows, int P, int stride, float* out, cudaStream_t stream);
+
+// sums: (1 + stat_rows(pixels)) rows of 2*C floats; the partial rows land in rows 1.., their fixed-order total in row 0
 int bn_bwd_reduce_launch(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
                          int raw_f32, const float* mean, const float* invstd, int relu, float* sums, cudaStream_t stream) {
   if (!vec_ok(C, dcs, dy) || !vec_ok(C, rcs, raw) || (relu && !vec_ok(C, ycs, y)) || C > 2048)
@@ -190,37 +205,37 @@ int bn_bwd_reduce_launch(int64_t pixels, int C, const void* dy, int dcs, const v
   const int cvec = C / 8, threads = 256;
   const int rows = threads / cvec;
   if (rows < 1) return set_error(FSB_ERR_INVALID, "bn_bwd_reduce: C too large");
-  int64_t blocks = (pixels + rows * 8 - 1) / (rows * 8);
-  if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  const int blocks = stat_rows(pixels);
+  float* part = sums + 2 * C;
   const size_t smem = static_cast<size_t>(rows) * C * 2 * sizeof(float);
   if (raw_f32)
     FSB_LAUNCH(bn_bwd_reduce_kernel<float>, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const float*>(raw), rcs, mean,
-               invstd, relu, sums);
+               invstd, relu, part);
   else
     FSB_LAUNCH(bn_bwd_reduce_kernel<__half>, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const __half*>(raw), rcs, mean,
-               invstd, relu, sums);
+               invstd, relu, part);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd_reduce launch");
-  return FSB_OK;
+  return rowsum_launch(2 * C, part, blocks, 2 * C, sums, stream);
 }
 int bn_bwd_apply_launch(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
                         int raw_f32, const float* mean, const float* invstd, const float* gamma, const float* sums, double count, int relu,
-                        void* draw, int ocs, float* dgamma, float* dbeta, float gscale, cudaStream_t stream) {
+                        void* draw, int ocs, float* dgamma, float* dbeta, float gscale, cudaStream_t stream, int accumulate,
+                        const fsb_bn_sel* sel, const int* width_idx) {
   if (!vec_ok(C, dcs, dy) || !vec_ok(C, rcs, raw) || !vec_ok(C, ocs, draw) || (relu && !vec_ok(C, ycs, y)))
     return set_error(FSB_ERR_INVALID, "bn_bwd_apply: C/strides multiples of 8, pointers 16B aligned");
   if (raw_f32)
     FSB_LAUNCH(bn_bwd_apply_kernel<float>, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const float*>(raw), rcs, mean,
                invstd, gamma, sums, static_cast<float>(1.0 / count), relu, static_cast<__half*>(draw), ocs, dgamma, dbeta,
-               1.0f / gscale);
+               1.0f / gscale, accumulate, sel, width_idx);
   else
     FSB_LAUNCH(bn_bwd_apply_kernel<__half>, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const __half*>(raw), rcs, mean,
                invstd, gamma, sums, static_cast<float>(1.0 / count), relu, static_cast<__half*>(draw), ocs, dgamma, dbeta,
-               1.0f / gscale);
+               1.0f / gscale, accumulate, sel, width_idx);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd_apply launch");
   return FSB_OK;
@@ -352,7 +367,7 @@ int conv_dgrad_launch(const fsb_conv_desc* d, const void* dy, int dcs, const voi
   // stride 2: the input pixels of each (row, column) parity receive contributions from a fixed subset of filter taps; each
   // parity plane is a stride-1 implicit GEMM over dy with that tap subset, written to the plane through a strided tensor map
   if (d->stride == 2 && wpacked_t && !(d->flags & FSB_CONV_FORCE_DIRECT) && d->Cin % 8 == 0 && xcs % 8 == 0 && dcs % 8 == 0 &&
-      d->Cout >= 16 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && !getenv("FSB_DGRAD_S2_DIRECT")) {
+      d->Cout >= 16 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && opt(OPT_DGRAD_S2_DIRECT) <= 0) {
     fsb_conv_desc t = dgrad_as_fwd_desc(d, dcs, xcs);  // stride-1 problem over dy; geometry fields only feed the packer
     t.pad = 0;
     t.Ho = d->Ho;
@@ -545,7 +560,7 @@ int conv_wgrad_launch(const fsb_conv_desc* d, const void* x, const void* dy, int
   int64_t chunks = (148 * 4 + tiles - 1) / tiles;
   const int64_t max_chunks = (npix + 255) / 256;
   if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
+  if (chunks < 1 || opt(OPT_DETERMINISTIC) == 1) chunks = 1;  // deterministic mode: one owner per output element, no split-K atomics
   p.chunk = ((npix + chunks - 1) / chunks + kWgK - 1) / kWgK * kWgK;
   chunks = (npix + p.chunk - 1) / p.chunk;
   FSB_LAUNCH(conv_wgrad_kernel, dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks)), dim3(256), 0, stream, p);
@@ -780,11 +795,18 @@ wsum_bwd_kernel(const WsumArgs a, int64_t pixels, int cvec, const __half* __rest
     if (lane == 0) red[k][warp] = v;
   }
   __syncthreads();
-  if (threadIdx.x < a.K) {
+  if (threadIdx.x < kMaxWsum) {  // partial row of this block (rows 1..; row 0 = fixed-order total, written by rowsum_kernel)
     float v = 0.f;
-    for (int wv = 0; wv < (blockDim.x >> 5); ++wv) v += red[threadIdx.x][wv];
-    atomicAdd(&dwts[threadIdx.x], v * inv_gscale);
+    if (threadIdx.x < a.K)
+      for (int wv = 0; wv < (blockDim.x >> 5); ++wv) v += red[threadIdx.x][wv];
+    dwts[(static_cast<size_t>(blockIdx.x) + 1) * kMaxWsum + threadIdx.x] = v * inv_gscale;
   }
+}
+int wsum_rows(int64_t pixels, int C) {
+  int64_t b = (pixels * (C / 8) + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 2) b = 148 * 2;
+  return static_cast<int>(b);
 }
 int wsum_fwd_launch(int K, int64_t pixels, int C, const void* const* xs, const int* xcs, const float* wts, void* out, int ocs,
                     cudaStream_t stream) {
@@ -825,10 +847,13 @@ int wsum_bwd_launch(int K, int64_t pixels, int C, const void* dout, int docs, co
     }
   }
   if (!vec_ok(C, docs, dout)) return set_error(FSB_ERR_INVALID, "wsum_bwd: bad dout view");
-  FSB_LAUNCH(wsum_bwd_kernel, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, a, pixels, C / 8,
+  // with scalar gradients the grid is capped so that the (1 + rows) x 8 partial buffer stays small; dwts[0..8) = totals
+  const unsigned grid = dwts ? static_cast<unsigned>(wsum_rows(pixels, C)) : grid_for(pixels * (C / 8), 256);
+  FSB_LAUNCH(wsum_bwd_kernel, dim3(grid), dim3(256), 0, stream, a, pixels, C / 8,
              static_cast<const __half*>(dout), docs, wts, dwts, 1.0f / gscale);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "wsum_bwd launch");
+  if (dwts) return rowsum_launch(kMaxWsum, dwts + kMaxWsum, static_cast<int>(grid), kMaxWsum, dwts, stream);
   return FSB_OK;
 }
 

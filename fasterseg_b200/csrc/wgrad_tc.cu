@@ -181,8 +181,7 @@ static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); 
 int conv_wgrad_tc_supported(const fsb_conv_desc* d, int dy_cstride) {
   if (!(d->ksize == 1 || d->ksize == 3) || !(d->stride == 1 || d->stride == 2) || d->dil != 1) return 0;
   if (d->Cin < 16 || d->Cout < 16 || (d->x_cstride % 8) != 0 || (dy_cstride % 8) != 0) return 0;
-  const char* e = getenv("FSB_WGRAD_TC");
-  if (e && e[0] == '0') return 0;
+  if (opt(OPT_WGRAD_TC) == 0) return 0;
   return 1;
 }
 
@@ -216,7 +215,9 @@ int conv_wgrad_tc_launch(const fsb_conv_desc* d, const void* x, const void* dy, 
   const int fixed = p.co_tiles * p.ci_tiles * p.taps;
   int chunks = (sm_count() * 2 + fixed - 1) / fixed;
   if (chunks > total_tiles) chunks = total_tiles;
-  if (chunks < 1) chunks = 1;
+  // deterministic mode (FSB_DETERMINISTIC=1 / fsb_set_option): no split over pixels, so every gradient element has exactly one
+  // writer and the fp32 accumulation order is fixed (slower: co_tiles * ci_tiles * taps CTAs only)
+  if (chunks < 1 || opt(OPT_DETERMINISTIC) == 1) chunks = 1;
   p.chunks = chunks;
   const size_t stage_bytes = static_cast<size_t>(2 + p.ci_tile / 64) * kWgSub;
   int stages = static_cast<int>((192 * 1024) / stage_bytes);
@@ -276,13 +277,8 @@ int conv_wgrad_tc_launch(const fsb_conv_desc* d, const void* x, const void* dy, 
         if (rc) return rc;
       }
   }
-  static bool attr_done = false;
   cudaError_t e;
-  if (!attr_done) {
-    e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_tc)");
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_tc_kernel), 220 * 1024, "cudaFuncSetAttribute(conv_wgrad_tc)")) return rc;
   dim3 grid(static_cast<unsigned>(fixed), static_cast<unsigned>(chunks));
   e = launch_kernel(conv_wgrad_tc_kernel, grid, dim3(kWgThreads), smem_bytes, stream, p);
   if (e != cudaSuccess) return set_cuda_error(e, "conv_wgrad_tc launch");

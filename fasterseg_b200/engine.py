@@ -104,7 +104,7 @@ def conv_bn_act_train_nograd(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
     assert conv.bias is None, "conv bias followed by train-mode BN is not on the hot path"
     k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
     wp = packed_weight(conv, ci, co)
-    stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
+    stats = F_.conv_stats_buffer(x, co, k, s, p, off=off)
     raw = F_.conv_fwd(x, wp, co, k, s, p, relu=False, off=off, stats=stats, out_f32=True)
     N, _, Ho, Wo = raw.shape
     stats = dp_allreduce_stats(stats)
@@ -145,6 +145,10 @@ def dp_native():
 
 
 def dp_allreduce_stats(stats):
+    """SyncBN exchange.  `stats` = partial rows [R, L] (or totals [L]); with more than one rank the rows are first added in
+    index order (deterministic), then summed over the ranks; single process: returned untouched (bn_finalize adds the rows)."""
     if dp_world_size() > 1:
+        if stats.dim() == 2 and stats.shape[0] > 1:
+            stats = F_.rowsum(stats)
         torch.distributed.all_reduce(stats, group=_SYNC_BN["group"])
     return stats

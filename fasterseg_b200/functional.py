@@ -131,10 +131,33 @@ def bn_fold(gamma, beta, mean, var, eps, conv_bias=None):
     return out[0], out[1]
 
 
+def conv_stats_buffer(x, Cout, ksize, stride, pad, off=(0, 0), total_C=None, force_direct=False):
+    """fp32 [rows, 2 * SC] buffer of partial statistic rows for `conv_fwd(..., stats=buf)` on this geometry (SC = total_C or
+    Cout; include/fsb200.h "Deterministic statistics").  Needs no zeroing: the conv writes every row."""
+    N, Cin, H, W, xcs = nhwc_info(x)
+    Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    SC = Cout if total_C is None else int(total_C)
+    flags = FSB_CONV_STATS | FSB_CONV_OUT_F32 | (FSB_CONV_FORCE_DIRECT if force_direct else 0)
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, (Cout + 7) // 8 * 8, flags)
+    rows = _lib.lib().fsb_conv_stats_rows(C.byref(d))
+    if rows <= 0:
+        raise _lib.FsbError("fsb_conv_stats_rows: invalid geometry")
+    return torch.empty((rows, 2 * SC), device=x.device, dtype=torch.float32)
+
+
+def rowsum(rows):
+    """[R, L] fp32 -> [1, L]: rows added in index order in double precision (the deterministic reduction)"""
+    assert rows.dim() == 2 and rows.dtype == torch.float32 and rows.is_contiguous()
+    out = torch.empty((1, rows.shape[1]), device=rows.device, dtype=torch.float32)
+    check(_lib.lib().fsb_rowsum(rows.shape[1], _ptr(rows), rows.shape[0], rows.shape[1], _ptr(out), _stream()), "fsb_rowsum")
+    return out
+
+
 def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=False, out=None, off=(0, 0),
-             stats=None, force_direct=False, out_f32=False):
+             stats=None, force_direct=False, out_f32=False, stats_off=0):
     """y = act(conv(x) * scale + shift); x/out NHWC fp16 views (see module docstring).  out_f32: fp32 NHWC output (the
-    training path's raw conv result, normalised by BatchNorm from un-rounded values)."""
+    training path's raw conv result, normalised by BatchNorm from un-rounded values).  stats: a `conv_stats_buffer`; this
+    conv's per-channel sums land at column stats_off + c, its sums of squares at SC + stats_off + c of every row."""
     N, Cin, H, W, xcs = nhwc_info(x)
     Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
     odt = torch.float32 if out_f32 else torch.float16
@@ -150,6 +173,11 @@ def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=
     if out_f32:
         flags |= FSB_CONV_OUT_F32
     d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, ycs, flags)
+    if stats is not None:
+        assert stats.dim() == 2 and stats.dtype == torch.float32 and stats.is_contiguous()
+        d.stats_C, d.stats_off = stats.shape[1] // 2, int(stats_off)
+        rows = _lib.lib().fsb_conv_stats_rows(C.byref(d))
+        assert rows == stats.shape[0], "statistics buffer has %d rows, this launch writes %d" % (stats.shape[0], rows)
     check(_lib.lib().fsb_conv_fwd(C.byref(d), _ptr(x), _ptr(wpacked), _ptr(scale), _ptr(shift), _ptr(out), _ptr(stats),
                                   _stream()), "fsb_conv_fwd")
     return out
@@ -212,18 +240,22 @@ def copy_channels(x, out):
     return out
 
 
-def bn_stats(x, stats=None):
+def bn_stats(x):
+    """-> fp32 [2C] = per-channel (sum | sum of squares); deterministic (partial rows + ordered row sum)"""
     N, Cc, H, W, xcs = nhwc_info(x)
-    if stats is None:
-        stats = torch.zeros(2 * Cc, device=x.device, dtype=torch.float32)
-    check(_lib.lib().fsb_bn_stats(N * H * W, Cc, _ptr(x), xcs, _ptr(stats), _stream()), "fsb_bn_stats")
-    return stats
+    rows = _lib.lib().fsb_stat_rows(N * H * W)
+    buf = torch.empty((1 + rows, 2 * Cc), device=x.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_stats(N * H * W, Cc, _ptr(x), xcs, _ptr(buf), _stream()), "fsb_bn_stats")
+    return buf[0]
 
 
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, want_save=False):
-    Cc = stats.numel() // 2
+    """stats: [rows, 2C] partial rows (conv_stats_buffer / rowsum output) or [2C] totals"""
+    if stats.dim() == 1:
+        stats = stats.view(1, -1)
+    Cc = stats.shape[1] // 2
     buf = torch.empty((4, Cc), device=stats.device, dtype=torch.float32)
-    check(_lib.lib().fsb_bn_finalize(Cc, _ptr(stats), float(count), _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+    check(_lib.lib().fsb_bn_finalize(Cc, _ptr(stats), stats.shape[0], Cc, float(count), _ptr(gamma), _ptr(beta), float(eps), float(momentum),
                                      _ptr(running_mean), _ptr(running_var), _ptr(buf[0]), _ptr(buf[1]),
                                      _ptr(buf[2]) if want_save else None, _ptr(buf[3]) if want_save else None, _stream()),
           "fsb_bn_finalize")
@@ -250,10 +282,11 @@ def bn_bwd_sums(dy, y, raw, mean, invstd, relu):
     _, _, _, _, rcs = nhwc_info(raw, raw.dtype)
     rf32 = int(raw.dtype == torch.float32)
     ycs = nhwc_info(y)[4] if relu else 0
-    sums = torch.zeros(2 * Cc, device=dy.device, dtype=torch.float32)
+    rows = _lib.lib().fsb_stat_rows(N * H * W)
+    sums = torch.empty((1 + rows, 2 * Cc), device=dy.device, dtype=torch.float32)   # row 0 = totals, rows 1.. = per-CTA partials
     check(_lib.lib().fsb_bn_bwd_reduce(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                        _ptr(invstd), int(relu), _ptr(sums), _stream()), "fsb_bn_bwd_reduce")
-    return sums
+    return sums[0]
 
 
 def bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads=True):
@@ -264,11 +297,11 @@ def bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, wan
     rf32 = int(raw.dtype == torch.float32)
     ycs = nhwc_info(y)[4] if relu else 0
     draw = empty_nhwc(N, Cc, H, W, dy.device)
-    dg = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
-    db = torch.zeros(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    dg = torch.empty(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
+    db = torch.empty(Cc, device=dy.device, dtype=torch.float32) if want_param_grads else None
     check(_lib.lib().fsb_bn_bwd_apply(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                       _ptr(invstd), _ptr(gamma), _ptr(sums), float(count), int(relu), _ptr(draw),
-                                      nhwc_info(draw)[4], _ptr(dg), _ptr(db), float(gscale), _stream()), "fsb_bn_bwd_apply")
+                                      nhwc_info(draw)[4], _ptr(dg), _ptr(db), float(gscale), 0, _stream()), "fsb_bn_bwd_apply")
     return draw, dg, db
 
 
@@ -391,12 +424,14 @@ def wsum_bwd(dout, xs, wts, need_dx, need_dw, gscale):
     N, Cc, H, W, docs = nhwc_info(dout)
     K = len(xs)
     dxs = [empty_nhwc(N, Cc, H, W, dout.device) if need_dx[k] else None for k in range(K)]
-    dw = torch.zeros(K, device=dout.device, dtype=torch.float32) if need_dw else None
+    dw = None
+    if need_dw:   # (1 + rows) x 8: row 0 = totals (ordered row sum of the per-CTA partials below it); needs no zeroing
+        dw = torch.empty((1 + _lib.lib().fsb_wsum_rows(N * H * W, Cc), 8), device=dout.device, dtype=torch.float32)
     xstr = (C.c_int * K)(*[nhwc_info(t)[4] for t in xs])
     dxstr = (C.c_int * K)(*[0 if t is None else nhwc_info(t)[4] for t in dxs])
     check(_lib.lib().fsb_wsum_bwd(K, N * H * W, Cc, _ptr(dout), docs, _ptr_array(xs), xstr, _ptr(wts), _ptr_array(dxs), dxstr,
                                   _ptr(dw), float(gscale), _stream()), "fsb_wsum_bwd")
-    return dxs, dw
+    return dxs, (dw[0, :K] if need_dw else None)
 
 
 def add_inplace(x, y):
@@ -409,44 +444,55 @@ def add_inplace(x, y):
 # fused training unit (one C-ABI call per direction; see csrc/train_fused.cu)
 # ----------------------------------------------------------------------------------------------
 def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta, eps, momentum, running_mean, running_var,
-                          num_batches_tracked, relu):
-    """-> (y fp16 NHWC, raw fp32 NHWC, vec fp32[6*Cout] = [sum|sumsq|scale|shift|mean|invstd], desc)"""
+                          num_batches_tracked, relu, sel=None, width_idx=None):
+    """-> (y fp16 NHWC, raw fp32 NHWC, vec fp32[(6 + 2R)*Cout] = [sum|sumsq|scale|shift|mean|invstd|R partial rows], desc).
+    sel / width_idx: device pointers (ints) of an fsb_bn_sel table and an int32 width index -- the BatchNorm parameter set is
+    then chosen on the device (captured training graphs) and gamma / beta / running stats arguments are ignored."""
     N, Cin, H, W, xcs = nhwc_info(x)
     Ho, Wo = conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
     cpad = (Cout + 7) // 8 * 8
     dev = x.device
     raw = empty_nhwc(N, Cout, Ho, Wo, dev, torch.float32)    # views at offset 0 of their buffers, pixel stride cpad
     y = empty_nhwc(N, Cout, Ho, Wo, dev)
-    vec = torch.empty(6 * Cout, device=dev, dtype=torch.float32)
-    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, cpad, 0)
-    check(_lib.lib().fsb_conv_bn_act_train_fwd(C.byref(d), x.data_ptr(), wpacked.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, cpad, FSB_CONV_OUT_F32 | FSB_CONV_STATS)
+    rows = _lib.lib().fsb_conv_stats_rows(C.byref(d))
+    d.flags = 0
+    vec = torch.empty((6 + 2 * rows) * Cout, device=dev, dtype=torch.float32)
+    check(_lib.lib().fsb_conv_bn_act_train_fwd(C.byref(d), x.data_ptr(), wpacked.data_ptr(),
+                                               None if gamma is None else gamma.data_ptr(), None if beta is None else beta.data_ptr(),
                                                float(eps), float(momentum),
                                                None if running_mean is None else running_mean.data_ptr(),
                                                None if running_var is None else running_var.data_ptr(),
                                                None if num_batches_tracked is None else num_batches_tracked.data_ptr(),
-                                               raw.data_ptr(), cpad, y.data_ptr(), cpad, vec.data_ptr(), int(relu), _stream()),
+                                               raw.data_ptr(), cpad, y.data_ptr(), cpad, vec.data_ptr(), int(relu), sel, width_idx,
+                                               _stream()),
           "fsb_conv_bn_act_train_fwd")
     return y, raw, vec, d
 
 
-def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale):
-    """-> (dx or None, dgamma, dbeta); the weight gradient is accumulated into `dw_accum` (fp32, master layout) when given."""
+def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale, sel=None, width_idx=None):
+    """-> (dx or None, dgamma, dbeta); the weight gradient is accumulated into `dw_accum` (fp32, master layout) when given.
+    With sel / width_idx (see conv_bn_act_train_fwd) dgamma / dbeta are accumulated into the selected parameter set's gradient
+    slots by the kernel and the returned tensors are meaningless."""
     N, Cout, Ho, Wo, dcs = nhwc_info(dy)
     dev = dy.device
     cpad = d.y_cstride
     draw = empty_nhwc(N, Cout, Ho, Wo, dev)
     assert draw.stride(3) == cpad
-    vb = torch.empty(4 * Cout, device=dev, dtype=torch.float32)
+    rows = _lib.lib().fsb_stat_rows(N * Ho * Wo)
+    vb = torch.empty((4 + 2 * rows) * Cout, device=dev, dtype=torch.float32)   # [totals 2C | partial rows | dgamma | dbeta]
     dx = None
     xcs = 0
     if need_dx:
         dx = empty_nhwc(N, d.Cin, d.H, d.W, dev)
         xcs = dx.stride(3)
     check(_lib.lib().fsb_conv_bn_act_train_bwd(C.byref(d), x.data_ptr(), dy.data_ptr(), dcs, y.data_ptr(), y.stride(3), raw.data_ptr(),
-                                               raw.stride(3), vec.data_ptr(), gamma.data_ptr(), int(relu),
+                                               raw.stride(3), vec.data_ptr(), None if gamma is None else gamma.data_ptr(), int(relu),
                                                None if wpacked_t is None else wpacked_t.data_ptr(), w.data_ptr(), w.stride(0),
                                                w.stride(1), draw.data_ptr(), cpad, vb.data_ptr(),
                                                None if dx is None else dx.data_ptr(), xcs,
-                                               None if dw_accum is None else dw_accum.data_ptr(), float(gscale), _stream()),
+                                               None if dw_accum is None else dw_accum.data_ptr(), float(gscale), sel, width_idx,
+                                               _stream()),
           "fsb_conv_bn_act_train_bwd")
-    return dx, vb[2 * Cout:3 * Cout], vb[3 * Cout:]
+    at = (2 + 2 * rows) * Cout
+    return dx, vb[at:at + Cout], vb[at + Cout:at + 2 * Cout]

@@ -357,15 +357,11 @@ def _factorized_reduce_s2(op, x, out):
         F_.conv_fwd(x, w1, co_half, 1, 2, 0, scale[:co_half], shift[:co_half], relu=True, out=out[:, :co_half])
         F_.conv_fwd(x, w2, co_half, 1, 2, 0, scale[co_half:], shift[co_half:], relu=True, out=out[:, co_half:], off=(1, 1))
         return out
-    stats = torch.zeros(2 * co, device=x.device, dtype=torch.float32)
-    # stats layout is [sum(co) | sumsq(co)]: run each half with its own view of a 2 x co_half scratch, then merge
-    s1 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
-    s2 = torch.zeros(2 * co_half, device=x.device, dtype=torch.float32)
+    # both halves write their columns of one statistics buffer ([rows, sum(co) | sumsq(co)], one row per spatial tile)
+    stats = F_.conv_stats_buffer(x, co_half, 1, 2, 0, total_C=co)
     raw = F_.empty_nhwc(N, co, H // 2, W // 2, x.device, dtype=torch.float32)
-    F_.conv_fwd(x, w1, co_half, 1, 2, 0, out=raw[:, :co_half], stats=s1, out_f32=True)
-    F_.conv_fwd(x, w2, co_half, 1, 2, 0, out=raw[:, co_half:], off=(1, 1), stats=s2, out_f32=True)
-    stats[:co_half], stats[co_half:co] = s1[:co_half], s2[:co_half]
-    stats[co:co + co_half], stats[co + co_half:] = s1[co_half:], s2[co_half:]
+    F_.conv_fwd(x, w1, co_half, 1, 2, 0, out=raw[:, :co_half], stats=stats, out_f32=True)
+    F_.conv_fwd(x, w2, co_half, 1, 2, 0, out=raw[:, co_half:], off=(1, 1), stats=stats, stats_off=co_half, out_f32=True)
     stats = engine.dp_allreduce_stats(stats)
     count = N * (H // 2) * (W // 2) * engine.dp_world_size()
     scale, shift, _, _ = F_.bn_finalize(stats, count, bn.weight, bn.bias, bn.eps, 0.1 if bn.momentum is None else bn.momentum,

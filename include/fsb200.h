@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FSB_ABI_VERSION 1
+#define FSB_ABI_VERSION 2
 
 typedef enum fsb_status {
   FSB_OK = 0,
@@ -44,8 +44,8 @@ typedef enum fsb_status {
 #define FSB_CONV_OUT_F32 16u    /* y is fp32 NHWC (y_cstride in fp32 elements): the training path keeps the raw conv output in
                                    fp32 so that BatchNorm normalises un-rounded values, like the fp32 reference */
 #define FSB_ACT_IN_F32 32u      /* fsb_affine_act: x is fp32 NHWC */
-#define FSB_CONV_STATS 8u       /* also accumulate per-channel sum / sum-of-squares of the (pre-affine) fp32 conv
-                                   output into stats[0..Cout) / stats[Cout..2Cout) (BN train, K2) */
+#define FSB_CONV_STATS 8u       /* also produce per-channel sum / sum-of-squares of the (pre-affine) fp32 conv output as
+                                   PARTIAL ROWS, one per CTA (BN train, K2) -- see "Deterministic statistics" below */
 
 /* One convolution launch.  Replaces F.conv2d at search/slimmable_ops.py:47 and every nn.Conv2d in
  * search/operations.py:42-534 / search/seg_oprs.py:17-39,228-274, fused with the BatchNorm (eval) +
@@ -63,7 +63,33 @@ typedef struct fsb_conv_desc {
   int32_t x_cstride;     /* elements between consecutive pixels of x (>= Cin) */
   int32_t y_cstride;     /* elements between consecutive pixels of y (>= Cout)*/
   uint32_t flags;
+  int32_t stats_C;       /* FSB_CONV_STATS: half-width SC of a statistics row (0 -> Cout); row stride = 2*SC floats     */
+  int32_t stats_off;     /* FSB_CONV_STATS: this conv's channel c lands at row[stats_off + c] / row[SC + stats_off + c]
+                            (FactorizedReduce: two convs fill the two halves of one BatchNorm's statistics)             */
 } fsb_conv_desc;
+
+/* Deterministic statistics.  BatchNorm statistics (forward: sum x, sum x^2; backward: sum dz, sum dz*xhat) and the scalar
+ * gradients of fsb_wsum_bwd are never accumulated with floating-point atomics: a chain of BatchNorm layers amplifies the
+ * run-to-run last-bit differences of atomics into percent-level gradient differences.  Every producer CTA writes one
+ * PARTIAL ROW [sum(0..SC) | sumsq(0..SC)] and the consumer adds the rows in index order in double precision
+ * (fsb_bn_finalize folds this in; fsb_rowsum is the stand-alone form).  The same inputs therefore give bit-identical
+ * activations and activation gradients on every run.  Weight gradients use split-K fp32 atomics by default (their
+ * rounding noise is not amplified); fsb_set_option("FSB_DETERMINISTIC", 1) removes those too. */
+
+/* BatchNorm parameter set selected ON THE DEVICE (captured training graphs: a slimmable unit runs at its maximum width,
+ * the width index of the pass lives in device memory, and channels >= C of the selected set are forced to zero --
+ * USBatchNorm2d's per-width nn.BatchNorm2d list, search/slimmable_ops.py:51-70). */
+typedef struct fsb_bn_sel {
+  float* gamma;
+  float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* dgamma; /* gradient destinations, accumulated into (may be NULL) */
+  float* dbeta;
+  int32_t C;     /* channels of this parameter set */
+  int32_t reserved;
+} fsb_bn_sel;
 
 int fsb_abi_version(void);
 const char* fsb_last_error_string(void);
@@ -73,6 +99,11 @@ int fsb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Programmatic dependent launch between consecutive kernels of this library (default on; env FSB_PDL=0 disables).
  * With it a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps its predecessor's tail. */
 int fsb_set_pdl(int enabled);
+/* Tuning / validation switches, named like their environment variables (FSB_CONV_TC2, FSB_TC2_R, FSB_NO_TMA_STORE,
+ * FSB_DGRAD_S2_DIRECT, FSB_WGRAD_TC, FSB_CONV_PERSIST, FSB_PERSIST_OCC, FSB_PERSIST_STAGES, FSB_UPSAMPLE_V2,
+ * FSB_DETERMINISTIC, FSB_CONV_TC3).  The environment is read once at first use; value -1 = unset. */
+int fsb_set_option(const char* name, int value);
+int fsb_get_option(const char* name);
 
 /* Developer aid: when set (device buffer of 128 uint64), the row-strip conv kernel records %globaltimer stamps of its
  * pipeline phases for the first and last CTA.  NULL disables (default). */
@@ -100,6 +131,9 @@ int fsb_bn_fold(int C, const float* gamma, const float* beta, const float* mean,
  * NHWC tiles; Cin < 16 (the RGB stem) and FSB_CONV_FORCE_DIRECT use the CUDA-core direct kernel. */
 int fsb_conv_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                  void* y, float* stats, void* stream);
+/* number of partial statistic rows fsb_conv_fwd writes for `d` with FSB_CONV_STATS (depends on the kernel it dispatches):
+ * stats must hold rows * 2 * SC floats; every row's entries of this conv's channels are written (no zeroing needed). */
+int fsb_conv_stats_rows(const fsb_conv_desc* d);
 
 /* Stem conv reading the caller's NCHW tensor directly (fp32 if x_is_f32 else fp16), 3x3 stride 2 pad 1,
  * Cin = 3, fused BN(eval)+ReLU, fp16 NHWC out.  ConvNorm at train/model_seg.py:193, search/model_search.py:148.
@@ -130,13 +164,19 @@ int fsb_nhwc_f16_to_nchw(int N, int C, int H, int W, const void* x, int x_cstrid
 int fsb_copy_channels(int64_t pixels, int C, const void* x, int x_cstride, void* y, int y_cstride, void* stream);
 
 /* --- BatchNorm training path (K2/K3) -------------------------------------------------------- */
-/* per-channel sum and sum of squares over `pixels` of an fp16 NHWC tensor: stats[0..C) += sum, stats[C..2C) += sumsq */
-int fsb_bn_stats(int64_t pixels, int C, const void* x, int x_cstride, float* stats, void* stream);
-/* from stats (summed over `count` elements per channel, possibly all-reduced across ranks by the caller):
+/* rows that fsb_bn_stats / fsb_bn_bwd_reduce produce for `pixels` (their buffers hold 1 + rows rows) */
+int fsb_stat_rows(int64_t pixels);
+/* out[c] = sum over r in [0, rows) of src[r * stride + c], c < L, added in index order in double precision */
+int fsb_rowsum(int L, const float* src, int rows, int stride, float* out, void* stream);
+/* per-channel sum and sum of squares over `pixels` of an fp16 NHWC tensor.  buf: (1 + fsb_stat_rows(pixels)) rows of 2*C
+ * floats; rows 1.. receive the per-CTA partials, row 0 their total: buf[0..C) = sum, buf[C..2C) = sumsq. */
+int fsb_bn_stats(int64_t pixels, int C, const void* x, int x_cstride, float* buf, void* stream);
+/* from `rows` partial rows of statistics (row stride 2*SC floats, sums at [c], sums of squares at [SC + c]; rows = 1 for
+ * totals, e.g. after an all-reduce across ranks), summed over `count` elements per channel:
  * mean, biased var -> scale/shift for the apply pass; running stats updated with momentum and UNBIASED var
  * (nn.BatchNorm2d training semantics; sequential per invocation, model_search.py:326-329). Also writes
  * save_mean / save_invstd (fp32[C]) for the backward pass when non-NULL. */
-int fsb_bn_finalize(int C, const float* stats, double count, const float* gamma, const float* beta, float eps,
+int fsb_bn_finalize(int C, const float* stats, int rows, int SC, double count, const float* gamma, const float* beta, float eps,
                     float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                     float* save_mean, float* save_invstd, void* stream);
 /* y = act(x * scale[c] + shift[c]) elementwise on fp16 NHWC (in place allowed) */
@@ -149,16 +189,17 @@ int fsb_affine_act(int64_t pixels, int C, const void* x, int x_cstride, const fl
 
 /* BatchNorm(+ReLU) backward, pass 1: per-channel sums over `pixels` of dz and dz * xhat, with
  *   dz = dy * (relu ? y > 0 : 1),  xhat = (raw - mean[c]) * invstd[c]   (raw = conv output saved by the forward)
- * sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat  (fp32, caller zeroes; all-reduce across ranks for SyncBN). */
+ * sums: (1 + fsb_stat_rows(pixels)) rows of 2*C floats; row 0 = totals: sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat
+ * (no zeroing needed; all-reduce row 0 across ranks for SyncBN). */
 int fsb_bn_bwd_reduce(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
                       int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, int relu, float* sums,
                       void* stream);
 /* pass 2: draw = gamma*invstd * (dz - sum_dz/count - xhat * sum_dzxhat/count); also dgamma = sum_dzxhat/gscale,
- * dbeta = sum_dz/gscale accumulated (+=) into fp32 dgamma/dbeta when non-NULL. */
+ * dbeta = sum_dz/gscale written (accumulate = 0) or added (accumulate != 0) to fp32 dgamma/dbeta when non-NULL. */
 int fsb_bn_bwd_apply(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
                      int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, const float* gamma, const float* sums,
                      double count, int relu, void* draw, int draw_cstride, float* dgamma, float* dbeta, float gscale,
-                     void* stream);
+                     int accumulate, void* stream);
 /* dy_in = dy * (y > 0)  (ReLU backward for affine-free paths) */
 int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, void* dx, int dx_cstride,
                  void* stream);
@@ -193,27 +234,35 @@ int fsb_nchw_grad_to_nhwc(int N, int C, int H, int W, const void* dy, int dy_is_
 
 /* K5: weighted multi-tensor sum (MixedOp / beta aggregation, model_search.py:75-78,326-333):
  *   out = sum_k wts[k] * xs[k]   (K <= 8 tensors of identical shape; wts fp32[K] on the device)
- * backward: dxs[k] = wts[k] * dout (fp16), dwts[k] += <dout, xs[k]> / gscale (fp32). */
+ * backward: dxs[k] = wts[k] * dout (fp16), dwts[k] = <dout, xs[k]> / gscale (fp32).  dwts: (1 + fsb_wsum_rows(pixels, C))
+ * rows of 8 floats (row 0 = totals, rows 1.. = per-CTA partials; no zeroing needed) or NULL. */
+int fsb_wsum_rows(int64_t pixels, int C);
 int fsb_wsum_fwd(int K, int64_t pixels, int C, const void* const* xs, const int* x_cstrides, const float* wts, void* out,
                  int out_cstride, void* stream);
 int fsb_wsum_bwd(int K, int64_t pixels, int C, const void* dout, int dout_cstride, const void* const* xs,
                  const int* x_cstrides, const float* wts, void* const* dxs, const int* dx_cstrides, float* dwts, float gscale,
                  void* stream);
 /* One training unit per call (host-overhead reduction; same kernels as the separate entry points):
- * forward  = conv (fp32 raw output + fused per-channel statistics) -> fsb_bn_finalize (+ running stats, num_batches_tracked)
- *            -> fsb_affine_act.   vec: fp32[6*Cout] = [sum | sumsq | scale | shift | mean | invstd] (zeroed by the call).
+ * forward  = conv (fp32 raw output + per-CTA statistic rows) -> fsb_bn_finalize (+ running stats, num_batches_tracked)
+ *            -> fsb_affine_act.   vec: fp32[(6 + 2*R) * Cout], R = fsb_conv_stats_rows(d) =
+ *            [sum | sumsq (totals; written under data parallelism only) | scale | shift | mean | invstd | R partial rows].
  * backward = fsb_bn_bwd_reduce -> fsb_bn_bwd_apply -> fsb_conv_dgrad (if dx) -> fsb_conv_wgrad accumulate (if dw).
- *            vec_bwd: fp32[4*Cout] = [sum dz | sum dz*xhat | dgamma | dbeta] (zeroed by the call); draw: fp16 NHWC scratch.
+ *            vec_bwd: fp32[(4 + 2*Rb) * Cout], Rb = fsb_stat_rows(N*Ho*Wo) =
+ *            [sum dz | sum dz*xhat | Rb partial rows | dgamma | dbeta]; draw: fp16 NHWC scratch.  Nothing needs zeroing.
+ * sel / width_idx (may be NULL): the BatchNorm parameter set is chosen on the device, sel[*width_idx] (see fsb_bn_sel);
+ *            gamma / beta / running stats arguments are then ignored and dgamma / dbeta accumulate into the selected set.
  * Data parallel: once fsb_dp_init() has created a communicator, both calls all-reduce their 2*Cout statistics over the ranks
  * on `stream` between the stages (SyncBN: global count, gamma/beta gradients from the rank-local sums); without it they are
  * single-process and SyncBN callers use the separate entry points with their own exchange. */
 int fsb_conv_bn_act_train_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* gamma, const float* beta,
                               float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
-                              void* raw_f32, int raw_cstride, void* y, int y_cstride, float* vec, int relu, void* stream);
+                              void* raw_f32, int raw_cstride, void* y, int y_cstride, float* vec, int relu,
+                              const fsb_bn_sel* sel, const int* width_idx, void* stream);
 int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void* dy, int dy_cstride, const void* y, int y_cstride,
                               const void* raw_f32, int raw_cstride, const float* vec_fwd, const float* gamma, int relu,
                               const void* wpacked_t, const float* w, int64_t w_stride_o, int64_t w_stride_i, void* draw,
-                              int draw_cstride, float* vec_bwd, void* dx, int dx_cstride, float* dw, float gscale, void* stream);
+                              int draw_cstride, float* vec_bwd, void* dx, int dx_cstride, float* dw, float gscale,
+                              const fsb_bn_sel* sel, const int* width_idx, void* stream);
 
 /* y (+)= x elementwise over a channel-slice view (gradient accumulation when a tensor feeds several consumers) */
 int fsb_add_inplace(int64_t pixels, int C, const void* x, int x_cstride, void* y, int y_cstride, void* stream);

@@ -20,3 +20,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def lib_option():
+    """set_option(name, value) on the library for the duration of one test (restored afterwards)"""
+    from fasterseg_b200 import _lib
+    saved = []
+
+    def setter(name, value):
+        saved.append((name, _lib.get_option(name)))
+        _lib.set_option(name, value)
+    yield setter
+    for name, old in reversed(saved):
+        _lib.set_option(name, old)
+
+
+@pytest.fixture
+def tc2_forced(lib_option):
+    return lambda: lib_option("FSB_CONV_TC2", 2)

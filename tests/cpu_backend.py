@@ -75,20 +75,31 @@ def _raw_conv(x, w16, stride, pad, off):
     return TF.conv2d(xin, w16.float(), None, stride, pad)
 
 
-def _add_stats(stats, y, Cout):
-    stats[:Cout] += y.sum((0, 2, 3))
-    stats[Cout:2 * Cout] += (y * y).sum((0, 2, 3))
+def _add_stats(stats, y, Cout, at=0):
+    """stats: [rows, 2 * SC] (the stand-in uses ONE zero-initialised row) or [2 * SC]"""
+    row = stats[0] if stats.dim() == 2 else stats
+    SC = row.numel() // 2
+    row[at:at + Cout] += y.sum((0, 2, 3))
+    row[SC + at:SC + at + Cout] += (y * y).sum((0, 2, 3))
+
+
+def conv_stats_buffer(x, Cout, ksize, stride, pad, off=(0, 0), total_C=None, force_direct=False):
+    return torch.zeros((1, 2 * (Cout if total_C is None else int(total_C))), dtype=torch.float32)
+
+
+def rowsum(rows):
+    return rows.double().sum(0, keepdim=True).float()
 
 
 def conv_fwd(x, wpacked, Cout, ksize, stride, pad, scale=None, shift=None, relu=False, out=None, off=(0, 0),
-             stats=None, force_direct=False, out_f32=False):
+             stats=None, force_direct=False, out_f32=False, stats_off=0):
     N, Cin, H, W, _ = nhwc_info(x)
     assert tuple(wpacked.shape) == (Cout, Cin, ksize, ksize), (tuple(wpacked.shape), (Cout, Cin, ksize, ksize))
     y = _raw_conv(x, wpacked, stride, pad, off)
     Ho, Wo = F_.conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
     assert tuple(y.shape) == (N, Cout, Ho, Wo)
     if stats is not None:
-        _add_stats(stats, y, Cout)
+        _add_stats(stats, y, Cout, stats_off)
     if scale is not None:
         y = y * scale.view(1, -1, 1, 1)
     if shift is not None:
@@ -155,15 +166,16 @@ def copy_channels(x, out):
     return out
 
 
-def bn_stats(x, stats=None):
+def bn_stats(x):
     N, Cc, H, W, _ = nhwc_info(x)
-    if stats is None:
-        stats = torch.zeros(2 * Cc, dtype=torch.float32)
+    stats = torch.zeros(2 * Cc, dtype=torch.float32)
     _add_stats(stats, x.float(), Cc)
     return stats
 
 
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, want_save=False):
+    if stats.dim() == 2:
+        stats = stats.double().sum(0).float()
     Cc = stats.numel() // 2
     mean = stats[:Cc].double() / count
     var = (stats[Cc:].double() / count - mean * mean).clamp_min(0)
@@ -293,7 +305,8 @@ def add_inplace(x, y):
 
 
 def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta, eps, momentum, running_mean, running_var,
-                          num_batches_tracked, relu):
+                          num_batches_tracked, relu, sel=None, width_idx=None):
+    assert sel is None and width_idx is None, "device-selected BatchNorm sets exist on the GPU only"
     N, Cin, H, W, xcs = nhwc_info(x)
     Ho, Wo = F_.conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
     stats = torch.zeros(2 * Cout, dtype=torch.float32)
@@ -308,7 +321,7 @@ def conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, gamma, beta
     return y, raw, vec, d
 
 
-def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale):
+def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need_dx, dw_accum, gscale, sel=None, width_idx=None):
     N, Cout, Ho, Wo, _ = nhwc_info(dy)
     mean, invstd = vec[4 * Cout:5 * Cout], vec[5 * Cout:6 * Cout]
     sums = bn_bwd_sums(dy, y, raw, mean, invstd, relu)
@@ -320,7 +333,7 @@ def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need
     return dx, dg, db
 
 
-_PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold", "conv_fwd", "stem_conv_nchw", "bilinear",
+_PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold", "conv_stats_buffer", "rowsum", "conv_fwd", "stem_conv_nchw", "bilinear",
             "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd_sums", "bn_bwd_apply", "relu_bwd",
             "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
             "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd")

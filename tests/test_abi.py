@@ -24,12 +24,12 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(dll, s), "libfsb200.so does not export " + s
     assert sorted(_lib.EXPORTED_SYMBOLS) == syms
-    assert _lib.lib().fsb_abi_version() == 1
+    assert _lib.lib().fsb_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_conv_desc_layout_matches_header():
     from fasterseg_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 16 * 4
+    assert ctypes.sizeof(ConvDesc) == 18 * 4
     src = open(os.path.join(ROOT, "include", "fsb200.h")).read()
     body = src[src.index("typedef struct fsb_conv_desc {"):src.index("} fsb_conv_desc;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)

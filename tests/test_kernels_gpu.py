@@ -71,10 +71,10 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("direct", [False, True])
-def test_conv_bn_relu_matches_oracle(case, direct, monkeypatch):
+def test_conv_bn_relu_matches_oracle(case, direct, tc2_forced):
     F_ = _F()
     if case[6] >= 96 and case[3] == 3 and case[4] == 1:
-        monkeypatch.setenv("FSB_CONV_TC2", "2")  # exercise the row-strip kernel on every wide 3x3 case, not only where it is faster
+        tc2_forced()  # exercise the row-strip kernel on every wide 3x3 case, not only where it is faster
     N, Cin, Cout, k, stride, Hh, Ww = case
     seed = hash(case) % 100000
     x = _rand((N, Cin, Hh, Ww), seed).half().float()
@@ -90,6 +90,72 @@ def test_conv_bn_relu_matches_oracle(case, direct, monkeypatch):
     _close(y.float().cpu(), ref)
 
 
+# channel-major 128 x 256 kernel (conv_tc3.cu): Cin % 64 == 0, Cout % 64 == 0, Cout >= 128; forced on (it is only dispatched on
+# maps >= 12 288 pixels by default)
+TC3_CASES = [
+    # N, Cin, Cout, k, stride, H, W
+    (1, 128, 128, 3, 1, 32, 64),     # heads8-like
+    (1, 192, 128, 3, 1, 24, 40),     # refines32.0-like, ragged tiles (24 x 40 is not a multiple of 8 x 32)
+    (2, 64, 192, 3, 1, 9, 21),       # two M tiles (128 + 64), odd sizes, batch 2
+    (1, 128, 128, 1, 1, 16, 48),     # 1x1 (ffm)
+    (1, 64, 128, 3, 2, 34, 50),      # stride 2: parity planes
+    (1, 256, 256, 3, 1, 8, 12),      # Wo < 16 -> 8 x 32 tiles, 2 M tiles, 4 k-chunks
+]
+
+
+@pytest.mark.parametrize("case", TC3_CASES)
+def test_conv_tc3_channel_major_kernel(case, lib_option):
+    F_ = _F()
+    lib_option("FSB_CONV_TC3", 2)
+    N, Cin, Cout, k, stride, Hh, Ww = case
+    seed = hash(case) % 100000
+    x = _rand((N, Cin, Hh, Ww), seed).half().float()
+    w = (_rand((Cout, Cin, k, k), seed + 1) * (2.0 / (Cin * k * k)) ** 0.5).half().float()
+    scale = torch.from_numpy(np.random.RandomState(seed + 2).uniform(0.5, 1.5, Cout).astype(np.float32))
+    shift = _rand((Cout,), seed + 3, 0.2)
+    pad = 1 if k == 3 else 0
+    ref = torch.relu(orc.conv2d(x, w, None, stride, pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    wp = F_.pack_conv_weight(w.cuda(), Cin, Cout, k)
+    # into a channel slice of a wider buffer: the TMA store must respect offset and stride (zero-copy concat)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    cat = F_.empty_nhwc(N, Cout + 64, Ho, Wo, "cuda")
+    cat.fill_(7.0)
+    y = F_.conv_fwd(_nhwc(x), wp, Cout, k, stride, pad, scale.cuda(), shift.cuda(), relu=True, out=cat[:, 32:32 + Cout])
+    torch.cuda.synchronize()
+    _close(y.float().cpu(), ref)
+    assert float((cat[:, :32] - 7.0).abs().max()) == 0.0 and float((cat[:, 32 + Cout:] - 7.0).abs().max()) == 0.0
+    # bit-identical to the per-tap kernel? no -- different accumulation order; but no epilogue / no relu must agree closely
+    lib_option("FSB_CONV_TC3", 0)
+    y0 = F_.conv_fwd(_nhwc(x), wp, Cout, k, stride, pad, scale.cuda(), shift.cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert float((y0.float() - y.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+def test_statistics_are_bit_reproducible():
+    """conv with fused statistics, bn_stats, bn_bwd sums and wsum scalar gradients: no floating-point atomics -> the same call
+    gives the same bits every time (round 1 differed run to run)."""
+    F_ = _F()
+    x = _nhwc(_rand((3, 64, 40, 72), 31))
+    w = (_rand((96, 64, 3, 3), 32) * 0.05)
+    wp = F_.pack_conv_weight(w.cuda(), 64, 96, 3)
+    outs = []
+    for _ in range(3):
+        st = F_.conv_stats_buffer(x, 96, 3, 1, 1)
+        raw = F_.conv_fwd(x, wp, 96, 3, 1, 1, stats=st, out_f32=True)
+        scale, shift, mean, invstd = F_.bn_finalize(st, 3 * 40 * 72, torch.ones(96, device="cuda"), torch.zeros(96, device="cuda"),
+                                                    1e-5, 0.1, None, None, want_save=True)
+        y = F_.affine_act(raw, scale, shift, relu=True)
+        dy = _nhwc(_rand((3, 96, 40, 72), 33))
+        sums = F_.bn_bwd_sums(dy, y, raw, mean, invstd, True).clone()
+        xs = [y, _nhwc(_rand((3, 96, 40, 72), 34))]
+        _, dw = F_.wsum_bwd(dy, xs, torch.tensor([0.3, 0.7], device="cuda"), [False, False], True, 1024.0)
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (F_.rowsum(st)[0], mean, invstd, F_.bn_stats(y), sums, dw)])
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+
+
 def test_conv_no_epilogue_and_stats():
     F_ = _F()
     N, Cin, Cout, Hh, Ww = 2, 64, 96, 12, 20
@@ -98,11 +164,13 @@ def test_conv_no_epilogue_and_stats():
     ref = orc.conv2d(x, w, None, 1, 1)
     wp = F_.pack_conv_weight(w.cuda(), Cin, Cout, 3)
     for direct in (False, True):
-        stats = torch.zeros(2 * Cout, device="cuda")
-        y = F_.conv_fwd(_nhwc(x), wp, Cout, 3, 1, 1, stats=stats, force_direct=direct)
+        xg = _nhwc(x)
+        stats = F_.conv_stats_buffer(xg, Cout, 3, 1, 1, force_direct=direct)
+        stats.fill_(float("nan"))    # every entry must be written by the launch (no zeroing contract)
+        y = F_.conv_fwd(xg, wp, Cout, 3, 1, 1, stats=stats, force_direct=direct, out_f32=True)
         torch.cuda.synchronize()
         _close(y.float().cpu(), ref)
-        s = stats.cpu().double()
+        s = F_.rowsum(stats)[0].cpu().double()
         np.testing.assert_allclose(s[:Cout].numpy(), ref.double().sum(dim=(0, 2, 3)).numpy(), rtol=2e-4, atol=2e-2)
         np.testing.assert_allclose(s[Cout:].numpy(), ref.double().pow(2).sum(dim=(0, 2, 3)).numpy(), rtol=2e-4, atol=2e-2)
 

@@ -33,7 +33,9 @@ class FakeLib:
                 if _name in ("fsb_conv_packed_bytes", "fsb_conv_packed_dgrad_bytes"):
                     return 4096
                 if _name == "fsb_abi_version":
-                    return 1
+                    return _lib.ABI_VERSION
+                if _name in ("fsb_conv_stats_rows", "fsb_stat_rows", "fsb_wsum_rows"):
+                    return 3       # partial statistic rows the fake "kernels" write
                 return None if _res is C.c_char_p else 0
 
             cb = proto(recorder)
@@ -85,13 +87,23 @@ def test_conv_fwd_marshalling(fake):
     assert d["flags"] == _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE
     assert (px, pw, ps, psh, py, pst) == (x.data_ptr(), wp.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(), None)
     # training flavour: fp32 raw output + statistics, shifted origin (FactorizedReduce's second conv)
-    stats = torch.zeros(48)
-    raw = F_.conv_fwd(x, wp, 24, 1, 2, 0, off=(1, 1), stats=stats, out_f32=True)
+    # (partial statistic rows: one per CTA of the kernel the library will dispatch; this conv fills columns 24.. of a 48-wide set)
+    stats = F_.conv_stats_buffer(x, 24, 1, 2, 0, off=(1, 1), total_C=48)
+    q = fake.last("fsb_conv_stats_rows")[0]
+    assert (q["Cout"], q["off_h"], q["Ho"]) == (24, 1, 6) and q["flags"] & _lib.FSB_CONV_STATS
+    assert tuple(stats.shape) == (3, 96) and stats.dtype == torch.float32
+    raw = F_.conv_fwd(x, wp, 24, 1, 2, 0, off=(1, 1), stats=stats, out_f32=True, stats_off=24)
     d, _, _, ps, psh, py, pst, _ = fake.last("fsb_conv_fwd")
     assert raw.dtype == torch.float32 and tuple(raw.shape) == (2, 24, 6, 10)
     assert (d["off_h"], d["off_w"], d["Ho"], d["Wo"]) == (1, 1, 6, 10)
     assert d["flags"] == _lib.FSB_CONV_STATS | _lib.FSB_CONV_OUT_F32 and (ps, psh) == (None, None)
+    assert (d["stats_C"], d["stats_off"]) == (48, 24)
     assert (py, pst) == (raw.data_ptr(), stats.data_ptr()) and d["y_cstride"] == raw.stride(3)
+    # finalize gets the rows as they are (it adds them in index order itself)
+    gamma, beta = torch.empty(48), torch.empty(48)
+    F_.bn_finalize(stats, 120, gamma, beta, 1e-5, 0.1, None, None)
+    f = fake.last("fsb_bn_finalize")
+    assert f[0] == 48 and f[1] == stats.data_ptr() and (f[2], f[3]) == (3, 48) and f[4] == pytest.approx(120.0)
 
 
 def test_fused_training_unit_marshalling(fake):
@@ -108,7 +120,7 @@ def test_fused_training_unit_marshalling(fake):
     assert a[7:10] == [rm.data_ptr(), rv.data_ptr(), nbt.data_ptr()]
     assert a[10] == raw.data_ptr() and a[11] == raw.stride(3) == 24 and raw.dtype == torch.float32
     assert a[12] == y.data_ptr() and a[13] == y.stride(3) == 24 and y.dtype == torch.float16
-    assert a[14] == vec.data_ptr() and vec.numel() == 6 * 20 and a[15] == 1
+    assert a[14] == vec.data_ptr() and vec.numel() == (6 + 2 * 3) * 20 and a[15] == 1 and a[16] is None and a[17] is None
     assert tuple(y.shape) == tuple(raw.shape) == (2, 20, 12, 20)
     cpu_backend.nhwc_info(y), cpu_backend.nhwc_info(raw, torch.float32)
     # backward
@@ -124,8 +136,10 @@ def test_fused_training_unit_marshalling(fake):
     assert b[11:15] == [wt.data_ptr(), w.data_ptr(), w.stride(0), w.stride(1)] and (w.stride(0), w.stride(1)) == (48 * 9, 9)
     assert b[16] == 24 and b[15] is not None and b[17] is not None        # draw (stride = padded Cout) and the 4C scratch vector
     assert tuple(dx.shape) == (2, 32, 12, 20) and b[18] == dx.data_ptr() and b[19] == dx.stride(3)
-    assert b[20] == acc.data_ptr() and b[21] == pytest.approx(1024.0)
+    assert b[20] == acc.data_ptr() and b[21] == pytest.approx(1024.0) and b[22] is None and b[23] is None
     assert dg.numel() == db.numel() == 20 and dg.data_ptr() != db.data_ptr()
+    # [totals 2C | 3 partial rows x 2C | dgamma | dbeta]
+    assert dg.data_ptr() - b[17] == (2 + 6) * 20 * 4 and db.data_ptr() - dg.data_ptr() == 20 * 4
     # no dx wanted (first layer): null pointer, no allocation
     dx, _, _ = F_.conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, True, None, w, False, acc, 1024.0)
     b = fake.last("fsb_conv_bn_act_train_bwd")
@@ -141,8 +155,8 @@ def test_bn_backward_marshalling(fake):
     assert r[0] == 2 * 6 * 10 and r[1] == 24 and r[2] == dy.data_ptr() and r[4] == y.data_ptr() and r[6] == raw.data_ptr()
     assert r[8] == 1 and r[11] == 1      # raw is fp32, relu mask on
     a = fake.last("fsb_bn_bwd_apply")
-    assert a[12] == r[12] and a[13] == pytest.approx(120.0)   # same sums buffer, count
-    assert a[15] == draw.data_ptr() and a[17] == dg.data_ptr() and a[18] == db.data_ptr()
+    assert a[12] == r[12] and a[13] == pytest.approx(120.0)   # same sums buffer (row 0 = totals), count
+    assert a[15] == draw.data_ptr() and a[17] == dg.data_ptr() and a[18] == db.data_ptr() and a[20] == 0
     # SyncBN composition: the apply kernel gets the all-reduced buffer and no gamma/beta outputs
     seen = {}
 
