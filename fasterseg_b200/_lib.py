@@ -64,6 +64,12 @@ _SIGS = {
     "fsb_bn_bwd_reduce": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
     "fsb_bn_bwd_apply": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_double,
                                    C.c_int, _P, C.c_int, _P, _P, C.c_float, C.c_int, _P]),
+    "fsb_bn_finalize_sel": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "fsb_affine_act_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_uint32, _P, _P, C.c_int, _P]),
+    "fsb_bn_bwd_reduce_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P,
+                                        _P, _P, C.c_int, _P]),
+    "fsb_bn_bwd_apply_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_double,
+                                       C.c_int, _P, C.c_int, C.c_float, _P, _P, C.c_int, _P]),
     "fsb_relu_bwd": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "fsb_conv_packed_dgrad_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "fsb_pack_conv_weight_dgrad": (C.c_int, [C.POINTER(ConvDesc), _P, C.c_int64, C.c_int64, _P, _P]),

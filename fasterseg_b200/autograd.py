@@ -173,7 +173,20 @@ def _dy(t):
     return t.contiguous(memory_format=torch.channels_last) if t.dtype == torch.float16 else F_.to_nhwc_half(t)
 
 
+def grad_slot(param):
+    """fp32 tensor the kernels accumulate this parameter's gradient into: `param.grad` (created zero-filled on first use), or
+    the staging view of the graph context that is capturing a pass (graphed.py)."""
+    ctx = engine.graph_ctx()
+    if ctx is not None:
+        return ctx.stage(param)
+    if param.grad is None:
+        param.grad = torch.zeros_like(param, memory_format=torch.contiguous_format)
+    return param.grad
+
+
 def _dgrad_pack(conv, ci, co):
+    if engine.graph_ctx() is not None:
+        return engine.graph_ctx().packed(conv, ci, co, True)
     cache = conv.__dict__.setdefault("_fsb_wtcache", {})
     ver = engine._versions(conv.weight)
     hit = cache.get((ci, co))
@@ -193,10 +206,7 @@ def _conv_backward(ctx_conv, x, draw, ci, co, off, need_dx, need_dw):
         dx = F_.conv_dgrad(draw, w, tuple(x.shape), ci, co, k, s, p, off=off, wpacked_t=wt)
     if need_dw:
         if FUSED_WGRAD_ACCUMULATION:
-            wparam = ctx_conv.weight
-            if wparam.grad is None:
-                wparam.grad = torch.zeros_like(wparam, memory_format=torch.contiguous_format)
-            F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off, accumulate_into=wparam.grad)
+            F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off, accumulate_into=grad_slot(ctx_conv.weight))
         else:
             dw = F_.conv_wgrad(x, draw, w, ci, co, k, s, p, GRAD_SCALE, off=off)
     return dx, dw
@@ -249,9 +259,7 @@ class ConvBnActFn(torch.autograd.Function):
                 if not FUSED_WGRAD_ACCUMULATION:
                     raise RuntimeError("the fused training unit accumulates weight gradients into param.grad; set "
                                        "FSB_FUSED_WGRAD=1 or enable SyncBN mode for the unfused path")
-                if conv.weight.grad is None:
-                    conv.weight.grad = torch.zeros_like(conv.weight, memory_format=torch.contiguous_format)
-                dw_acc = conv.weight.grad
+                dw_acc = grad_slot(conv.weight)
             wt = _dgrad_pack(conv, ctx.ci, ctx.co) if need[0] else None
             dx, dgamma, dbeta = F_.conv_bn_act_train_bwd(ctx.desc, x, dy, y, raw, vec, gamma, ctx.relu, wt, conv.weight.detach(),
                                                          bool(need[0]), dw_acc, GRAD_SCALE)
@@ -262,6 +270,66 @@ class ConvBnActFn(torch.autograd.Function):
                                         want_param_grads=bool(need[2] or need[3]), allreduce=sync)
         dx, dw = _conv_backward(ctx.conv, x, draw, ctx.ci, ctx.co, ctx.off, need[0], need[1])
         return dx, dw, dgamma if need[2] else None, dbeta if need[3] else None, None, None, None, None, None, None
+
+
+class ConvBnActSelFn(torch.autograd.Function):
+    """act(BN_train(conv(x))) of a slimmable unit whose width is chosen ON THE DEVICE (engine.SelBN): the unit runs at its maximum
+    width, the BatchNorm kernels pick the parameter set from the width index of the pass and force the inactive channel tail to
+    zero, which reproduces USConv2d / USBatchNorm2d slicing exactly (zero activations meet the unused weight columns downstream;
+    zero gradients meet the unused weight rows).  gamma / beta / weight gradients are accumulated by the kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, conv, sel, relu, ci, co):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        wp = engine.packed_weight(conv, ci, co)
+        y, raw, vec, d = F_.conv_bn_act_train_fwd_sel(x, wp, co, k, s, p, (0, 0), sel, relu)
+        ctx.conv, ctx.sel, ctx.relu, ctx.ci, ctx.co, ctx.desc = conv, sel, relu, ci, co, d
+        ctx.save_for_backward(x, raw, y, vec)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, y, vec = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        conv = ctx.conv
+        wt = _dgrad_pack(conv, ctx.ci, ctx.co) if need[0] else None
+        dx = F_.conv_bn_act_train_bwd_sel(ctx.desc, x, _dy(dy), y, raw, vec, ctx.sel, ctx.relu, wt, conv.weight.detach(), bool(need[0]),
+                                          grad_slot(conv.weight) if need[1] else None, GRAD_SCALE)
+        return dx, None, None, None, None, None, None
+
+
+class FactorizedReduceSelFn(torch.autograd.Function):
+    """FactorizedReduceFn with a device-selected width: both 1x1 stride-2 convs run at their maximum half-width hmax and write
+    raw channels [0, hmax) / [hmax, 2 hmax); the BatchNorm kernels map that to the compact order [conv1[:h] | conv2[:h] | 0...]
+    the parameter set and every consumer expect (h = active half-width, read on the device)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, op, sel, ci, hmax):
+        co = 2 * hmax
+        N, _, H, W = x.shape
+        p1 = engine.packed_weight(op.conv1, ci, hmax)
+        p2 = engine.packed_weight(op.conv2, ci, hmax)
+        raw = F_.empty_nhwc(N, co, H // 2, W // 2, x.device, dtype=torch.float32)
+        stats = F_.conv_stats_buffer(x, hmax, 1, 2, 0, total_C=co)
+        F_.conv_fwd(x, p1, hmax, 1, 2, 0, out=raw[:, :hmax], stats=stats, out_f32=True)
+        F_.conv_fwd(x, p2, hmax, 1, 2, 0, out=raw[:, hmax:], off=(1, 1), stats=stats, stats_off=hmax, out_f32=True)
+        count = N * (H // 2) * (W // 2)
+        scale, shift, mean, invstd = F_.bn_finalize_sel(stats, count, sel, hmax=hmax)
+        y = F_.affine_act_sel(raw, scale, shift, sel, hmax, relu=True)
+        ctx.op, ctx.sel, ctx.ci, ctx.hmax, ctx.count = op, sel, ci, hmax, count
+        ctx.save_for_backward(x, raw, y, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, y, mean, invstd = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        h = ctx.hmax
+        draw = F_.bn_bwd_sel(_dy(dy), y, raw, mean, invstd, ctx.count, True, GRAD_SCALE, ctx.sel, hmax=h)
+        dx1, _ = _conv_backward(ctx.op.conv1, x, draw[:, :h], ctx.ci, h, (0, 0), need[0], need[1])
+        dx2, _ = _conv_backward(ctx.op.conv2, x, draw[:, h:], ctx.ci, h, (1, 1), need[0], need[2])
+        dx = F_.add_inplace(dx2, dx1) if need[0] else None
+        return dx, None, None, None, None, None, None
 
 
 class ConvBiasFn(torch.autograd.Function):
@@ -428,6 +496,17 @@ def conv_bn_act_train(x, conv, bn, relu, ci, co, out=None, off=(0, 0)):
     if out is not None:  # autograd-visible copy into a caller-provided slot (training path does not use zero-copy concat)
         raise RuntimeError("out= is an inference-only fast path")
     return y
+
+
+def conv_bn_act_train_sel(x, conv, sel, relu, ci, co):
+    assert conv.bias is None
+    assert FUSED_WGRAD_ACCUMULATION, "device-selected units accumulate weight gradients in the kernels"
+    return call(ConvBnActSelFn, x, conv.weight, conv, sel, relu, ci, co)
+
+
+def factorized_reduce_sel(op, x, sel, ci, hmax):
+    assert FUSED_WGRAD_ACCUMULATION
+    return call(FactorizedReduceSelFn, x, op.conv1.weight, op.conv2.weight, op, sel, ci, hmax)
 
 
 def conv_bias_act(x, conv, relu, ci, co):

@@ -110,14 +110,15 @@ int rowsum_launch(int, const float*, int, int, float*, cudaStream_t);
 int conv_tc_m_tiles(const fsb_conv_desc*);
 int conv_tc2_ctas(const fsb_conv_desc*);
 int bn_finalize_launch(int, const float*, int, int, double, const float*, const float*, float, float, float*, float*, float*, float*,
-                       float*, float*, cudaStream_t, long long* = nullptr, const fsb_bn_sel* = nullptr, const int* = nullptr);
-int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t);
+                       float*, float*, cudaStream_t, long long* = nullptr, const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0);
+int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t,
+                      const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0);
 
 int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*, int,
-                         float*, cudaStream_t);
+                         float*, cudaStream_t, const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0);
 int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
                         const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t, int = 1,
-                        const fsb_bn_sel* = nullptr, const int* = nullptr);
+                        const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0);
 int relu_bwd_launch(int64_t, int, const void*, int, const void*, int, void*, int, cudaStream_t);
 fsb_conv_desc dgrad_as_fwd_desc(const fsb_conv_desc*, int, int);
 int pack_dgrad_launch(const fsb_conv_desc*, const float*, int64_t, int64_t, void*, cudaStream_t);
@@ -312,6 +313,38 @@ int fsb_bn_bwd_apply(int64_t pixels, int C, const void* dy, int dcs, const void*
   return bn_bwd_apply_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, gamma, sums, count, relu, draw, ocs,
                              dgamma, dbeta, gscale, static_cast<cudaStream_t>(stream), accumulate);
 }
+/* ---- device-selected BatchNorm sets (captured training graphs) ---- */
+int fsb_bn_finalize_sel(int C, const float* stats, int rows, int SC, double count, float eps, float momentum, float* scale,
+                        float* shift, float* save_mean, float* save_invstd, const fsb_bn_sel* sel, const int* width_idx, int hmax,
+                        void* stream) {
+  if (C <= 0 || !stats || count <= 0 || rows <= 0 || SC < C || !sel || !width_idx || hmax < 0 || (hmax > 0 && C != 2 * hmax))
+    return set_error(FSB_ERR_INVALID, "bn_finalize_sel: bad argument");
+  return bn_finalize_launch(C, stats, rows, SC, count, nullptr, nullptr, eps, momentum, nullptr, nullptr, scale, shift, save_mean,
+                            save_invstd, static_cast<cudaStream_t>(stream), nullptr, sel, width_idx, hmax);
+}
+int fsb_affine_act_sel(int64_t pixels, int C, const void* x, int xcs, const float* scale, const float* shift, void* y, int ycs,
+                       uint32_t flags, const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream) {
+  if (pixels <= 0 || C <= 0 || !x || !y || !scale || !shift) return set_error(FSB_ERR_INVALID, "affine_act_sel: bad argument");
+  return affine_act_launch(pixels, C, x, xcs, scale, shift, y, ycs, flags, static_cast<cudaStream_t>(stream), sel, width_idx, hmax);
+}
+int fsb_bn_bwd_reduce_sel(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
+                          int raw_is_f32, const float* mean, const float* invstd, int relu, float* sums, const fsb_bn_sel* sel,
+                          const int* width_idx, int hmax, void* stream) {
+  if (pixels <= 0 || C <= 0 || !dy || !raw || !mean || !invstd || !sums || (relu && !y))
+    return set_error(FSB_ERR_INVALID, "bn_bwd_reduce_sel: bad argument");
+  return bn_bwd_reduce_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, relu, sums,
+                              static_cast<cudaStream_t>(stream), sel, width_idx, hmax);
+}
+int fsb_bn_bwd_apply_sel(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
+                         int raw_is_f32, const float* mean, const float* invstd, const float* sums, double count, int relu, void* draw,
+                         int ocs, float gscale, const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream) {
+  if (pixels <= 0 || C <= 0 || !dy || !raw || !mean || !invstd || !sums || !draw || count <= 0 || gscale <= 0 || (relu && !y) || !sel ||
+      !width_idx)
+    return set_error(FSB_ERR_INVALID, "bn_bwd_apply_sel: bad argument");
+  return bn_bwd_apply_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, nullptr, sums, count, relu, draw, ocs,
+                             nullptr, nullptr, gscale, static_cast<cudaStream_t>(stream), 1, sel, width_idx, hmax);
+}
+
 int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, void* dx, int xcs, void* stream) {
   if (pixels <= 0 || C <= 0 || !dy || !y || !dx) return set_error(FSB_ERR_INVALID, "relu_bwd: bad argument");
   return relu_bwd_launch(pixels, C, dy, dcs, y, ycs, dx, xcs, static_cast<cudaStream_t>(stream));

@@ -36,6 +36,18 @@ int bn_fold_launch(int C, const float* gamma, const float* beta, const float* me
 //     row[r][0 .. SC)  = per-channel sum,   row[r][SC .. 2*SC) = per-channel sum of squares   (row stride 2*SC floats)
 // and the consumer adds the rows in index order (bn_finalize folds that in; rowsum_kernel is the stand-alone form).
 // ------------------------------------------------------------------------------------------
+// FactorizedReduce at maximum width (captured training graphs): conv1 writes raw channels [0, hmax), conv2 [hmax, 2*hmax),
+// but with an active half-width h < hmax the BatchNorm set and every consumer see the COMPACT order [conv1[0..h) | conv2[0..h) |
+// inactive...].  remap() is the bijection compact channel -> raw ("expanded") channel; all quantities are multiples of 8 and
+// the kernels apply it per 8-channel vector.  hmax == 0 disables it.
+__host__ __device__ __forceinline__ int split_remap(int c, int h, int hmax) {
+  if (hmax <= 0) return c;
+  if (c < h) return c;
+  if (c < 2 * h) return hmax + (c - h);
+  const int k = c - 2 * h;
+  return k < hmax - h ? h + k : hmax + h + (k - (hmax - h));
+}
+
 int stat_rows(int64_t pixels) {
   int64_t b = (pixels + 255) / 256;
   if (b < 1) b = 1;
@@ -183,7 +195,8 @@ int bn_stats_launch(int64_t pixels, int C, const void* x, int xcs, int x_is_f32,
 __global__ void __launch_bounds__(512)
 bn_finalize_kernel(int C, const float* __restrict__ stats, int P, int SC, double count, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                   float* save_mean, float* save_invstd, long long* num_batches_tracked, const fsb_bn_sel* sel, const int* width_idx) {
+                   float* save_mean, float* save_invstd, long long* num_batches_tracked, const fsb_bn_sel* sel, const int* width_idx,
+                   int hmax) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sh[16][32][2];
@@ -202,9 +215,10 @@ bn_finalize_kernel(int C, const float* __restrict__ stats, int P, int SC, double
   double s = 0.0, q = 0.0;
   if (c < C) {
     const size_t stride = 2 * static_cast<size_t>(SC);
+    const int src = split_remap(c, active / 2, hmax);  // statistics columns are in raw channel order
     for (int r = ty; r < P; r += 16) {
-      s += static_cast<double>(stats[r * stride + c]);
-      q += static_cast<double>(stats[r * stride + SC + c]);
+      s += static_cast<double>(stats[r * stride + src]);
+      q += static_cast<double>(stats[r * stride + SC + src]);
     }
   }
   sh[ty][tx][0] = s;
@@ -246,9 +260,9 @@ bn_finalize_kernel(int C, const float* __restrict__ stats, int P, int SC, double
 int bn_finalize_launch(int C, const float* stats, int P, int SC, double count, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
                        float* save_invstd, cudaStream_t stream, long long* num_batches_tracked, const fsb_bn_sel* sel,
-                       const int* width_idx) {
+                       const int* width_idx, int hmax) {
   FSB_LAUNCH(bn_finalize_kernel, dim3((C + 31) / 32), dim3(512), 0, stream, C, stats, P, SC, count, gamma, beta, eps, momentum,
-             running_mean, running_var, scale, shift, save_mean, save_invstd, num_batches_tracked, sel, width_idx);
+             running_mean, running_var, scale, shift, save_mean, save_invstd, num_batches_tracked, sel, width_idx, hmax);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_finalize launch");
   return FSB_OK;
@@ -278,16 +292,18 @@ __device__ __forceinline__ void load8f<float>(const float* p, float (&f)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 affine_act_kernel(int64_t pixels, int cvec, const T* __restrict__ x, int xcs, const float* __restrict__ scale,
-                  const float* __restrict__ shift, __half* __restrict__ y, int ycs, int relu) {
+                  const float* __restrict__ shift, __half* __restrict__ y, int ycs, int relu, const fsb_bn_sel* sel,
+                  const int* width_idx, int hmax) {
   pdl_launch_dependents();
   pdl_wait();
+  const int h8 = (sel && hmax > 0) ? sel[*width_idx].C / 16 : 0;  // active half-width in 8-channel vectors (x is in raw order)
   const int64_t total = pixels * cvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % cvec);
     const int64_t pix = i / cvec;
     float xin[8];
-    load8f<T>(x + pix * xcs + cv * 8, xin);
+    load8f<T>(x + pix * xcs + split_remap(cv, h8, hmax >> 3) * 8, xin);
     const float4 s0 = *reinterpret_cast<const float4*>(scale + cv * 8);
     const float4 s1 = *reinterpret_cast<const float4*>(scale + cv * 8 + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(shift + cv * 8);
@@ -310,7 +326,8 @@ affine_act_kernel(int64_t pixels, int cvec, const T* __restrict__ x, int xcs, co
   }
 }
 int affine_act_launch(int64_t pixels, int C, const void* x, int xcs, const float* scale, const float* shift, void* y, int ycs,
-                      uint32_t flags, cudaStream_t stream) {
+                      uint32_t flags, cudaStream_t stream, const fsb_bn_sel* sel, const int* width_idx, int hmax) {
+  if (hmax > 0 && (!sel || !width_idx || hmax % 8 || C != 2 * hmax)) return set_error(FSB_ERR_INVALID, "affine_act: bad split arguments");
   if (C % 8 || xcs % 8 || ycs % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
       (reinterpret_cast<uintptr_t>(scale) & 15) || (reinterpret_cast<uintptr_t>(shift) & 15))
     return set_error(FSB_ERR_INVALID, "affine_act: C/strides multiples of 8, pointers 16B aligned");
@@ -320,10 +337,12 @@ int affine_act_launch(int64_t pixels, int C, const void* x, int xcs, const float
   if (blocks < 1) blocks = 1;
   if (flags & FSB_ACT_IN_F32)
     FSB_LAUNCH(affine_act_kernel<float>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8,
-               static_cast<const float*>(x), xcs, scale, shift, static_cast<__half*>(y), ycs, (flags & FSB_CONV_RELU) ? 1 : 0);
+               static_cast<const float*>(x), xcs, scale, shift, static_cast<__half*>(y), ycs, (flags & FSB_CONV_RELU) ? 1 : 0, sel,
+               width_idx, hmax);
   else
     FSB_LAUNCH(affine_act_kernel<__half>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, pixels, C / 8,
-               static_cast<const __half*>(x), xcs, scale, shift, static_cast<__half*>(y), ycs, (flags & FSB_CONV_RELU) ? 1 : 0);
+               static_cast<const __half*>(x), xcs, scale, shift, static_cast<__half*>(y), ycs, (flags & FSB_CONV_RELU) ? 1 : 0, sel,
+               width_idx, hmax);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "affine_act launch");
   return FSB_OK;

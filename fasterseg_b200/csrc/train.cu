@@ -70,11 +70,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------
 // BatchNorm (+ReLU) backward
 // ------------------------------------------------------------------------------------------
+// compact -> raw channel bijection of a FactorizedReduce running at maximum width (see bn.cu split_remap)
+__device__ __forceinline__ int split_remap_t(int c, int h, int hmax) {
+  if (hmax <= 0) return c;
+  if (c < h) return c;
+  if (c < 2 * h) return hmax + (c - h);
+  const int k = c - 2 * h;
+  return k < hmax - h ? h + k : hmax + h + (k - (hmax - h));
+}
 template <typename TR>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dcs, const __half* __restrict__ y, int ycs,
                      const TR* __restrict__ raw, int rcs, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     int relu, float* __restrict__ rows_out) {
+                     int relu, float* __restrict__ rows_out, const fsb_bn_sel* sel, const int* width_idx, int hmax) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];
@@ -82,6 +90,7 @@ bn_bwd_reduce_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int d
   const int rows = blockDim.x / cvec;
   const int cv = threadIdx.x % cvec;
   const int row = threadIdx.x / cvec;
+  const int rcv = split_remap_t(cv, (sel && hmax > 0) ? sel[*width_idx].C / 16 : 0, hmax >> 3);  // raw is in raw channel order
   float s[8], q[8], mu[8], is[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -93,7 +102,7 @@ bn_bwd_reduce_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int d
     for (int64_t p = static_cast<int64_t>(blockIdx.x) * rows + row; p < pixels; p += static_cast<int64_t>(gridDim.x) * rows) {
       float d[8], r[8], yy[8];
       unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cv * 8), d);
-      load8t<TR>(raw + p * rcs + cv * 8, r);
+      load8t<TR>(raw + p * rcs + rcv * 8, r);
       if (relu) unpack8(*reinterpret_cast<const uint4*>(y + p * ycs + cv * 8), yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -128,7 +137,7 @@ bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dc
                     const TR* __restrict__ raw, int rcs, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int relu,
                     __half* __restrict__ draw, int ocs, float* __restrict__ dgamma, float* __restrict__ dbeta, float inv_gscale,
-                    int accumulate, const fsb_bn_sel* sel, const int* width_idx) {
+                    int accumulate, const fsb_bn_sel* sel, const int* width_idx, int hmax) {
   pdl_launch_dependents();
   pdl_wait();
   const int cvec = C >> 3;
@@ -151,9 +160,10 @@ bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dc
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % cvec);
     const int64_t p = i / cvec;
+    const int rcv = split_remap_t(cv, hmax > 0 ? active >> 4 : 0, hmax >> 3);  // raw and draw are in raw channel order
     float d[8], r[8], yy[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cv * 8), d);
-    load8t<TR>(raw + p * rcs + cv * 8, r);
+    load8t<TR>(raw + p * rcs + rcv * 8, r);
     if (relu) unpack8(*reinterpret_cast<const uint4*>(y + p * ycs + cv * 8), yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -163,7 +173,7 @@ bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dc
       const float g = (gamma && c < active) ? gamma[c] : (c < active ? 1.f : 0.f);
       o[j] = g * invstd[c] * (dz - sums[c] * inv_count - xh * sums[C + c] * inv_count);
     }
-    *reinterpret_cast<uint4*>(draw + p * ocs + cv * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(draw + p * ocs + rcv * 8) = pack8(o);
   }
 }
 
@@ -199,7 +209,9 @@ int rowsum_launch(int L, const float* rows, int P, int stride, float* out, cudaS
 
 // sums: (1 + stat_rows(pixels)) rows of 2*C floats; the partial rows land in rows 1.., their fixed-order total in row 0
 int bn_bwd_reduce_launch(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
-                         int raw_f32, const float* mean, const float* invstd, int relu, float* sums, cudaStream_t stream) {
+                         int raw_f32, const float* mean, const float* invstd, int relu, float* sums, cudaStream_t stream,
+                         const fsb_bn_sel* sel, const int* width_idx, int hmax) {
+  if (hmax > 0 && (!sel || !width_idx || hmax % 8 || C != 2 * hmax)) return set_error(FSB_ERR_INVALID, "bn_bwd_reduce: bad split arguments");
   if (!vec_ok(C, dcs, dy) || !vec_ok(C, rcs, raw) || (relu && !vec_ok(C, ycs, y)) || C > 2048)
     return set_error(FSB_ERR_INVALID, "bn_bwd_reduce: C/strides multiples of 8, pointers 16B aligned");
   const int cvec = C / 8, threads = 256;
@@ -211,11 +223,11 @@ int bn_bwd_reduce_launch(int64_t pixels, int C, const void* dy, int dcs, const v
   if (raw_f32)
     FSB_LAUNCH(bn_bwd_reduce_kernel<float>, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const float*>(raw), rcs, mean,
-               invstd, relu, part);
+               invstd, relu, part, sel, width_idx, hmax);
   else
     FSB_LAUNCH(bn_bwd_reduce_kernel<__half>, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const __half*>(raw), rcs, mean,
-               invstd, relu, part);
+               invstd, relu, part, sel, width_idx, hmax);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd_reduce launch");
   return rowsum_launch(2 * C, part, blocks, 2 * C, sums, stream);
@@ -223,19 +235,20 @@ int bn_bwd_reduce_launch(int64_t pixels, int C, const void* dy, int dcs, const v
 int bn_bwd_apply_launch(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
                         int raw_f32, const float* mean, const float* invstd, const float* gamma, const float* sums, double count, int relu,
                         void* draw, int ocs, float* dgamma, float* dbeta, float gscale, cudaStream_t stream, int accumulate,
-                        const fsb_bn_sel* sel, const int* width_idx) {
+                        const fsb_bn_sel* sel, const int* width_idx, int hmax) {
+  if (hmax > 0 && (!sel || !width_idx || hmax % 8 || C != 2 * hmax)) return set_error(FSB_ERR_INVALID, "bn_bwd_apply: bad split arguments");
   if (!vec_ok(C, dcs, dy) || !vec_ok(C, rcs, raw) || !vec_ok(C, ocs, draw) || (relu && !vec_ok(C, ycs, y)))
     return set_error(FSB_ERR_INVALID, "bn_bwd_apply: C/strides multiples of 8, pointers 16B aligned");
   if (raw_f32)
     FSB_LAUNCH(bn_bwd_apply_kernel<float>, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const float*>(raw), rcs, mean,
                invstd, gamma, sums, static_cast<float>(1.0 / count), relu, static_cast<__half*>(draw), ocs, dgamma, dbeta,
-               1.0f / gscale, accumulate, sel, width_idx);
+               1.0f / gscale, accumulate, sel, width_idx, hmax);
   else
     FSB_LAUNCH(bn_bwd_apply_kernel<__half>, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const __half*>(raw), rcs, mean,
                invstd, gamma, sums, static_cast<float>(1.0 / count), relu, static_cast<__half*>(draw), ocs, dgamma, dbeta,
-               1.0f / gscale, accumulate, sel, width_idx);
+               1.0f / gscale, accumulate, sel, width_idx, hmax);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd_apply launch");
   return FSB_OK;

@@ -6,13 +6,14 @@
 namespace fsb {
 
 int bn_finalize_launch(int, const float*, int, int, double, const float*, const float*, float, float, float*, float*, float*, float*,
-                       float*, float*, cudaStream_t, long long*, const fsb_bn_sel*, const int*);
-int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t);
+                       float*, float*, cudaStream_t, long long*, const fsb_bn_sel*, const int*, int);
+int affine_act_launch(int64_t, int, const void*, int, const float*, const float*, void*, int, uint32_t, cudaStream_t,
+                      const fsb_bn_sel*, const int*, int);
 int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*, int,
-                         float*, cudaStream_t);
+                         float*, cudaStream_t, const fsb_bn_sel*, const int*, int);
 int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
                         const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t, int,
-                        const fsb_bn_sel*, const int*);
+                        const fsb_bn_sel*, const int*, int);
 int rowsum_launch(int, const float*, int, int, float*, cudaStream_t);
 int conv_tc_m_tiles(const fsb_conv_desc*);
 int conv_tc2_ctas(const fsb_conv_desc*);
@@ -79,10 +80,10 @@ int fsb_conv_bn_act_train_fwd(const fsb_conv_desc* d, const void* x, const void*
     R = 1;
   }
   rc = bn_finalize_launch(C, stats, R, C, static_cast<double>(pixels) * world, gamma, beta, eps, momentum, running_mean, running_var,
-                          vec + 2 * C, vec + 3 * C, vec + 4 * C, vec + 5 * C, st, num_batches_tracked, sel, width_idx);
+                          vec + 2 * C, vec + 3 * C, vec + 4 * C, vec + 5 * C, st, num_batches_tracked, sel, width_idx, 0);
   if (rc) return rc;
   return affine_act_launch(pixels, C, raw_f32, raw_cstride, vec + 2 * C, vec + 3 * C, y, y_cstride,
-                           (relu ? FSB_CONV_RELU : 0u) | FSB_ACT_IN_F32, st);
+                           (relu ? FSB_CONV_RELU : 0u) | FSB_ACT_IN_F32, st, nullptr, nullptr, 0);
 }
 
 /* Backward of the unit.  vec_fwd: the forward's vec (mean at 4C, invstd at 5C).  vec_bwd: fp32[(4 + 2Rb)*Cout] = [sum dz |
@@ -103,7 +104,7 @@ int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void*
   float* dgamma = vec_bwd + static_cast<size_t>(2 + 2 * Rb) * C;  // [totals (2C) | Rb partial rows | dgamma | dbeta]
   float* dbeta = dgamma + C;
   int rc = bn_bwd_reduce_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, relu,
-                                vec_bwd, st);
+                                vec_bwd, st, nullptr, nullptr, 0);
   if (rc) return rc;
   const int world = dp_world();
   if (world > 1) {
@@ -115,10 +116,10 @@ int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void*
     if (rc) return rc;
     rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
                              static_cast<double>(pixels) * world, relu, draw, draw_cstride, nullptr, nullptr, gscale, st, 0, sel ? sel : nullptr,
-                             width_idx);
+                             width_idx, 0);
   } else {
     rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
-                             static_cast<double>(pixels), relu, draw, draw_cstride, dgamma, dbeta, gscale, st, sel ? 1 : 0, sel, width_idx);
+                             static_cast<double>(pixels), relu, draw, draw_cstride, dgamma, dbeta, gscale, st, sel ? 1 : 0, sel, width_idx, 0);
   }
   if (rc) return rc;
   if (dx) {

@@ -16,12 +16,58 @@ import torch.nn as nn
 from . import functional as F_
 
 
+# ----------------------------------------------------------------------------------------------
+# Device-selected widths (captured training graphs, graphed.py).  A SymRatio stands for "the width whose index sits in slot
+# `slot` of the pass's width-index vector on the device"; a slimmable conv given a SymRatio runs at its MAXIMUM width and its
+# USBatchNorm2d hands out a SelBN (all per-width parameter sets as a device table) instead of one nn.BatchNorm2d.
+# ----------------------------------------------------------------------------------------------
+class SymRatio:
+    __slots__ = ("slot",)
+
+    def __init__(self, slot):
+        self.slot = int(slot)
+
+    def __repr__(self):
+        return "SymRatio(%d)" % self.slot
+
+
+class SelBN:
+    """The per-width nn.BatchNorm2d sets of one USBatchNorm2d, selected on the device by the width index in slot `slot`."""
+    training = True
+
+    def __init__(self, usbn, slot, ctx):
+        self.usbn, self.slot, self.ctx = usbn, int(slot), ctx
+        self.bns = list(usbn.bn)
+        self.eps = self.bns[0].eps
+        self.momentum = 0.1 if self.bns[0].momentum is None else self.bns[0].momentum
+        assert all(b.eps == self.eps and (0.1 if b.momentum is None else b.momentum) == self.momentum and b.track_running_stats
+                   for b in self.bns), "the per-width BatchNorm sets of a slimmable unit must share eps / momentum"
+        self.C_max = usbn.num_features_max
+
+    @property
+    def table_ptr(self):
+        return self.ctx.sel_table_ptr(self)
+
+    @property
+    def idx_ptr(self):
+        return self.ctx.width_idx_ptr(self.slot)
+
+
+_GRAPH_CTX = None   # the graphed.PassContext that is currently building / capturing a pass (None: ordinary execution)
+
+
+def graph_ctx():
+    return _GRAPH_CTX
+
+
 def _versions(*tensors):
     return tuple(-1 if t is None else (t._version, t.data_ptr()) for t in tensors)
 
 
 def packed_weight(conv: nn.Conv2d, ci: int, co: int) -> torch.Tensor:
     """fp16 packed copy of conv.weight[:co, :ci] (USConv2d slice, slimmable_ops.py:42), cached."""
+    if _GRAPH_CTX is not None:
+        return _GRAPH_CTX.packed(conv, ci, co, False)
     cache = conv.__dict__.setdefault("_fsb_wcache", {})
     key = (ci, co)
     weight = conv.weight
@@ -82,6 +128,10 @@ def conv_bn_act(x: torch.Tensor, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], 
     assert conv.dilation[0] == 1 and conv.groups == 1, "only dense dilation-1 convs are on the hot path (SURVEY section 0)"
     wp = packed_weight(conv, ci, co)
     bn = active_bn(bn) if bn is not None else None
+    if isinstance(bn, SelBN):
+        from .autograd import conv_bn_act_train_sel
+        assert out is None and off == (0, 0)
+        return conv_bn_act_train_sel(x, conv, bn, relu, ci, co)
     training = bn is not None and (bn.training or bn.running_mean is None)
     from . import autograd as AG
     want_grad = AG.grad_mode(x, conv.weight)

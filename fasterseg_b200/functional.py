@@ -111,13 +111,15 @@ def make_conv_desc(N, H, W, Cin, Cout, ksize, stride, pad, x_cstride, y_cstride,
     return ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, dil, off_h, off_w, Ho, Wo, x_cstride, y_cstride, flags)
 
 
-def pack_conv_weight(w: torch.Tensor, Cin: int, Cout: int, ksize: int) -> torch.Tensor:
-    """fp32 OIHW master weight (possibly max-width; only [:Cout, :Cin] is read) -> packed fp16 buffer."""
+def pack_conv_weight(w: torch.Tensor, Cin: int, Cout: int, ksize: int, out=None) -> torch.Tensor:
+    """fp32 OIHW master weight (possibly max-width; only [:Cout, :Cin] is read) -> packed fp16 buffer (`out`: re-pack in place)."""
     assert _on_device(w) and w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] == ksize and w.shape[3] == ksize
     assert w.stride(3) == 1 and w.stride(2) == ksize
     d = ConvDesc(1, 8, 8, Cin, Cout, ksize, 1, 0, 1, 0, 0, 8, 8, Cin, Cout, 0)
     nbytes = _lib.lib().fsb_conv_packed_bytes(C.byref(d))
-    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.float16)
+    if out is None:
+        out = torch.empty(nbytes // 2, device=w.device, dtype=torch.float16)
+    assert out.numel() * 2 == nbytes and out.dtype == torch.float16
     check(_lib.lib().fsb_pack_conv_weight(C.byref(d), _ptr(w), w.stride(0), w.stride(1), _ptr(out), _stream()),
           "fsb_pack_conv_weight")
     return out
@@ -331,10 +333,12 @@ def relu_bwd(dy, y):
     return dx
 
 
-def pack_conv_weight_dgrad(w, Cin, Cout, ksize):
+def pack_conv_weight_dgrad(w, Cin, Cout, ksize, out=None):
     d = ConvDesc(1, 8, 8, Cin, Cout, ksize, 1, (ksize - 1) // 2, 1, 0, 0, 8, 8, Cin, Cout, 0)
     nbytes = _lib.lib().fsb_conv_packed_dgrad_bytes(C.byref(d))
-    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.float16)
+    if out is None:
+        out = torch.empty(nbytes // 2, device=w.device, dtype=torch.float16)
+    assert out.numel() * 2 == nbytes and out.dtype == torch.float16
     check(_lib.lib().fsb_pack_conv_weight_dgrad(C.byref(d), _ptr(w), w.stride(0), w.stride(1), _ptr(out), _stream()),
           "fsb_pack_conv_weight_dgrad")
     return out
@@ -496,3 +500,57 @@ def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need
           "fsb_conv_bn_act_train_bwd")
     at = (2 + 2 * rows) * Cout
     return dx, vb[at:at + Cout], vb[at + Cout:at + 2 * Cout]
+
+
+# ----------------------------------------------------------------------------------------------
+# device-selected BatchNorm sets (captured training graphs, fasterseg_b200/graphed.py).  `sel` is an engine.SelBN: `.table_ptr`
+# = device address of its fsb_bn_sel table (one entry per width), `.idx_ptr` = device address of the int32 width index of the
+# current pass.  Units run at their maximum width; the kernels zero the inactive tail (include/fsb200.h).
+# ----------------------------------------------------------------------------------------------
+def conv_bn_act_train_fwd_sel(x, wpacked, Cout, ksize, stride, pad, off, sel, relu):
+    return conv_bn_act_train_fwd(x, wpacked, Cout, ksize, stride, pad, off, None, None, sel.eps, sel.momentum, None, None, None, relu,
+                                 sel=sel.table_ptr, width_idx=sel.idx_ptr)
+
+
+def conv_bn_act_train_bwd_sel(d, x, dy, y, raw, vec, sel, relu, wpacked_t, w, need_dx, dw_accum, gscale):
+    dx, _, _ = conv_bn_act_train_bwd(d, x, dy, y, raw, vec, None, relu, wpacked_t, w, need_dx, dw_accum, gscale,
+                                     sel=sel.table_ptr, width_idx=sel.idx_ptr)
+    return dx
+
+
+def bn_finalize_sel(stats, count, sel, hmax=0):
+    """-> (scale, shift, mean, invstd) fp32 [C]; C = stats columns / 2 (the unit's maximum width)"""
+    Cc = stats.shape[1] // 2
+    buf = torch.empty((4, Cc), device=stats.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_finalize_sel(Cc, _ptr(stats), stats.shape[0], Cc, float(count), float(sel.eps), float(sel.momentum),
+                                         _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), sel.table_ptr, sel.idx_ptr, int(hmax),
+                                         _stream()), "fsb_bn_finalize_sel")
+    return buf[0], buf[1], buf[2], buf[3]
+
+
+def affine_act_sel(x, scale, shift, sel, hmax, relu=False):
+    N, Cc, H, W, xcs = nhwc_info(x, x.dtype)
+    out = empty_nhwc(N, Cc, H, W, x.device)
+    flags = (FSB_CONV_RELU if relu else 0) | (FSB_ACT_IN_F32 if x.dtype == torch.float32 else 0)
+    check(_lib.lib().fsb_affine_act_sel(N * H * W, Cc, _ptr(x), xcs, _ptr(scale), _ptr(shift), _ptr(out), nhwc_info(out)[4], flags,
+                                        sel.table_ptr, sel.idx_ptr, int(hmax), _stream()), "fsb_affine_act_sel")
+    return out
+
+
+def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0):
+    """BatchNorm(+ReLU) backward of a device-selected set -> draw (raw channel order when hmax > 0); gamma / beta gradients are
+    accumulated into the selected set's gradient slots by the kernel."""
+    N, Cc, H, W, dcs = nhwc_info(dy)
+    _, _, _, _, rcs = nhwc_info(raw, raw.dtype)
+    rf32 = int(raw.dtype == torch.float32)
+    ycs = nhwc_info(y)[4] if relu else 0
+    rows = _lib.lib().fsb_stat_rows(N * H * W)
+    sums = torch.empty((1 + rows, 2 * Cc), device=dy.device, dtype=torch.float32)
+    check(_lib.lib().fsb_bn_bwd_reduce_sel(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
+                                           _ptr(invstd), int(relu), _ptr(sums), sel.table_ptr, sel.idx_ptr, int(hmax), _stream()),
+          "fsb_bn_bwd_reduce_sel")
+    draw = empty_nhwc(N, Cc, H, W, dy.device)
+    check(_lib.lib().fsb_bn_bwd_apply_sel(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
+                                          _ptr(invstd), _ptr(sums), float(count), int(relu), _ptr(draw), nhwc_info(draw)[4],
+                                          float(gscale), sel.table_ptr, sel.idx_ptr, int(hmax), _stream()), "fsb_bn_bwd_apply_sel")
+    return draw

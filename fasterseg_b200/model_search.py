@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from torch.autograd import Variable
 
 from . import autograd as AG
+from . import engine
 from . import functional as F_
 from .genotypes import PRIMITIVES
 from .operations import *  # noqa: F401,F403
@@ -72,7 +73,10 @@ def gumbel_softmax(logits, temperature=1, hard=False):
 
 
 def _resolve_ratio(r, width_mult_list):
-    """tensor -> (width_mult_list[argmax], score tensor = r[argmax]) ; float -> (forced width, 1.)  (model_search.py:63-74)"""
+    """tensor -> (width_mult_list[argmax], score tensor = r[argmax]) ; float -> (forced width, 1.)  (model_search.py:63-74);
+    engine.SymRatio (width chosen on the device in a captured pass) -> itself, score folded into the planned weights"""
+    if isinstance(r, engine.SymRatio):
+        return r, 1.
     if isinstance(r, torch.Tensor):
         idx = int(r.argmax())
         return width_mult_list[idx], r[idx]
@@ -97,6 +101,8 @@ class MixedOp(nn.Module):
         """switch every primitive to the (in, out) widths and fold the two width scores into the op weights"""
         (w_in, score_in), (w_out, score_out) = (_resolve_ratio(r, self._width_mult_list) for r in ratios[:2])
         self.set_prun_ratio((w_in, w_out))
+        if hasattr(weights, "take_slot"):       # planned pass (graphed.py): a static slot holding softmax(alpha) x width scores
+            return weights.take_slot(ratios[0], ratios[1])
         return weights * score_in * score_out  # [len(PRIMITIVES)] scalar arithmetic (plumbing)
 
     def forward(self, x, weights, ratios):
@@ -280,29 +286,36 @@ class Network_Multi_Path(nn.Module):
             return AG.run_taped(self, self._forward, input)   # EXPERIMENTAL: the whole pass as one autograd node
         return self._forward(input)
 
-    def _forward(self, input):
+    def _forward(self, input, plan=None):
+        """plan (graphed.PassContext): a captured pass -- mixing weights and widths come from static device slots instead of being
+        computed here; the tensor work is identical."""
         idx = self.arch_idx
         refine16, refine32 = self.refine16[idx], self.refine32[idx]
-        alphas, betas = self._distributions()
-        # one host read instead of a GPU->CPU sync per `betas[...] > 0` test (model_search.py:326-329)
-        alive = [None] + [(b.detach() > 0).tolist() for b in betas[1:]]
-        ratios = self.sample_prun_ratio(mode=self._current_mode())
+        if plan is None:
+            alphas, betas = self._distributions()
+            # one host read instead of a GPU->CPU sync per `betas[...] > 0` test (model_search.py:326-329)
+            alive = [None] + [(b.detach() > 0).tolist() for b in betas[1:]]
+            ratios = self.sample_prun_ratio(mode=self._current_mode())
+        else:
+            ratios = plan.sym_ratios
 
         prev, cur, at_layer = {0: (self.stem[idx](input), None)}, {}, 0
         for node in self._nodes:
             if node.layer != at_layer:
                 prev, cur, at_layer = cur, {}, node.layer
             cell = self.cells[node.layer][node.scale]
-            alpha = alphas[node.scale][node.layer - node.scale]
+            arow = node.layer - node.scale
+            alpha = alphas[node.scale][arow] if plan is None else plan.alpha(node.scale, arow)
             ratio = self._ratio_triple(node.layer, node.scale, ratios)
             if node.beta_row is None:
                 (src, port), = node.feeds
                 cur[node.scale] = cell(prev[src][port], alpha, ratio)
             else:
                 # same weights, two inputs ("0: from down", then "1: from keep"); BN running stats see both, in this order
-                flags = alive[node.scale][node.beta_row]
+                flags = alive[node.scale][node.beta_row] if plan is None else (True, True)   # softmax(beta) > 0 barring underflow
                 results = [cell(prev[src][port], alpha, ratio) if flags[n] else None for n, (src, port) in enumerate(node.feeds)]
-                cur[node.scale] = _blend(betas[node.scale][node.beta_row], results)
+                brow = betas[node.scale][node.beta_row] if plan is None else plan.beta(node.scale, node.beta_row)
+                cur[node.scale] = _blend(brow, results)
         f8, f16, f32 = (cur[s][KEEP] for s in range(3))
 
         out0 = f8
@@ -382,6 +395,9 @@ class Network_Multi_Path(nn.Module):
             passes += [(None, mode) for mode in ["max", "min"] + (["random", "random"] if pretrain == True else [])]  # noqa: E712
         elif pretrain == True and len(self._width_mult_list) == 1:  # noqa: E712
             passes.append((None, "max"))
+        runner = self._graph_runner(input)
+        if runner is not None:
+            return runner.loss(input, target, passes)
         loss = 0
         for arch, mode in passes:
             if arch is not None:
@@ -389,6 +405,23 @@ class Network_Multi_Path(nn.Module):
             self.prun_mode = mode
             loss = loss + sum(self._criterion(logit, target) for logit in self(input))
         return loss
+
+    def _graph_runner(self, input):
+        """graphed.GraphedLoss of this model when `_loss` can run as captured passes (training mode, gradients on, CUDA, single
+        process or library-owned data parallelism, more than one width), else None -> the eager path above."""
+        from . import graphed
+        forced = self.__dict__.get("_fsb_graph_mode")          # tests: True forces (eager passes on CPU), False disables
+        if forced is False or (forced is None and not (graphed.ENABLED and input.is_cuda)):
+            return None
+        if not (self.training and torch.is_grad_enabled() and len(self._width_mult_list) > 1 and AG.FUSED_WGRAD_ACCUMULATION):
+            return None
+        if engine.dp_world_size() > 1 and not engine.dp_native():
+            return None
+        runner = self.__dict__.get("_fsb_graph_runner")
+        if runner is None:
+            runner = graphed.GraphedLoss(self, capture=input.is_cuda)
+            self.__dict__["_fsb_graph_runner"] = runner
+        return runner
 
     def _arch_shapes(self, idx):
         num_ops = len(PRIMITIVES)

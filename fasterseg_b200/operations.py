@@ -345,6 +345,10 @@ def _factorized_reduce_s2(op, x, out):
     assert H % 2 == 0 and W % 2 == 0, "FactorizedReduce needs even H, W (the reference's cat fails otherwise)"
     co = 2 * co_half
     from .autograd import grad_mode
+    if isinstance(bn, engine.SelBN):   # width chosen on the device: both halves at their maximum width (autograd.FactorizedReduceSelFn)
+        from .autograd import factorized_reduce_sel
+        assert out is None
+        return factorized_reduce_sel(op, x, bn, ci, co_half)
     if bn.training and grad_mode(x, op.conv1.weight):
         from .autograd import factorized_reduce_train
         return factorized_reduce_train(op, x, bn, ci, co_half, out)

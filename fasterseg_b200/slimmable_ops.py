@@ -55,7 +55,8 @@ class USConv2d(_WidthSwitch, nn.Conv2d):
         known = self.__dict__.setdefault("_corner_cache", {})
         active = known.get(ratio)
         if active is None:
-            fractions = [self._checked(r) for r in ratio]
+            # a SymRatio (width chosen on the device, engine.SymRatio) runs the conv at its maximum width
+            fractions = [1. if isinstance(r, engine.SymRatio) else self._checked(r) for r in ratio]
             active = tuple(make_divisible(full * r) for full, r in zip((self.in_channels_max, self.out_channels_max), fractions))
             known[ratio] = active
         state = self.__dict__     # in_channels / out_channels / groups are plain attributes of nn.Conv2d
@@ -81,6 +82,10 @@ class USBatchNorm2d(_WidthSwitch, nn.BatchNorm2d):
         self.ratio = 1.
 
     def _active_bn(self):
+        if isinstance(self.ratio, engine.SymRatio):
+            ctx = engine.graph_ctx()
+            assert ctx is not None, "a device-selected width needs an active graph context"
+            return ctx.sel_bn(self, self.ratio.slot)
         return self.bn[self.width_mult_list.index(self._checked(self.ratio))]
 
     def forward(self, input):

@@ -200,6 +200,23 @@ int fsb_bn_bwd_apply(int64_t pixels, int C, const void* dy, int dy_cstride, cons
                      int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, const float* gamma, const float* sums,
                      double count, int relu, void* draw, int draw_cstride, float* dgamma, float* dbeta, float gscale,
                      int accumulate, void* stream);
+/* Device-selected variants (captured training graphs).  The BatchNorm parameter set is sel[*width_idx]; channels at or
+ * beyond its width C get scale = shift = mean = invstd = 0 (forward) and draw = 0 (backward); gamma / beta gradients are
+ * ACCUMULATED into sel[...].dgamma / dbeta.  hmax > 0 (FactorizedReduce at maximum width, C == 2*hmax): the conv outputs
+ * (raw, statistics columns, draw) are in "raw" channel order [conv1 0..hmax | conv2 0..hmax) while y / dy / the parameter
+ * set use the compact order [conv1 0..h | conv2 0..h | inactive], h = sel[...].C / 2; the kernels apply the bijection. */
+int fsb_bn_finalize_sel(int C, const float* stats, int rows, int SC, double count, float eps, float momentum, float* scale,
+                        float* shift, float* save_mean, float* save_invstd, const fsb_bn_sel* sel, const int* width_idx, int hmax,
+                        void* stream);
+int fsb_affine_act_sel(int64_t pixels, int C, const void* x, int x_cstride, const float* scale, const float* shift, void* y,
+                       int y_cstride, uint32_t flags, const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream);
+int fsb_bn_bwd_reduce_sel(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
+                          int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, int relu, float* sums,
+                          const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream);
+int fsb_bn_bwd_apply_sel(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
+                         int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, const float* sums, double count,
+                         int relu, void* draw, int draw_cstride, float gscale, const fsb_bn_sel* sel, const int* width_idx, int hmax,
+                         void* stream);
 /* dy_in = dy * (y > 0)  (ReLU backward for affine-free paths) */
 int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, void* dx, int dx_cstride,
                  void* stream);

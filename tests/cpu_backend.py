@@ -55,9 +55,13 @@ def to_nchw(x, dtype=torch.float32):
     return x.detach().to(dtype).contiguous()
 
 
-def pack_conv_weight(w, Cin, Cout, ksize):
+def pack_conv_weight(w, Cin, Cout, ksize, out=None):
     assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] == ksize and w.shape[3] == ksize
-    return w[:Cout, :Cin].detach().half().contiguous()
+    packed = w[:Cout, :Cin].detach().half().contiguous()
+    if out is not None:
+        out.copy_(packed)
+        return out
+    return packed
 
 
 def bn_fold(gamma, beta, mean, var, eps, conv_bias=None):
@@ -70,8 +74,15 @@ def bn_fold(gamma, beta, mean, var, eps, conv_bias=None):
     return scale.contiguous(), shift.contiguous()
 
 
+# float64 accumulation in the stand-in convs / gradients: makes results independent of the summation order (needed where two
+# code paths that differ only in zero-padded channels must agree to the last fp32 bit, tests/test_graphed_cpu.py)
+PRECISE = {"on": False}
+
+
 def _raw_conv(x, w16, stride, pad, off):
     xin = x[:, :, off[0]:, off[1]:].float()
+    if PRECISE["on"]:
+        return TF.conv2d(xin.double(), w16.double(), None, stride, pad).float()
     return TF.conv2d(xin, w16.float(), None, stride, pad)
 
 
@@ -79,8 +90,9 @@ def _add_stats(stats, y, Cout, at=0):
     """stats: [rows, 2 * SC] (the stand-in uses ONE zero-initialised row) or [2 * SC]"""
     row = stats[0] if stats.dim() == 2 else stats
     SC = row.numel() // 2
-    row[at:at + Cout] += y.sum((0, 2, 3))
-    row[SC + at:SC + at + Cout] += (y * y).sum((0, 2, 3))
+    yd = y.double()
+    row[at:at + Cout] += yd.sum((0, 2, 3)).float()
+    row[SC + at:SC + at + Cout] += (yd * yd).sum((0, 2, 3)).float()
 
 
 def conv_stats_buffer(x, Cout, ksize, stride, pad, off=(0, 0), total_C=None, force_direct=False):
@@ -211,7 +223,7 @@ def _dz_xhat(dy, y, raw, mean, invstd, relu):
 def bn_bwd_sums(dy, y, raw, mean, invstd, relu):
     nhwc_info(dy)
     dz, xhat = _dz_xhat(dy, y, raw, mean, invstd, relu)
-    return torch.cat([dz.sum((0, 2, 3)), (dz * xhat).sum((0, 2, 3))])
+    return torch.cat([dz.double().sum((0, 2, 3)), (dz.double() * xhat.double()).sum((0, 2, 3))]).float()
 
 
 def bn_bwd_apply(dy, y, raw, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads=True):
@@ -230,8 +242,8 @@ def relu_bwd(dy, y):
     return _put(_empty(N, Cc, H, W, dy.device), dy.float() * (y.float() > 0))
 
 
-def pack_conv_weight_dgrad(w, Cin, Cout, ksize):
-    return w[:Cout, :Cin].detach().half().contiguous()
+def pack_conv_weight_dgrad(w, Cin, Cout, ksize, out=None):
+    return pack_conv_weight(w, Cin, Cout, ksize, out=out)
 
 
 def conv_dgrad(dy, w, x_shape, Cin, Cout, ksize, stride, pad, off=(0, 0), wpacked_t=None, force_direct=False):
@@ -239,7 +251,10 @@ def conv_dgrad(dy, w, x_shape, Cin, Cout, ksize, stride, pad, off=(0, 0), wpacke
     nhwc_info(dy)
     w16 = w[:Cout, :Cin].detach().half().float()
     eff = (N, Cin, H - off[0], W - off[1])
-    g = torch.nn.grad.conv2d_input(eff, w16, dy.float(), stride=stride, padding=pad)
+    if PRECISE["on"]:
+        g = torch.nn.grad.conv2d_input(eff, w16.double(), dy.double(), stride=stride, padding=pad).float()
+    else:
+        g = torch.nn.grad.conv2d_input(eff, w16, dy.float(), stride=stride, padding=pad)
     full = torch.zeros((N, Cin, H, W), dtype=torch.float32)
     full[:, :, off[0]:, off[1]:] = g
     return _put(_empty(N, Cin, H, W, dy.device), full)
@@ -247,7 +262,10 @@ def conv_dgrad(dy, w, x_shape, Cin, Cout, ksize, stride, pad, off=(0, 0), wpacke
 
 def conv_wgrad(x, dy, w_like, Cin, Cout, ksize, stride, pad, gscale, off=(0, 0), accumulate_into=None, force_direct=False):
     xin = x[:, :, off[0]:, off[1]:].float()
-    g = torch.nn.grad.conv2d_weight(xin, (Cout, Cin, ksize, ksize), dy.float(), stride=stride, padding=pad) / gscale
+    if PRECISE["on"]:
+        g = (torch.nn.grad.conv2d_weight(xin.double(), (Cout, Cin, ksize, ksize), dy.double(), stride=stride, padding=pad) / gscale).float()
+    else:
+        g = torch.nn.grad.conv2d_weight(xin, (Cout, Cin, ksize, ksize), dy.float(), stride=stride, padding=pad) / gscale
     if accumulate_into is not None:
         assert accumulate_into.dtype == torch.float32 and accumulate_into.shape == w_like.shape
         with torch.no_grad():
@@ -333,10 +351,98 @@ def conv_bn_act_train_bwd(d, x, dy, y, raw, vec, gamma, relu, wpacked_t, w, need
     return dx, dg, db
 
 
+# ---- device-selected BatchNorm sets (engine.SelBN): the stand-in reads the width index from the context's vector ----------
+def _sel_bn(sel):
+    return sel.bns[int(sel.ctx.width_idx[sel.slot])]
+
+
+def _split_perm(h, hmax):
+    """compact channel -> raw channel of a FactorizedReduce at maximum width (csrc/bn.cu split_remap)"""
+    def remap(c):
+        if c < h:
+            return c
+        if c < 2 * h:
+            return hmax + (c - h)
+        k = c - 2 * h
+        return h + k if k < hmax - h else hmax + h + (k - (hmax - h))
+    return torch.tensor([remap(c) for c in range(2 * hmax)], dtype=torch.long)
+
+
+def _pad(v, C):
+    out = torch.zeros(C, dtype=torch.float32)
+    out[:v.numel()] = v
+    return out
+
+
+def bn_finalize_sel(stats, count, sel, hmax=0):
+    bn = _sel_bn(sel)
+    Ca, Cc = bn.num_features, stats.shape[1] // 2
+    tot = stats.double().sum(0).float()
+    s, q = tot[:Cc], tot[Cc:]
+    if hmax:
+        perm = _split_perm(Ca // 2, hmax)
+        s, q = s[perm], q[perm]
+    scale, shift, mean, invstd = bn_finalize(torch.cat([s[:Ca], q[:Ca]]), count, bn.weight, bn.bias, sel.eps, sel.momentum,
+                                             bn.running_mean, bn.running_var, True)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return _pad(scale, Cc), _pad(shift, Cc), _pad(mean, Cc), _pad(invstd, Cc)
+
+
+def affine_act_sel(x, scale, shift, sel, hmax, relu=False):
+    if hmax:
+        perm = _split_perm(_sel_bn(sel).num_features // 2, hmax)
+        xc = _put(_empty(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device, dtype=x.dtype), x[:, perm].float())
+        return affine_act(xc, scale, shift, relu=relu)
+    return affine_act(x, scale, shift, relu=relu)
+
+
+def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0):
+    bn = _sel_bn(sel)
+    Ca, Cc = bn.num_features, dy.shape[1]
+    perm = _split_perm(Ca // 2, hmax) if hmax else None
+    rawc = raw if perm is None else raw[:, perm]
+    sums = bn_bwd_sums(dy, y, rawc, mean, invstd, relu)
+    gamma = _pad(bn.weight.detach().float(), Cc)
+    draw, _, _ = bn_bwd_apply(dy, y, rawc, mean, invstd, gamma, sums, count, relu, gscale, want_param_grads=False)
+    with torch.no_grad():
+        sel.ctx.flat.sview(bn.weight).add_(sums[Cc:Cc + Ca] / gscale)
+        sel.ctx.flat.sview(bn.bias).add_(sums[:Ca] / gscale)
+    if perm is None:
+        return draw
+    out = _empty(dy.shape[0], Cc, dy.shape[2], dy.shape[3], dy.device)
+    out[:, perm] = draw
+    return out
+
+
+def conv_bn_act_train_fwd_sel(x, wpacked, Cout, ksize, stride, pad, off, sel, relu):
+    N, Cin, H, W, xcs = nhwc_info(x)
+    Ho, Wo = F_.conv_out_size(H, W, ksize, stride, pad, 1, off[0], off[1])
+    stats = torch.zeros((1, 2 * Cout), dtype=torch.float32)
+    raw = conv_fwd(x, wpacked, Cout, ksize, stride, pad, off=off, stats=stats, out_f32=True)
+    scale, shift, mean, invstd = bn_finalize_sel(stats, N * Ho * Wo, sel)
+    y = affine_act(raw, scale, shift, relu=relu)
+    cpad = (Cout + 7) // 8 * 8
+    d = ConvDesc(N, H, W, Cin, Cout, ksize, stride, pad, 1, off[0], off[1], Ho, Wo, xcs, cpad, 0)
+    return y, raw, (mean, invstd), d
+
+
+def conv_bn_act_train_bwd_sel(d, x, dy, y, raw, vec, sel, relu, wpacked_t, w, need_dx, dw_accum, gscale):
+    N, Cout, Ho, Wo, _ = nhwc_info(dy)
+    mean, invstd = vec
+    draw = bn_bwd_sel(dy, y, raw, mean, invstd, N * Ho * Wo, relu, gscale, sel)
+    off = (d.off_h, d.off_w)
+    dx = conv_dgrad(draw, w, (N, d.Cin, d.H, d.W), d.Cin, Cout, d.ksize, d.stride, d.pad, off=off) if need_dx else None
+    if dw_accum is not None:
+        conv_wgrad(x, draw, w, d.Cin, Cout, d.ksize, d.stride, d.pad, gscale, off=off, accumulate_into=dw_accum)
+    return dx
+
+
 _PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold", "conv_stats_buffer", "rowsum", "conv_fwd", "stem_conv_nchw", "bilinear",
             "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd_sums", "bn_bwd_apply", "relu_bwd",
             "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
-            "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd")
+            "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd",
+            "bn_finalize_sel", "affine_act_sel", "bn_bwd_sel", "conv_bn_act_train_fwd_sel", "conv_bn_act_train_bwd_sel")
 
 
 @contextlib.contextmanager

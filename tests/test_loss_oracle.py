@@ -36,3 +36,30 @@ def test_distillation_kl_matches_reference(name):
     assert float(loss) == pytest.approx(float(Z[name + "/loss"][0]), rel=1e-5)
     loss.backward()
     np.testing.assert_allclose(student.grad.numpy()[:, :, ::4, ::4], Z[name + "/grad.s4"], rtol=1e-4, atol=1e-10)
+
+
+# ---- the product's own criteria (fasterseg_b200/losses.py, sync-free restatement) against the same reference goldens ----------
+@pytest.mark.parametrize("name", sorted(mk.OHEM_CASES))
+def test_product_ohem_matches_reference(name):
+    from fasterseg_b200.losses import ProbOhemCrossEntropy2d
+    pred, tgt, thresh, min_kept = mk.ohem_inputs(name)
+    pred.requires_grad_(True)
+    loss = ProbOhemCrossEntropy2d(ignore_label=255, thresh=thresh, min_kept=min_kept)(pred, tgt)
+    want = float(Z[name + "/loss"][0])
+    if math.isnan(want):
+        assert math.isnan(float(loss))
+        return
+    assert float(loss) == pytest.approx(want, rel=1e-6)
+    loss.backward()
+    np.testing.assert_allclose(pred.grad.numpy()[:, :, ::4, ::4], Z[name + "/grad.s4"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", sorted(mk.KL_CASES))
+def test_product_distillation_kl_matches_reference(name):
+    from fasterseg_b200.losses import distillation_kl
+    student, teacher = mk.kl_inputs(name)
+    student.requires_grad_(True)
+    loss = distillation_kl(student, teacher)
+    assert float(loss) == pytest.approx(float(Z[name + "/loss"][0]), rel=1e-5)
+    loss.backward()
+    np.testing.assert_allclose(student.grad.numpy()[:, :, ::4, ::4], Z[name + "/grad.s4"], rtol=1e-4, atol=1e-10)

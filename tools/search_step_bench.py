@@ -26,8 +26,14 @@ from fasterseg_b200.model_search import Network_Multi_Path  # noqa: E402
 WML = [4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.]
 
 
-def build(layers):
-    crit = nn.CrossEntropyLoss(ignore_index=255)
+def build(layers, criterion="ohem"):
+    # the reference's search criterion: ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept = batch * H * W / 8^2 / 16
+    # (search/train_search.py:104-105 with config_search.py:47,84-86); "ce" = plain cross entropy (round-1 numbers)
+    if criterion == "ohem":
+        from fasterseg_b200.losses import ProbOhemCrossEntropy2d
+        crit = None   # needs the batch geometry: set by measure()
+    else:
+        crit = nn.CrossEntropyLoss(ignore_index=255)
     m = Network_Multi_Path(19, layers, crit, Fch=12, width_mult_list=WML, prun_modes=['max', 'arch_ratio'],
                            stem_head_width=[(1, 1), (8. / 12, 8. / 12)])
     synth_weights_(m)
@@ -45,15 +51,18 @@ def weight_params(m):
     return ps
 
 
-def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape=None):
+def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape=None, graph=None, criterion="ohem"):
     """Time `steps` optimizer steps; returns the result dict (identical on every rank).
-    tape: None = whatever FSB_TAPE says; True / False = force the experimental one-node-per-forward autograd mode."""
+    tape: None = whatever FSB_TAPE says; True / False = force the one-node-per-forward autograd mode of the EAGER path.
+    graph: None = default (captured passes, fasterseg_b200/graphed.py); False = eager per-unit path."""
     from fasterseg_b200 import autograd as AG
     if tape is not None:
         AG.TAPE_ENABLED = bool(tape)
     args = argparse.Namespace(mode=mode, layers=layers, steps=steps, warmup=warmup)
     parallel.seed_all_ranks_identically(12345)   # identical weights + lock-step width sampling / gumbel noise on every rank
-    model = build(args.layers)
+    model = build(args.layers, criterion)
+    if graph is not None:
+        model.__dict__["_fsb_graph_mode"] = None if graph else False
     params = weight_params(model)
     opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=5e-4)
     arch_opts = [torch.optim.Adam(ps, lr=3e-4, betas=(0.5, 0.999)) for ps in model._arch_parameters]
@@ -66,6 +75,9 @@ def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape
     t = torch.randint(0, 19, (B, H // 8, W // 8), generator=g)
     t[torch.rand(t.shape, generator=g) < 0.05] = 255
     t = t.cuda()
+    if criterion == "ohem":
+        from fasterseg_b200.losses import ProbOhemCrossEntropy2d
+        model._criterion = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=int(B * (H // 8) * (W // 8) // 16))
     sync = parallel.GradSync(list(model.parameters())).install() if world > 1 else None
 
     def step():
@@ -101,7 +113,8 @@ def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape
         sync.uninstall()
     return {"metric": "supernet_%s_step_ms" % args.mode, "value": round(dt * 1e3, 1), "min_ms": round(tmin * 1e3, 1),
             "max_ms": round(tmax * 1e3, 1), "unit": "ms/step", "n_gpus": world, "layers": args.layers, "steps": args.steps,
-            "warmup": args.warmup, "autograd": "tape" if AG.TAPE_ENABLED else "per-unit", "batch_per_gpu": [B, 3, H, W], "images_per_s": round(B * world / dt, 2),
+            "warmup": args.warmup, "criterion": criterion,
+            "autograd": "captured passes (CUDA graphs)" if model.__dict__.get("_fsb_graph_runner") is not None else ("tape" if AG.TAPE_ENABLED else "per-unit"), "batch_per_gpu": [B, 3, H, W], "images_per_s": round(B * world / dt, 2),
             "grad_syncs": sync.syncs if sync else 0, "loss": float(loss.detach()),
             "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
             "mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
@@ -113,10 +126,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--mode", default="pretrain", choices=["pretrain", "search"])
+    ap.add_argument("--graph", type=int, default=1, help="1 = captured passes (default), 0 = eager per-unit path")
+    ap.add_argument("--criterion", default="ohem", choices=["ohem", "ce"])
     args = ap.parse_args()
     rank, local_rank, world = parallel.init_from_env()
     torch.cuda.set_device(local_rank)
-    res = measure(args.mode, args.layers, args.steps, args.warmup, rank, world)
+    res = measure(args.mode, args.layers, args.steps, args.warmup, rank, world, graph=bool(args.graph), criterion=args.criterion)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
