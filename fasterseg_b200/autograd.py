@@ -57,10 +57,14 @@ class _NodeCtx:
 
 
 class Tape:
-    def __init__(self):
-        self.nodes = []        # (Function class, ctx, args, output) in execution order
+    def __init__(self, streams=False):
+        self.nodes = []        # (Function class, ctx, args, output, stream) in execution order
         self.tracked = set()   # ids of tape-produced tensors that need a gradient
         self.keep = []         # every tape-produced tensor stays alive until backward, so ids are unique
+        # streams=True (captured passes, graphed.py): every node remembers the CUDA stream it ran on; the backward replay runs
+        # each node's backward on that stream and orders streams with events along the gradient data flow, so the independent
+        # ops of a MixedOp / Cell overlap in both directions
+        self.streams = streams
 
     def needs(self, t):
         return isinstance(t, torch.Tensor) and (t.requires_grad or id(t) in self.tracked)
@@ -77,16 +81,72 @@ class Tape:
             torch._C._set_grad_enabled(prev)
         if any(ctx.needs_input_grad):
             self.tracked.add(id(out))
-            self.nodes.append((fn, ctx, args, out))
+            self.nodes.append((fn, ctx, args, out, torch.cuda.current_stream() if self.streams else None))
         self.keep.append(out)
         return out
+
+    def _backward_streams(self, out_grads):
+        """`backward` with every node on the stream of its forward.  A gradient tensor becomes visible to other streams through
+        the event recorded after the node that (last) wrote it; gradients are kept alive until the end so that the caching
+        allocator never hands a block to one stream while another still reads it."""
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        ready, keep, used = {}, [], {}
+        grads = dict(out_grads)
+        leaves = {}
+        for fn, ctx, args, out, s in reversed(self.nodes):
+            g = grads.pop(id(out), None)
+            if g is None:
+                continue
+            s.wait_event(ready.get(id(g), start))
+            used[id(s)] = s
+            with torch.cuda.stream(s):
+                res = fn.backward(ctx, g)
+                if not isinstance(res, tuple):
+                    res = (res,)
+                wrote = []
+                for a, need, ga in zip(args, ctx.needs_input_grad, res):
+                    if ga is None or not need:
+                        continue
+                    key = id(a)
+                    if key in self.tracked:
+                        have = grads.get(key)
+                        if have is None:
+                            grads[key] = ga
+                        else:
+                            s.wait_event(ready.get(id(have), start))
+                            F_.add_inplace(ga, have)
+                        wrote.append(grads[key])
+                    else:
+                        have = leaves.get(key)
+                        if have is None:
+                            leaves[key] = (a, ga)
+                        else:
+                            s.wait_event(ready.get(id(have[1]), start))
+                            leaves[key] = (a, have[1] + ga)
+                        wrote.append(leaves[key][1])
+                done = torch.cuda.Event()
+                done.record(s)
+            for t in wrote:
+                ready[id(t)] = done
+            keep.append(g)
+            keep.extend(r for r in res if r is not None)
+        for s in used.values():      # join: everything (incl. gradients accumulated in place by the kernels) is done
+            e = torch.cuda.Event()
+            e.record(s)
+            main.wait_event(e)
+        self._bwd_keep = keep
+        return leaves
 
     def backward(self, out_grads):
         """out_grads: {id(output tensor): gradient}.  Returns {id: (leaf tensor, gradient)} for everything that is not a
         tape intermediate: parameters and tensors of the surrounding torch autograd graph (the scalar plumbing)."""
+        if self.streams:
+            return self._backward_streams(out_grads)
         grads = dict(out_grads)
         leaves = {}
-        for fn, ctx, args, out in reversed(self.nodes):
+        for fn, ctx, args, out, _ in reversed(self.nodes):
             g = grads.pop(id(out), None)
             if g is None:
                 continue

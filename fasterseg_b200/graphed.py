@@ -131,6 +131,10 @@ class PassContext:
         self._packs, self._pack_list = {}, []
         self._sel, self._sel_tables = {}, {}
         self.static_touched = {}               # id -> Parameter staged by this context outside device-selected sets
+        # independent ops of a MixedOp / the two MixedOps of a Cell run on side streams (GPU only): the pass is a chain of ~8 000
+        # kernels that each occupy a fraction of the machine for a few microseconds
+        self.use_streams = self.dev.type == "cuda" and os.environ.get("FSB_GRAPH_STREAMS", "1") != "0"
+        self._streams, self._stream_cursor, self._par_depth = [], 0, 0
         self.built = False
         self.graphs = None
         self._pack_versions = None
@@ -214,10 +218,42 @@ class PassContext:
         assert self._bmeta[i] == meta
         return self._bslots[i]
 
+    def parallel(self, thunks):
+        """run independent pieces of the pass concurrently: thunk i on side stream (cursor + i), forked from and joined to the
+        current stream with events.  The stream assignment depends only on the call structure, so the same module always runs
+        on the same stream (twice-invoked cells update their BatchNorm statistics and weight gradients in program order)."""
+        if not self.use_streams or len(thunks) < 2:
+            return [t() for t in thunks]
+        base = self._stream_cursor
+        while len(self._streams) < base + len(thunks):
+            self._streams.append(torch.cuda.Stream(device=self.dev))
+        self._stream_cursor = base + len(thunks)
+        self._par_depth += 1
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        outs, joins = [], []
+        try:
+            for i, t in enumerate(thunks):
+                s = self._streams[base + i]
+                s.wait_event(fork)
+                with torch.cuda.stream(s):
+                    outs.append(t())
+                    e = torch.cuda.Event()
+                    e.record(s)
+                    joins.append(e)
+        finally:
+            self._par_depth -= 1
+            if self._par_depth == 0:
+                self._stream_cursor = 0
+        for e in joins:
+            main.wait_event(e)
+        return outs
+
     # ---- one planned forward + backward on the tape ------------------------------------------------------------------
     def _run_forward(self):
         self._wcount = self._bcount = 0
-        tape = AG.Tape()
+        tape = AG.Tape(streams=self.use_streams)
         prev_tape, prev_ctx = AG._TAPE, engine._GRAPH_CTX
         AG._TAPE, engine._GRAPH_CTX = tape, self
         try:

@@ -107,8 +107,15 @@ class MixedOp(nn.Module):
 
     def forward(self, x, weights, ratios):
         # a ratio is a tensor (searched width distribution) or a float (forced width)
-        wvec = self._scaled_weights(weights, ratios)
-        outs = [F_.to_nhwc_half(op(x)) for op in self._ops]
+        return self._mix(x, self._scaled_weights(weights, ratios))
+
+    def _mix(self, x, wvec):
+        """sum_k wvec[k] * op_k(x) at the widths `_scaled_weights` just configured"""
+        ctx = engine.graph_ctx()
+        if ctx is not None:     # captured pass: the five primitives are independent chains of small kernels -> side streams
+            outs = ctx.parallel([(lambda op=op: F_.to_nhwc_half(op(x))) for op in self._ops])
+        else:
+            outs = [F_.to_nhwc_half(op(x)) for op in self._ops]
         if _needs_graph(wvec, *outs):
             return AG.weighted_sum(wvec, outs)
         return F_.wsum_fwd(outs, wvec.detach().float().contiguous())
@@ -136,6 +143,13 @@ class Cell(nn.Module):
     def _both(self, method, x, alphas, ratios):
         """(keep, down) through `method` of the two MixedOps; ratios = (in, out, down) and `down` is None iff no down path"""
         assert (ratios[2] is not None) == bool(self._down)
+        ctx = engine.graph_ctx() if method == "forward" else None
+        if ctx is not None and self._down:     # captured pass: the two MixedOps read the same x and are independent
+            # (the mixing-weight slots are taken in program order BEFORE forking, so slot numbering stays deterministic)
+            w_keep = self._op._scaled_weights(alphas, (ratios[0], ratios[1]))
+            w_down = self.downsample._scaled_weights(alphas, (ratios[0], ratios[2]))
+            keep, down = ctx.parallel([lambda: self._op._mix(x, w_keep), lambda: self.downsample._mix(x, w_down)])
+            return keep, down
         keep = getattr(self._op, method)(x, alphas, (ratios[0], ratios[1]))
         down = getattr(self.downsample, method)(x, alphas, (ratios[0], ratios[2])) if self._down else None
         return keep, down
