@@ -42,6 +42,7 @@ _SIGS = {
     "fsb_set_pdl": (C.c_int, [C.c_int]),
     "fsb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "fsb_get_option": (C.c_int, [C.c_char_p]),
+    "fsb_conv_kernel_id": (C.c_int, [C.POINTER(ConvDesc), _P, C.c_int]),
     "fsb_conv_stats_rows": (C.c_int, [C.POINTER(ConvDesc)]),
     "fsb_stat_rows": (C.c_int, [C.c_int64]),
     "fsb_wsum_rows": (C.c_int, [C.c_int64, C.c_int]),
@@ -52,6 +53,8 @@ _SIGS = {
     "fsb_bn_fold": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
     "fsb_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P]),
     "fsb_stem_conv_nchw": (C.c_int, [C.c_int] * 4 + [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_uint32, _P]),
+    "fsb_stem_conv_u8hwc": (C.c_int, [C.c_int] * 4 + [_P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, _P]),
+    "fsb_confusion_matrix": (C.c_int, [C.c_int64, _P, _P, C.c_int, C.c_int, _P, _P]),
     "fsb_bilinear_fwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, C.c_uint32, _P]),
     "fsb_upsample_logits_nchw": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, _P]),
     "fsb_upsample_argmax": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, _P]),

@@ -96,6 +96,9 @@ PFN_encodeTiled get_encode_tiled() {
 int pack_conv_weight(const fsb_conv_desc*, const float*, int64_t, int64_t, void*, cudaStream_t);
 int stem_conv_nchw_launch(int, int, int, int, const void*, int, const float*, const float*, const float*, void*, int, uint32_t,
                           cudaStream_t);
+int stem_conv_u8hwc_launch(int, int, int, int, const uint8_t*, const void*, const float*, const float*, const float*, void*, int, uint32_t,
+                           cudaStream_t);
+int confusion_launch(int64_t, const uint8_t*, const void*, int, int, long long*, cudaStream_t);
 int bilinear_launch(int, int, int, int, int, int, const void*, int, void*, int, uint32_t, cudaStream_t);
 int upsample_logits_launch(int, int, int, int, int, int, const void*, int, void*, int, cudaStream_t);
 int upsample_argmax_launch(int, int, int, int, int, int, const void*, int, uint8_t*, cudaStream_t);
@@ -191,6 +194,13 @@ int fsb_conv_stats_rows(const fsb_conv_desc* d) {
   if (conv_tc2_supported(d)) return conv_tc2_ctas(d);
   return conv_tc_m_tiles(d);
 }
+int fsb_conv_kernel_id(const fsb_conv_desc* d, const void* y, int with_stats) {
+  if (check_desc(d)) return -1;
+  if ((d->flags & FSB_CONV_FORCE_DIRECT) || !conv_tc_supported(d)) return 0;
+  if (!with_stats && conv_tc3_supported(d, y)) return 3;
+  if (conv_tc2_supported(d)) return 2;
+  return 1;
+}
 int fsb_stat_rows(int64_t pixels) { return stat_rows(pixels); }
 int fsb_wsum_rows(int64_t pixels, int C) { return wsum_rows(pixels, C); }
 int fsb_rowsum(int L, const float* src, int rows, int stride, float* out, void* stream) {
@@ -248,6 +258,17 @@ int fsb_stem_conv_nchw(int N, int H, int W, int Cout, const void* x, int x_is_f3
   if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0 || !x || !w || !y || y_cstride < Cout)
     return set_error(FSB_ERR_INVALID, "stem_conv_nchw: bad argument");
   return stem_conv_nchw_launch(N, H, W, Cout, x, x_is_f32, w, scale, shift, y, y_cstride, flags, static_cast<cudaStream_t>(stream));
+}
+
+int fsb_stem_conv_u8hwc(int N, int H, int W, int Cout, const uint8_t* x, const void* lut_f16, const float* w, const float* scale,
+                        const float* shift, void* y, int y_cstride, uint32_t flags, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0 || !x || !lut_f16 || !w || !y || y_cstride < Cout)
+    return set_error(FSB_ERR_INVALID, "stem_conv_u8hwc: bad argument");
+  return stem_conv_u8hwc_launch(N, H, W, Cout, x, lut_f16, w, scale, shift, y, y_cstride, flags, static_cast<cudaStream_t>(stream));
+}
+int fsb_confusion_matrix(int64_t n, const uint8_t* pred, const void* gt, int gt_bytes, int n_cl, long long* out, void* stream) {
+  if (n <= 0 || !pred || !gt || !out) return set_error(FSB_ERR_INVALID, "confusion_matrix: bad argument");
+  return confusion_launch(n, pred, gt, gt_bytes, n_cl, out, static_cast<cudaStream_t>(stream));
 }
 
 int fsb_bilinear_fwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* x, int xcs, void* y, int ycs, uint32_t flags,

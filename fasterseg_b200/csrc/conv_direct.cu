@@ -5,6 +5,8 @@
 //   * stem_conv_nchw_kernel   : 3x3 s2 p1 RGB stem reading the caller's NCHW fp32/fp16 tensor directly, so the
 //                               NCHW->NHWC layout change and the fp32->fp16 cast cost no extra HBM round trip
 //                               (ConvNorm at train/model_seg.py:193, search/model_search.py:148)
+#include <type_traits>
+
 #include "fsb_common.cuh"
 #include "fsb_internal.h"
 
@@ -229,12 +231,17 @@ stem_conv_nchw_kernel(int N, int H, int W, int Cout, const TIn* __restrict__ x, 
 // tile in TMEM; the epilogue applies BN scale/shift + ReLU and each thread stores its pixel's Cout fp16 values
 // contiguously (a warp writes 32 x 2*Cout contiguous bytes).  No im2col buffer, no fp16 NHWC copy of the image.
 // ------------------------------------------------------------------------------------------
+// TIn = uint8_t: the frame is the camera / dataset image itself, uint8 HWC (tools/engine/evaluator.py:206-225 hands the model
+// `normalize(img, mean, std)` = (img / 255 - mean) / std as fp32 CHW, evaluator.py:329, tools/utils/img_utils.py:179-185).  The
+// normalisation is a 3 x 256 lookup table of fp16 values (exactly the fp16 rounding of what the reference computes for each
+// byte value), so the H2D copy shrinks 4x and the result is bit-identical to feeding the normalised fp32 image.
 template <typename TIn>
 __global__ void __launch_bounds__(128)
 stem_conv_tc_kernel(int N, int H, int W, int Cout, int npad, const TIn* __restrict__ x, const float* __restrict__ w,
                     const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ y,
-                    int y_cstride, uint32_t flags, uint32_t tmem_cols) {
+                    int y_cstride, uint32_t flags, uint32_t tmem_cols, const __half* __restrict__ lut) {
   __shared__ __align__(1024) uint8_t s_a[128 * 64];
+  __shared__ __half s_lut[std::is_same<TIn, uint8_t>::value ? 768 : 2];
   __shared__ __align__(1024) uint8_t s_b[64 * 64];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
@@ -256,6 +263,10 @@ stem_conv_tc_kernel(int N, int H, int W, int Cout, int npad, const TIn* __restri
     tmem_relinquish();
   }
   pdl_wait();  // weights / scale / shift may have been produced by the immediately preceding kernel
+  if constexpr (std::is_same<TIn, uint8_t>::value) {
+    for (int i = t; i < 768; i += 128) s_lut[i] = lut[i];
+    __syncthreads();
+  }
   // weights -> B tile rows (one thread per output channel), fp32 OIHW is already [co][27]
   if (t < npad) {
     __half hv[32];
@@ -282,9 +293,16 @@ stem_conv_tc_kernel(int N, int H, int W, int Cout, int npad, const TIn* __restri
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           const int wi = wo * 2 + s - 1;
-          float v = 0.f;
-          if (hok && wi >= 0 && wi < W) v = static_cast<float>(x[(static_cast<size_t>(n) * 3 + ci) * plane + static_cast<size_t>(hi) * W + wi]);
-          hv[ci * 9 + r * 3 + s] = __float2half_rn(v);
+          if constexpr (std::is_same<TIn, uint8_t>::value) {
+            __half hvv = __float2half_rn(0.f);   // zero padding of the NORMALISED image, like the reference's conv
+            if (hok && wi >= 0 && wi < W)
+              hvv = s_lut[ci * 256 + x[((static_cast<size_t>(n) * H + hi) * W + wi) * 3 + ci]];
+            hv[ci * 9 + r * 3 + s] = hvv;
+          } else {
+            float v = 0.f;
+            if (hok && wi >= 0 && wi < W) v = static_cast<float>(x[(static_cast<size_t>(n) * 3 + ci) * plane + static_cast<size_t>(hi) * W + wi]);
+            hv[ci * 9 + r * 3 + s] = __float2half_rn(v);
+          }
         }
       }
     }
@@ -360,10 +378,10 @@ int stem_conv_nchw_launch(int N, int H, int W, int Cout, const void* x, int x_is
     const uint32_t cols = cpad <= 32 ? 32u : 64u;
     if (x_is_f32)
       FSB_LAUNCH(stem_conv_tc_kernel<float>, grid_tc, dim3(128), 0, stream, N, H, W, Cout, cpad, static_cast<const float*>(x), w,
-                 scale, shift, static_cast<__half*>(y), y_cstride, flags, cols);
+                 scale, shift, static_cast<__half*>(y), y_cstride, flags, cols, static_cast<const __half*>(nullptr));
     else
       FSB_LAUNCH(stem_conv_tc_kernel<__half>, grid_tc, dim3(128), 0, stream, N, H, W, Cout, cpad, static_cast<const __half*>(x), w,
-                 scale, shift, static_cast<__half*>(y), y_cstride, flags, cols);
+                 scale, shift, static_cast<__half*>(y), y_cstride, flags, cols, static_cast<const __half*>(nullptr));
     cudaError_t e2 = last_launch_error();
     if (e2 != cudaSuccess) return set_cuda_error(e2, "stem_conv_tc launch");
     return FSB_OK;
@@ -380,6 +398,66 @@ int stem_conv_nchw_launch(int N, int H, int W, int Cout, const void* x, int x_is
                                                                  shift, static_cast<__half*>(y), y_cstride, flags);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "stem_conv_nchw launch");
+  return FSB_OK;
+}
+
+int stem_conv_u8hwc_launch(int N, int H, int W, int Cout, const uint8_t* x, const void* lut, const float* w, const float* scale,
+                           const float* shift, void* y, int y_cstride, uint32_t flags, cudaStream_t stream) {
+  const int Ho = H / 2 + (H & 1), Wo = W / 2 + (W & 1);
+  const int cpad = (Cout + 15) / 16 * 16;
+  if (cpad > 64) return set_error(FSB_ERR_UNSUPPORTED, "stem_conv_u8hwc: Cout <= 64");
+  dim3 grid_tc((Wo + 127) / 128, Ho, N);
+  const uint32_t cols = cpad <= 32 ? 32u : 64u;
+  FSB_LAUNCH(stem_conv_tc_kernel<uint8_t>, grid_tc, dim3(128), 0, stream, N, H, W, Cout, cpad, x, w, scale, shift,
+             static_cast<__half*>(y), y_cstride, flags, cols, static_cast<const __half*>(lut));
+  cudaError_t e = last_launch_error();
+  if (e != cudaSuccess) return set_cuda_error(e, "stem_conv_u8hwc launch");
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// confusion matrix of a predicted label map against the ground truth (tools/seg_opr/metric.py:7-15 hist_info):
+//   k = (gt >= 0) & (gt < n_cl);  hist[n_cl * gt + pred] += 1 over k;  labeled = sum(k);  correct = sum(pred == gt over k)
+// per-block shared-memory histogram, then integer atomics (exact and order-independent).  out: int64 [n_cl * n_cl + 2].
+// ------------------------------------------------------------------------------------------
+template <typename TGt>
+__global__ void __launch_bounds__(256)
+confusion_kernel(int64_t n, const uint8_t* __restrict__ pred, const TGt* __restrict__ gt, int n_cl, unsigned long long* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ unsigned int s_hist[];  // n_cl * n_cl + 2
+  const int cells = n_cl * n_cl + 2;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const long long g = static_cast<long long>(gt[i]);
+    if (g < 0 || g >= n_cl) continue;
+    const int p = pred[i];
+    if (p < n_cl) atomicAdd(&s_hist[g * n_cl + p], 1u);
+    atomicAdd(&s_hist[n_cl * n_cl], 1u);
+    if (p == g) atomicAdd(&s_hist[n_cl * n_cl + 1], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cells; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&out[i], static_cast<unsigned long long>(s_hist[i]));
+}
+int confusion_launch(int64_t n, const uint8_t* pred, const void* gt, int gt_bytes, int n_cl, long long* out, cudaStream_t stream) {
+  if (n_cl < 1 || n_cl > 64) return set_error(FSB_ERR_INVALID, "confusion_matrix: 1 <= n_cl <= 64");
+  int64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const size_t smem = static_cast<size_t>(n_cl * n_cl + 2) * sizeof(unsigned int);
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+  if (gt_bytes == 1)
+    FSB_LAUNCH(confusion_kernel<uint8_t>, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, stream, n, pred, static_cast<const uint8_t*>(gt), n_cl, o);
+  else if (gt_bytes == 4)
+    FSB_LAUNCH(confusion_kernel<int32_t>, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, stream, n, pred, static_cast<const int32_t*>(gt), n_cl, o);
+  else if (gt_bytes == 8)
+    FSB_LAUNCH(confusion_kernel<long long>, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, stream, n, pred, static_cast<const long long*>(gt), n_cl, o);
+  else
+    return set_error(FSB_ERR_INVALID, "confusion_matrix: ground truth must be uint8, int32 or int64");
+  cudaError_t e = last_launch_error();
+  if (e != cudaSuccess) return set_cuda_error(e, "confusion_matrix launch");
   return FSB_OK;
 }
 

@@ -201,6 +201,46 @@ def stem_conv_nchw(x, w, scale, shift, relu=True, out=None):
     return out
 
 
+def normalization_lut(mean, std, device):
+    """3 x 256 fp16 table: the normalised value of every byte per channel, computed like the reference does
+    (tools/utils/img_utils.py:179-185: float32 byte / 255.0, then float64 `- mean` and `/ std`, evaluator.py:329 casts the image
+    to float32) and rounded to fp16 once -- what the stem kernel would make of the normalised fp32 frame."""
+    import numpy as np
+    v = np.arange(256, dtype=np.uint8).astype(np.float32) / 255.0                     # float32, like img.astype(np.float32) / 255.0
+    table = (v[None, :] - np.asarray(mean, dtype=np.float64)[:, None]) / np.asarray(std, dtype=np.float64)[:, None]
+    return torch.from_numpy(table.astype(np.float32)).to(torch.float16).contiguous().to(device)
+
+
+def stem_conv_u8hwc(x_u8, lut, w, scale, shift, relu=True, out=None):
+    """3x3 s2 p1 RGB stem on a uint8 HWC frame given as a logical (N, 3, H, W) view of an (N, H, W, 3) buffer, normalisation
+    folded into the gather through `lut` (normalization_lut)."""
+    assert x_u8.dtype == torch.uint8 and x_u8.dim() == 4 and x_u8.shape[1] == 3 and _on_device(x_u8)
+    N, _, H, W = x_u8.shape
+    assert x_u8.stride() == (H * W * 3, 1, W * 3, 3), "expected the permute(0, 3, 1, 2) view of a contiguous (N, H, W, 3) uint8 frame"
+    assert lut.dtype == torch.float16 and lut.numel() == 768 and lut.is_contiguous()
+    assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (3, 3, 3)
+    Cout = w.shape[0]
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    if out is None:
+        out = empty_nhwc(N, Cout, Ho, Wo, x_u8.device)
+    _, _, _, _, ycs = nhwc_info(out)
+    flags = (FSB_CONV_RELU if relu else 0) | (FSB_CONV_AFFINE if scale is not None else 0)
+    check(_lib.lib().fsb_stem_conv_u8hwc(N, H, W, Cout, _ptr(x_u8), _ptr(lut), _ptr(w), _ptr(scale), _ptr(shift), _ptr(out), ycs, flags,
+                                         _stream()), "fsb_stem_conv_u8hwc")
+    return out
+
+
+def confusion_matrix(pred_u8, gt, n_cl, out=None):
+    """accumulate hist_info (tools/seg_opr/metric.py:7-15) of `pred_u8` vs `gt` into the int64 [n_cl^2 + 2] tensor `out`"""
+    assert pred_u8.dtype == torch.uint8 and pred_u8.is_contiguous() and gt.is_contiguous() and pred_u8.numel() == gt.numel()
+    assert gt.dtype in (torch.uint8, torch.int32, torch.int64)
+    if out is None:
+        out = torch.zeros(n_cl * n_cl + 2, device=pred_u8.device, dtype=torch.int64)
+    check(_lib.lib().fsb_confusion_matrix(pred_u8.numel(), _ptr(pred_u8), _ptr(gt), gt.element_size(), int(n_cl), _ptr(out), _stream()),
+          "fsb_confusion_matrix")
+    return out
+
+
 def bilinear(x, size, relu=False, out=None):
     N, Cc, Hi, Wi, xcs = nhwc_info(x)
     Ho, Wo = int(size[0]), int(size[1])

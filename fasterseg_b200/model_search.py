@@ -313,31 +313,43 @@ class Network_Multi_Path(nn.Module):
         else:
             ratios = plan.sym_ratios
 
-        prev, cur, at_layer = {0: (self.stem[idx](input), None)}, {}, 0
-        for node in self._nodes:
-            if node.layer != at_layer:
-                prev, cur, at_layer = cur, {}, node.layer
+        def run_cell(node, prev):
             cell = self.cells[node.layer][node.scale]
             arow = node.layer - node.scale
             alpha = alphas[node.scale][arow] if plan is None else plan.alpha(node.scale, arow)
             ratio = self._ratio_triple(node.layer, node.scale, ratios)
             if node.beta_row is None:
                 (src, port), = node.feeds
-                cur[node.scale] = cell(prev[src][port], alpha, ratio)
-            else:
-                # same weights, two inputs ("0: from down", then "1: from keep"); BN running stats see both, in this order
-                flags = alive[node.scale][node.beta_row] if plan is None else (True, True)   # softmax(beta) > 0 barring underflow
-                results = [cell(prev[src][port], alpha, ratio) if flags[n] else None for n, (src, port) in enumerate(node.feeds)]
-                brow = betas[node.scale][node.beta_row] if plan is None else plan.beta(node.scale, node.beta_row)
-                cur[node.scale] = _blend(brow, results)
+                return cell(prev[src][port], alpha, ratio)
+            # same weights, two inputs ("0: from down", then "1: from keep"); BN running stats see both, in this order
+            flags = alive[node.scale][node.beta_row] if plan is None else (True, True)   # softmax(beta) > 0 barring underflow
+            results = [cell(prev[src][port], alpha, ratio) if flags[n] else None for n, (src, port) in enumerate(node.feeds)]
+            brow = betas[node.scale][node.beta_row] if plan is None else plan.beta(node.scale, node.beta_row)
+            return _blend(brow, results)
+
+        def fan(thunks):
+            """independent pieces: on side streams in a captured pass, in order otherwise"""
+            return plan.parallel(thunks) if plan is not None else [t() for t in thunks]
+
+        cur = {0: (self.stem[idx](input), None)}
+        for layer in range(self._layers):
+            nodes = [n for n in self._nodes if n.layer == layer]      # the cells of a layer only read the previous layer
+            prev = cur
+            outs = fan([(lambda n=n, prev=prev: run_cell(n, prev)) for n in nodes])
+            cur = {n.scale: o for n, o in zip(nodes, outs)}
         f8, f16, f32 = (cur[s][KEEP] for s in range(3))
 
+        def chain16():
+            return refine16[1](_cat([_resize2x(refine16[0](f16)), f8]))
+
+        def chain32():
+            o = refine32[1](_cat([_resize2x(refine32[0](f32)), f16]))
+            return refine32[3](_cat([_resize2x(refine32[2](o)), f8]))
+
         out0 = f8
-        out1 = refine16[1](_cat([_resize2x(refine16[0](f16)), f8]))
-        out2 = refine32[1](_cat([_resize2x(refine32[0](f32)), f16]))
-        out2 = refine32[3](_cat([_resize2x(refine32[2](out2)), f8]))
-        preds = [self.head0[idx](out0), self.head1[idx](out1), self.head2[idx](out2),
-                 self.head02[idx](_cat([out0, out2])), self.head12[idx](_cat([out1, out2]))]
+        out1, out2 = fan([chain16, chain32])
+        preds = fan([lambda: self.head0[idx](out0), lambda: self.head1[idx](out1), lambda: self.head2[idx](out2),
+                     lambda: self.head02[idx](_cat([out0, out2])), lambda: self.head12[idx](_cat([out1, out2]))])
         leave = _to_nchw if self.training else _upsample8
         return tuple(leave(p) for p in preds)
 

@@ -330,6 +330,14 @@ class Network_Multi_Path_Infer(nn.Module):
             outs.append(pred)
         return tuple(outs)
 
+    def set_input_normalization(self, mean, std):
+        """Evaluator path (tools/engine/evaluator.py:206-225,329): after this the network also accepts the uint8 HWC image itself
+        -- `img_u8` of shape (N, H, W, 3), passed as `img_u8.permute(0, 3, 1, 2)` -- and applies (v / 255 - mean) / std inside the
+        stem kernel.  mean / std: per-channel sequences (config.image_mean / image_std)."""
+        stem0 = self.stem[0]
+        stem0.__dict__["_fsb_norm_lut"] = F_.normalization_lut(mean, std, next(self.parameters()).device)
+        stem0.__dict__["_fsb_norm"] = (tuple(float(m) for m in mean), tuple(float(s) for s in std))
+
     @torch.no_grad()
     def predict_labels(self, input, out=None):
         """argmax(forward(input), dim=1) as uint8, fused into the x8 upsample: the evaluator's

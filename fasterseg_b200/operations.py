@@ -157,6 +157,14 @@ class ConvNorm(_Primitive):
     def forward(self, x, out=None):
         assert x.size()[1] == self.C_in, "{} {}".format(x.size()[1], self.C_in)
         conv, bn = self.conv[0], self.conv[1]
+        if x.dtype == torch.uint8:
+            # the image itself (uint8 HWC behind a logical NCHW view): normalisation folded into the stem's gather (evaluator path)
+            lut = self.__dict__.get("_fsb_norm_lut")
+            assert lut is not None, "uint8 input needs set_input_normalization(mean, std) on the network"
+            assert self.C_in == 3 and self.kernel_size == 3 and self.stride == 2 and self.padding == 1 and not bn.training
+            scale, shift = engine.folded_bn(bn, self.C_out, None)
+            w = conv.weight.detach()
+            return F_.stem_conv_u8hwc(x, lut, w if w.dtype == torch.float32 else w.float(), scale, shift, relu=True, out=out)
         if (self.C_in == 3 and self.kernel_size == 3 and self.stride == 2 and self.padding == 1 and not self.slimmable
                 and not F_.is_nhwc_half(x) and not bn.training and conv.bias is None and x.is_contiguous()):
             # RGB stem straight from the caller's NCHW tensor (model_seg.py:193, model_search.py:148)

@@ -68,6 +68,8 @@ class GraphedInference:
 
     mode = "logits": output is the upsampled NCHW logits tensor (dtype `logits_dtype`)
     mode = "labels": output is the uint8 argmax label map (fused upsample+argmax)
+    The example input fixes the input format: an fp32 / fp16 NCHW frame, or -- after model.set_input_normalization(mean, std) --
+    the uint8 HWC image itself as `img_u8.permute(0, 3, 1, 2)` (evaluator path: 4x less host->device traffic).
     The input is read from `self.static_input`; `__call__(x)` first copies x into it (device->device or
     host->device on the current stream).
     """

@@ -131,6 +131,9 @@ int fsb_bn_fold(int C, const float* gamma, const float* beta, const float* mean,
  * NHWC tiles; Cin < 16 (the RGB stem) and FSB_CONV_FORCE_DIRECT use the CUDA-core direct kernel. */
 int fsb_conv_fwd(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                  void* y, float* stats, void* stream);
+/* which kernel fsb_conv_fwd dispatches for `d` (y: the output pointer, its alignment matters): 0 = CUDA-core direct, 1 = per-tap
+ * tcgen05 (conv_tc), 2 = row-strip (conv_tc2), 3 = channel-major 128x256 (conv_tc3); negative = invalid descriptor */
+int fsb_conv_kernel_id(const fsb_conv_desc* d, const void* y, int with_stats);
 /* number of partial statistic rows fsb_conv_fwd writes for `d` with FSB_CONV_STATS (depends on the kernel it dispatches):
  * stats must hold rows * 2 * SC floats; every row's entries of this conv's channels are written (no zeroing needed). */
 int fsb_conv_stats_rows(const fsb_conv_desc* d);
@@ -140,6 +143,17 @@ int fsb_conv_stats_rows(const fsb_conv_desc* d);
  * w: fp32 OIHW (read directly, no packing). */
 int fsb_stem_conv_nchw(int N, int H, int W, int Cout, const void* x_nchw, int x_is_f32, const float* w,
                        const float* scale, const float* shift, void* y, int y_cstride, uint32_t flags, void* stream);
+
+/* Same stem conv fed with the image itself: uint8 HWC frame [N, H, W, 3] (what the dataset / camera delivers) + a 3 x 256
+ * fp16 lookup table of the normalised value of every byte per channel ((v / 255 - mean[c]) / std[c],
+ * tools/utils/img_utils.py:179-185, applied at tools/engine/evaluator.py:329).  Zero padding applies to the NORMALISED image.
+ * Bit-identical to fsb_stem_conv_nchw on the normalised fp32 frame; the host->device copy is 4x smaller. */
+int fsb_stem_conv_u8hwc(int N, int H, int W, int Cout, const uint8_t* x_hwc, const void* lut_f16, const float* w,
+                        const float* scale, const float* shift, void* y, int y_cstride, uint32_t flags, void* stream);
+/* Evaluator's confusion matrix on the device (tools/seg_opr/metric.py:7-15 hist_info): for the n pixels with 0 <= gt < n_cl:
+ * out[n_cl * gt + pred] += 1, out[n_cl^2] += 1 (labeled), out[n_cl^2 + 1] += (pred == gt) (correct).  out: int64
+ * [n_cl * n_cl + 2], accumulated into (caller zeroes once per evaluation); gt: uint8 / int32 / int64 (gt_bytes = 1 / 4 / 8). */
+int fsb_confusion_matrix(int64_t n, const uint8_t* pred, const void* gt, int gt_bytes, int n_cl, long long* out, void* stream);
 
 /* --- resize / layout ------------------------------------------------------------------------ */
 /* F.interpolate(mode='bilinear', align_corners=True) on fp16 NHWC; call sites operations.py:271,275,437,444,

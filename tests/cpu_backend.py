@@ -138,6 +138,31 @@ def stem_conv_nchw(x, w, scale, shift, relu=True, out=None):
     return _put(out, y)
 
 
+def stem_conv_u8hwc(x_u8, lut, w, scale, shift, relu=True, out=None):
+    N, _, H, W = x_u8.shape
+    xn = torch.stack([lut.view(3, 256)[c][x_u8[:, c].long()] for c in range(3)], dim=1).float()   # fp16 table values
+    y = TF.conv2d(xn, w.half().float(), None, 2, 1)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if relu:
+        y = y.relu()
+    if out is None:
+        out = _empty(y.shape[0], y.shape[1], y.shape[2], y.shape[3], x_u8.device)
+    return _put(out, y)
+
+
+def confusion_matrix(pred_u8, gt, n_cl, out=None):
+    if out is None:
+        out = torch.zeros(n_cl * n_cl + 2, dtype=torch.int64)
+    g = gt.reshape(-1).long()
+    p = pred_u8.reshape(-1).long()
+    k = (g >= 0) & (g < n_cl)
+    out[:n_cl * n_cl] += torch.bincount(n_cl * g[k] + p[k], minlength=n_cl * n_cl)
+    out[n_cl * n_cl] += int(k.sum())
+    out[n_cl * n_cl + 1] += int((p[k] == g[k]).sum())
+    return out
+
+
 def _interp(x32, size):
     return TF.interpolate(x32, size=(int(size[0]), int(size[1])), mode="bilinear", align_corners=True)
 
@@ -442,7 +467,7 @@ _PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold
             "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd_sums", "bn_bwd_apply", "relu_bwd",
             "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
             "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd",
-            "bn_finalize_sel", "affine_act_sel", "bn_bwd_sel", "conv_bn_act_train_fwd_sel", "conv_bn_act_train_bwd_sel")
+            "stem_conv_u8hwc", "confusion_matrix", "bn_finalize_sel", "affine_act_sel", "bn_bwd_sel", "conv_bn_act_train_fwd_sel", "conv_bn_act_train_bwd_sel")
 
 
 @contextlib.contextmanager

@@ -235,3 +235,30 @@ def test_weight_and_bn_caches_follow_parameter_updates():
         # 3. load_state_dict back to the original weights reproduces the original output bit for bit
         _load_seeded(model, g, 2024)
         assert torch.equal(model(x), y0)
+
+
+def test_uint8_frame_path_matches_normalised_fp32_path_and_gpu_free_metrics():
+    """Evaluator path (N4): feeding the uint8 HWC image + set_input_normalization must give the labels of feeding
+    normalize(img) as fp32 CHW (tools/engine/evaluator.py:329); the device confusion matrix must equal metric.hist_info."""
+    from fasterseg_b200 import metric
+    model, g = _build_student(1)
+    model = model.eval()
+    _load_seeded(model, g, 77)
+    rs = np.random.RandomState(3)
+    img = rs.randint(0, 256, size=(1, 64, 128, 3)).astype(np.uint8)
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    ref_in = ((img.astype(np.float32) / 255.0 - mean) / std).astype(np.float32).transpose(0, 3, 1, 2)      # img_utils.normalize
+    model.set_input_normalization(mean, std)
+    with torch.no_grad():
+        lab_u8 = model.predict_labels(torch.from_numpy(img).permute(0, 3, 1, 2))
+        lab_f32 = model.predict_labels(torch.from_numpy(np.ascontiguousarray(ref_in)))
+    assert torch.equal(lab_u8, lab_f32)
+    gt = torch.from_numpy(rs.randint(0, 19, size=(1, 64, 128)).astype(np.int64))
+    gt[0, :5] = 255
+    hist, labeled, correct = metric.hist_info(19, lab_u8, gt)
+    p, t = lab_u8.numpy(), gt.numpy()
+    k = (t >= 0) & (t < 19)
+    want = np.bincount(19 * t[k].astype(int) + p[k].astype(int), minlength=19 ** 2).reshape(19, 19)
+    assert np.array_equal(hist, want) and labeled == int(k.sum()) and correct == int((p[k] == t[k]).sum())
+    iu, miou, _, acc = metric.compute_score(hist, correct, labeled)
+    assert 0 <= acc <= 1 and iu.shape == (19,)

@@ -171,3 +171,30 @@ def test_student_train_step_gradients_vs_oracle():
     no_grad_ours = {k for k, p in model.named_parameters() if p.grad is None}
     no_grad_ref = {k for k in dict(model.named_parameters()) if k not in g32}
     assert no_grad_ours == no_grad_ref, sorted(no_grad_ours ^ no_grad_ref)
+
+
+def test_uint8_frame_path_and_device_confusion_matrix():
+    """Evaluator path (N4): the uint8 HWC image through the stem's lookup-table gather gives bit-identical labels to the
+    normalised fp32 CHW frame (tools/engine/evaluator.py:329), and the device confusion matrix equals metric.hist_info."""
+    from fasterseg_b200 import metric
+    model, g = _build_student(1)
+    model = model.cuda().eval()
+    _load_seeded(model, g, 77)
+    rs = np.random.RandomState(3)
+    img = rs.randint(0, 256, size=(2, 96, 160, 3)).astype(np.uint8)
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    ref_in = ((img.astype(np.float32) / 255.0 - mean) / std).astype(np.float32).transpose(0, 3, 1, 2)
+    model.set_input_normalization(mean, std)
+    with torch.no_grad():
+        lab_u8 = model.predict_labels(torch.from_numpy(img).cuda().permute(0, 3, 1, 2))
+        lab_f32 = model.predict_labels(torch.from_numpy(np.ascontiguousarray(ref_in)).cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(lab_u8, lab_f32)
+    gt = rs.randint(0, 19, size=(2, 96, 160)).astype(np.int64)
+    gt[:, :7] = 255
+    for dtype in (torch.int64, torch.int32, torch.uint8):
+        hist, labeled, correct = metric.hist_info(19, lab_u8, torch.from_numpy(gt).to(dtype).cuda())
+        p = lab_u8.cpu().numpy()
+        k = (gt >= 0) & (gt < 19)
+        want = np.bincount(19 * gt[k].astype(int) + p[k].astype(int), minlength=19 ** 2).reshape(19, 19)
+        assert np.array_equal(hist, want) and labeled == int(k.sum()) and correct == int((p[k] == gt[k]).sum())
