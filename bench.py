@@ -8,9 +8,15 @@ One "step" = one 1024x2048 frame through the student network (BASELINE.json conf
   value : frames/s with the frame already resident in HBM (CUDA-graph replay of the whole forward; full-resolution
           fp16 NCHW logits are materialised, i.e. the work the reference's `model(input)` does in
           tools/utils/darts_utils.py:182-223)
-  e2e   : frames/s through the public host API (fasterseg_b200.runtime.InferencePipeline): pinned-host fp32 NCHW
-          frame -> H2D -> network -> fused upsample+argmax -> uint8 label map D2H, 3 frames in flight
-  roofline    : the dominant kernel (tcgen05 implicit-GEMM conv) on its most expensive launch, timed live
+  e2e   : frames/s through the public host API (fasterseg_b200.runtime.InferencePipeline) on the evaluator path
+          (tools/engine/evaluator.py:206-225): pinned-host uint8 HWC image -> H2D -> normalisation folded into the stem kernel
+          -> network -> fused upsample+argmax -> uint8 label map D2H, 3 frames in flight.  `e2e_fp32_input` is the same with
+          the normalised fp32 NCHW frame of round 1 (25 MB per frame over PCIe).
+  roofline    : the dominant kernel (tcgen05 implicit-GEMM conv) timed live on BOTH 9.66-GFLOP layers of the frame
+                (heads8 3x3 128->128 @128x256 and stem.1.conv2 64->64 @256x512); the line reports the WORSE of the two
+  supernet_steps: the other half of BASELINE's metric -- pretrain (configs[2]) and search (configs[4]) step of the 16-layer
+                supernet with the reference's OHEM criterion, as captured passes; under torchrun data parallel (SyncBN over
+                NVLink peer memory + one flat gradient all-reduce), images/s summed over ranks
   cpu_baseline: the CPU oracle port of the reference path (same weights) on the host cores (N=1, rank 0 only)
 Multi-GPU: inference has no exchange step -> N independent replicas ("replicas only"), weak scaling.
 `--impl reference` times the reference's CPU path (oracle port; the Python reference tree does not exist on the GPU box).
@@ -145,26 +151,28 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def dominant_kernel_roofline(device):
-    """Time the tcgen05 implicit-GEMM conv on its most expensive launch of the student frame: heads8.conv_3x3
-    (3x3, 128 -> 128 channels on the 128x256 1/8-resolution map, 9.66 GFLOP = 17 % of the frame; stem.1.conv2 has the
-    same FLOPs).  Algorithmic work per launch: 2*9*128*128*(128*256) FLOP; bytes = in + out + weights, each once."""
+KERNEL_NAMES = {0: "conv_direct_kernel", 1: "conv_tc_kernel (per-tap, 128 px x Cout tile)", 2: "conv_tc2_kernel (row strip)",
+                3: "conv_tc3_kernel (channel-major 128 x 256 MMA)"}
+
+
+def _time_conv_layer(device, Cin, Cout, h, w, reps=5):
+    """one 3x3 stride-1 conv+BN+ReLU launch, CUDA events over rotating > L2 buffers -> (us per launch, kernel id)"""
+    import ctypes as C
+    from fasterseg_b200 import _lib
     from fasterseg_b200 import functional as F_
-    Cin = Cout = 128
-    h, w = 128, 256
-    flops = 2.0 * 9 * Cin * Cout * h * w
-    abytes = 2.0 * (Cin * h * w + Cout * h * w + 9 * Cin * Cout)
-    nbuf = 12  # 12 x (8.4 + 8.4) MB = 201 MB > 126 MB L2: every launch reads its input from HBM
+    per_pair = 2.0 * (Cin + Cout) * h * w
+    nbuf = max(6, int(160e6 / per_pair) + 1)   # > 126 MB L2: every launch reads its input from HBM
     xs = [F_.empty_nhwc(1, Cin, h, w, device).normal_() for _ in range(nbuf)]
     ys = [F_.empty_nhwc(1, Cout, h, w, device) for _ in range(nbuf)]
     wt = torch.randn(Cout, Cin, 3, 3, device=device) * 0.03
     wp = F_.pack_conv_weight(wt, Cin, Cout, 3)
     scale = torch.rand(Cout, device=device) + 0.5
     shift = torch.randn(Cout, device=device) * 0.1
+    d = _lib.ConvDesc(1, h, w, Cin, Cout, 3, 1, 1, 1, 0, 0, h, w, Cin, Cout, _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE)
+    kid = _lib.lib().fsb_conv_kernel_id(C.byref(d), C.c_void_p(ys[0].data_ptr()), 0)
     for i in range(nbuf):
         F_.conv_fwd(xs[i], wp, Cout, 3, 1, 1, scale, shift, relu=True, out=ys[i])
     torch.cuda.synchronize()
-    reps = 5
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st.record()
     for _ in range(reps):
@@ -172,27 +180,44 @@ def dominant_kernel_roofline(device):
             F_.conv_fwd(xs[i], wp, Cout, 3, 1, 1, scale, shift, relu=True, out=ys[i])
     en.record()
     en.synchronize()
-    us = st.elapsed_time(en) * 1000.0 / (reps * nbuf)
+    return st.elapsed_time(en) * 1000.0 / (reps * nbuf), kid
+
+
+def dominant_kernel_roofline(device):
+    """The tcgen05 implicit-GEMM conv on the two most expensive launches of the student frame (9.66 GFLOP each, 17 % of the
+    frame's FLOPs each): heads8.conv_3x3 (128 -> 128 channels on the 128x256 map, intensity 566 FLOP/B: tensor-bound) and
+    stem.1.conv2 (64 -> 64 on the 256x512 map, intensity 288 FLOP/B: at the ridge, 5.7 us by FLOPs vs 5.1 us by bytes).
+    Algorithmic work per launch: 2*9*Cin*Cout*h*w FLOP; bytes = input + output + weights, each once, fp16.
+    The line's `roofline` is the WORSE of the two; both are listed under `layers`."""
     pk = measured_peaks()
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
-    tj = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
-    if os.path.isfile(tj):
-        with open(tj) as f:
-            traffic = json.load(f).get("traffic_bytes")
-    t_tensor = flops / (pk["tflops"] * 1e12)
-    t_hbm = abytes / (pk["hbm_gbs"] * 1e9)
-    if t_tensor >= t_hbm:
-        achieved = flops / (us * 1e-6) / 1e12
-        return {"kernel": "conv_tc_kernel<64> (heads8.conv_3x3: 3x3 128->128 @128x256)", "bound": "tensor",
-                "achieved": round(achieved, 2), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["tflops"], 4),
-                "traffic": traffic, "us_per_launch": round(us, 2), "peak_source": pk["source"],
-                "algorithmic_flops": flops, "algorithmic_bytes": abytes,
-                "note": "tensor-bound by the roofline (intensity 566 FLOP/B); ncu: tensor pipe active 31 %, L2->SM 8.1 TB/s: 1-CTA "
-                        "SS-mode MMAs are operand-fetch bound (~130 cycles per 128x128x16 MMA, tools/tc2_timeline.py); traffic "
-                        "< algorithmic bytes because the 8.4 MB output stays in L2 during the captured launch"}
-    achieved = abytes / (us * 1e-6) / 1e9
-    return {"kernel": "conv_tc_kernel<64>", "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "us_per_launch": round(us, 2), "peak_source": pk["source"]}
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of the heads8 launch
+    for name in ("r2_roofline_traffic.json", "r1_roofline_traffic.json"):
+        tj = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(tj):
+            with open(tj) as f:
+                traffic = json.load(f).get("traffic_bytes")
+            break
+    layers = []
+    for label, Cin, Cout, h, w in (("heads8.conv_3x3: 3x3 128->128 @128x256", 128, 128, 128, 256),
+                                   ("stem.1.conv2: 3x3 64->64 @256x512", 64, 64, 256, 512)):
+        us, kid = _time_conv_layer(device, Cin, Cout, h, w)
+        flops = 2.0 * 9 * Cin * Cout * h * w
+        abytes = 2.0 * (Cin * h * w + Cout * h * w + 9 * Cin * Cout)
+        t_tensor, t_hbm = flops / (pk["tflops"] * 1e12), abytes / (pk["hbm_gbs"] * 1e9)
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        achieved = flops / (us * 1e-6) / 1e12 if bound == "tensor" else abytes / (us * 1e-6) / 1e9
+        peak = pk["tflops"] if bound == "tensor" else pk["hbm_gbs"]
+        layers.append({"kernel": "%s on %s" % (KERNEL_NAMES.get(kid, "?"), label), "bound": bound, "achieved": round(achieved, 2),
+                       "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(achieved / peak, 4),
+                       "us_per_launch": round(us, 2), "roofline_us": round(max(t_tensor, t_hbm) * 1e6, 2),
+                       "algorithmic_flops": flops, "algorithmic_bytes": abytes})
+    worst = dict(min(layers, key=lambda r: r["frac"]))
+    worst.update({"traffic": traffic if "heads8" in worst["kernel"] else None, "peak_source": pk["source"], "layers": layers,
+                  "note": "worse of the two 9.66-GFLOP launches of the frame; heads8 runs the channel-major kernel (weights as the "
+                          "M = 128 operand, 256 pixels as N: 96 B/clk of shared-memory operand traffic instead of 128 B/clk for "
+                          "128 x 128 tiles); stem.1.conv2 has only 64 output channels (N = 64 per MMA) and sits at the "
+                          "tensor/HBM ridge"})
+    return worst
 
 
 def cpu_port_fps(model_state_cpu, frames, threads):
@@ -269,38 +294,79 @@ def frame_sigma_roofline(model, x, frame_us):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def supernet_step_metric():
-    """Second half of BASELINE.json's metric: supernet pretrain step (configs[2], 3x3x256x512 per GPU, 16 layers, 252 M
-    parameters: 4 forwards + backward + clip + SGD) through the reference-facing classes.  Extra key only -- it never fails
-    the headline line.  Measured per-unit (the default autograd wiring) and, if that works on this box, with the
-    experimental tape mode (FSB_TAPE: one autograd node per forward pass, same kernels, same work); the tape number is only
-    reported when its loss agrees with the per-unit run.  Multi-GPU numbers come from `torchrun ... tools/search_step_bench.py`."""
+def _load_tool(name):
+    import importlib.util
+    path = os.path.join(ROOT, "tools", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def supernet_cpu_step_ms(mode, threads):
+    """The reference's CPU path for one supernet step (oracle port of search/model_search.py:478-505 + backward, fp32, torch CPU):
+    ONE step (bounded sample: ~10-40 s), same synthetic shapes as the GPU measurement."""
+    import numpy as np
+    import torch.nn as nn
+    from oracle import fasterseg_oracle as orc
+    from oracle import supernet_oracle as sno
+    torch.set_num_threads(threads)
+    B, Hh, Ww = (3, 256, 512) if mode == "pretrain" else (2, 224, 448)
+    from fasterseg_b200.model_search import Network_Multi_Path
+    m = Network_Multi_Path(19, 16, nn.CrossEntropyLoss(ignore_index=255), Fch=12, width_mult_list=orc.WIDTH_MULT_LIST,
+                           prun_modes=['max', 'arch_ratio'], stem_head_width=[(1, 1), (8. / 12, 8. / 12)])
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    del m
+    sd = orc.random_state_dict(shapes, seed=1)
+    for k, v in sd.items():
+        if "running" not in k and v.dtype.is_floating_point:
+            v.requires_grad_(True)
+    x = orc.random_input((B, 3, Hh, Ww), seed=2)
+    t = torch.randint(0, 19, (B, Hh // 8, Ww // 8), generator=torch.Generator().manual_seed(3))
+    from fasterseg_b200.losses import ProbOhemCrossEntropy2d
+    crit = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=int(B * (Hh // 8) * (Ww // 8) // 16))
+    np.random.seed(4)
+    torch.manual_seed(5)
+    t0 = time.perf_counter()
+    n_losses = 2 if mode == "search" else 1          # the search step evaluates `_loss` twice (architect step + weight step)
+    for _ in range(n_losses):
+        loss = sno.supernet_loss(x, t, sd, sno.SupernetConfig(layers=16), crit, True if mode == "pretrain" else "dir")
+        loss.backward()
+    return (time.perf_counter() - t0) * 1e3
+
+
+def supernet_steps_metric(rank, world, with_cpu):
+    """Second half of BASELINE.json's metric: supernet pretrain step (configs[2], 3x3x256x512 per GPU) and search step
+    (configs[4], 2x3x224x448 per GPU) of the 16-layer / 252 M parameter supernet through the reference-facing classes:
+    `_loss` (4 forwards, 5 OHEM terms each) + backward + clip + SGD (+ the architect's first-order step for search).
+    Captured passes (fasterseg_b200/graphed.py); under torchrun: data parallel, SyncBN over NVLink peer memory, one flat
+    gradient all-reduce per `_loss`.  Extra key only -- it never fails the headline line."""
+    out = {}
     try:
-        import importlib.util
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "search_step_bench.py")
-        spec = importlib.util.spec_from_file_location("search_step_bench", path)
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        res = mod.measure("pretrain", 16, steps=3, warmup=2, tape=False)
-        res["timing"] = "host wall clock around step + synchronize, median of 3 (the step is host-launch-bound: ~20 k launches)"
-        try:
-            taped = mod.measure("pretrain", 16, steps=3, warmup=2, tape=True)
-            same = abs(taped["loss"] - res["loss"]) <= 2e-2 * abs(res["loss"])   # same seeds, same data; chaotic net -> loose
-            res["tape_mode"] = {"value": taped["value"], "min_ms": taped["min_ms"], "loss": taped["loss"], "loss_agrees": bool(same),
-                                "what": "FSB_TAPE=1 (experimental, default off): one torch.autograd node per forward pass"}
-        except Exception as e:  # noqa: BLE001
-            res["tape_mode"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        finally:
-            from fasterseg_b200 import autograd as AG
-            AG.TAPE_ENABLED = os.environ.get("FSB_TAPE", "0") == "1"
-        return res
-    except Exception as e:  # noqa: BLE001 -- secondary metric, reported not raised
-        return {"error": "%s: %s" % (type(e).__name__, e)}
-    finally:
-        try:
-            torch.cuda.empty_cache()
-        except Exception:  # noqa: BLE001 -- a poisoned context must not take the headline line down
-            pass
+        mod = _load_tool("search_step_bench")
+        for mode, steps, warm in (("pretrain", 8, 3), ("search", 5, 2)):
+            try:
+                res = mod.measure(mode, 16, steps=steps, warmup=warm, rank=rank, world=world, graph=True, criterion="ohem")
+                res["timing"] = "host wall clock around step + synchronize, median of %d, max over ranks" % steps
+                if with_cpu and rank == 0:
+                    try:
+                        threads = min(os.cpu_count() or 1, 32)
+                        ms = supernet_cpu_step_ms(mode, threads)
+                        res["cpu_baseline"] = {"value": round(ms, 1), "unit": "ms/step", "cores": threads, "kind": "port",
+                                               "sample": "1 step of the same shapes through the CPU oracle port (torch CPU fp32)"}
+                    except Exception as e:  # noqa: BLE001
+                        res["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
+                out[mode] = res
+            except Exception as e:  # noqa: BLE001 -- secondary metric, reported not raised
+                out[mode] = {"error": "%s: %s" % (type(e).__name__, e)}
+            finally:
+                try:
+                    torch.cuda.empty_cache()
+                except Exception:  # noqa: BLE001
+                    pass
+    except Exception as e:  # noqa: BLE001
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
 
 
 def main():
@@ -311,7 +377,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supernet-step", action="store_true",
-                    help="skip the secondary metric (supernet pretrain-step ms, BASELINE configs[2]) reported at N=1")
+                    help="skip the secondary metric (supernet pretrain / search step, BASELINE configs[2] / [4])")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 30:
@@ -328,7 +394,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        from fasterseg_b200 import parallel
+        parallel.init_from_env()          # NCCL group + the library's peer-memory exchange for the data-parallel supernet steps
 
     from fasterseg_b200 import zoo
     from fasterseg_b200.runtime import GraphedInference, InferencePipeline, bind_host_thread_to_gpu
@@ -344,6 +411,7 @@ def main():
     npool = 6  # 6 x 25.2 MB = 151 MB of distinct frames > 126 MB L2
     pool = [torch.randn(1, 3, H, W, generator=g).to(device) for _ in range(npool)]
     runner = GraphedInference(model, pool[0], mode="logits", logits_dtype=torch.float16)
+    launches_value = runner.launches_per_replay
     for i in range(args.warmup):
         runner(pool[i % npool])
     torch.cuda.synchronize()
@@ -367,29 +435,43 @@ def main():
     value = world * args.steps / (ms_total / 1000.0)
 
     # ---- end-to-end FPS through the host API ----
-    pipe = InferencePipeline(model, pool[0], mode="labels", depth=3)
-    host_frames = [torch.randn(1, 3, H, W, generator=g).pin_memory() for _ in range(4)]
-    pipe.run(host_frames[i % 4] for i in range(max(3, args.warmup // 2)))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     checksum = [0]
 
     def consume(lbl):
         checksum[0] += int(lbl[0, 0, 0])  # touch the result on the host
 
     e2e_steps = args.steps
-    t0 = time.perf_counter()
-    pipe.run((host_frames[i % 4] for i in range(e2e_steps)), consume)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_fps = world * e2e_steps / e2e_s
+
+    def run_e2e(example, host_frames):
+        pipe = InferencePipeline(model, example, mode="labels", depth=3)
+        pipe.run(host_frames[i % 4] for i in range(max(3, args.warmup // 2)))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        pipe.run((host_frames[i % 4] for i in range(e2e_steps)), consume)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return pipe, world * e2e_steps / dt
+
+    # evaluator path: the uint8 HWC image itself crosses PCIe (6.3 MB), normalisation happens inside the stem kernel
+    model.set_input_normalization([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    u8_frames = [torch.randint(0, 256, (1, H, W, 3), generator=g, dtype=torch.uint8).pin_memory().permute(0, 3, 1, 2) for _ in range(4)]
+    pipe, e2e_fps = run_e2e(u8_frames[0].to(device), u8_frames)
+    # round-1 input format (normalised fp32 NCHW frame, 25 MB): kept for comparison / fp32-input parity
+    f32_frames = [torch.randn(1, 3, H, W, generator=g).pin_memory() for _ in range(4)]
+    pipe32, e2e32_fps = run_e2e(pool[0], f32_frames)
     clocks = sampler.stop() if rank == 0 else None
 
+    steps_metric = None
+    if not args.no_supernet_step:
+        del runner, pipe32
+        torch.cuda.empty_cache()
+        steps_metric = supernet_steps_metric(rank, world, with_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -410,16 +492,21 @@ def main():
                    "frame_gflop": STUDENT_GFLOP},
         "clocks": clocks,
         "e2e": {"value": round(e2e_fps, 1), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                "what": "pinned fp32 NCHW frame -> H2D -> student -> fused upsample+argmax -> uint8 labels D2H; 3 frames in flight",
+                "what": "pinned uint8 HWC image -> H2D -> normalisation folded into the stem kernel -> student -> fused "
+                        "upsample+argmax -> uint8 labels D2H; 3 frames in flight (evaluator path, tools/engine/evaluator.py:206-225)",
                 "steps": e2e_steps, "host_cpus_bound_to_gpu_socket": local_cpus},
-        "gpu_launches": runner.launches_per_replay * args.steps + pipe.launches_per_frame * e2e_steps,
-        "launches_per_frame": runner.launches_per_replay,
+        "e2e_fp32_input": {"value": round(e2e32_fps, 1), "unit": UNIT, "h2d_bytes_per_step": H * W * 3 * 4,
+                           "what": "same pipeline fed with the normalised fp32 NCHW frame (round-1 format)"},
+        "gpu_launches": launches_value * args.steps + pipe.launches_per_frame * e2e_steps * 2,
+        "launches_per_frame": launches_value,
         "roofline": roof,
         "frame_tflops": round(STUDENT_GFLOP * value / world / 1000.0, 2),
     }
     line["frame_roofline"] = frame_sigma_roofline(model, pool[0], ms_total / args.steps * 1000.0 )
-    if world == 1 and not args.no_supernet_step:
-        line["supernet_step"] = supernet_step_metric()
+    if steps_metric is not None:
+        line["supernet_steps"] = steps_metric
+        if isinstance(steps_metric.get("pretrain"), dict) and "value" in steps_metric["pretrain"]:
+            line["supernet_step"] = steps_metric["pretrain"]      # round-1 key: the pretrain step
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
         threads = best_cpu_threads(sd)

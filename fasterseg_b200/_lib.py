@@ -71,7 +71,7 @@ _SIGS = {
     "fsb_affine_act_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_uint32, _P, _P, C.c_int, _P]),
     "fsb_bn_bwd_reduce_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P,
                                         _P, _P, C.c_int, _P]),
-    "fsb_bn_bwd_apply_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_double,
+    "fsb_bn_bwd_apply_sel": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_double,
                                        C.c_int, _P, C.c_int, C.c_float, _P, _P, C.c_int, _P]),
     "fsb_relu_bwd": (C.c_int, [C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "fsb_conv_packed_dgrad_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
@@ -94,6 +94,13 @@ _SIGS = {
     "fsb_dp_enable": (C.c_int, [C.c_int]),
     "fsb_dp_allreduce_f32": (C.c_int, [_P, C.c_int64, _P]),
     "fsb_dp_shutdown": (C.c_int, []),
+    "fsb_peer_alloc": (C.c_int, [_P]),
+    "fsb_peer_open": (C.c_int, [_P, C.c_int, C.c_int]),
+    "fsb_peer_world": (C.c_int, []),
+    "fsb_peer_enable": (C.c_int, [C.c_int]),
+    "fsb_peer_begin": (C.c_int, [C.c_int, _P]),
+    "fsb_peer_allreduce_f32": (C.c_int, [_P, C.c_int64, _P]),
+    "fsb_peer_shutdown": (C.c_int, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -373,10 +373,13 @@ class FactorizedReduceSelFn(torch.autograd.Function):
         stats = F_.conv_stats_buffer(x, hmax, 1, 2, 0, total_C=co)
         F_.conv_fwd(x, p1, hmax, 1, 2, 0, out=raw[:, :hmax], stats=stats, out_f32=True)
         F_.conv_fwd(x, p2, hmax, 1, 2, 0, out=raw[:, hmax:], off=(1, 1), stats=stats, stats_off=hmax, out_f32=True)
-        count = N * (H // 2) * (W // 2)
+        world = engine.dp_world_size()
+        if world > 1:      # SyncBN: totals of all ranks (exchanged by the library, on the stream)
+            stats = F_.dp_allreduce(F_.rowsum(stats))
+        count = N * (H // 2) * (W // 2) * world
         scale, shift, mean, invstd = F_.bn_finalize_sel(stats, count, sel, hmax=hmax)
         y = F_.affine_act_sel(raw, scale, shift, sel, hmax, relu=True)
-        ctx.op, ctx.sel, ctx.ci, ctx.hmax, ctx.count = op, sel, ci, hmax, count
+        ctx.op, ctx.sel, ctx.ci, ctx.hmax, ctx.count, ctx.world = op, sel, ci, hmax, count, world
         ctx.save_for_backward(x, raw, y, mean, invstd)
         return y
 
@@ -385,7 +388,7 @@ class FactorizedReduceSelFn(torch.autograd.Function):
         x, raw, y, mean, invstd = ctx.saved_tensors
         need = ctx.needs_input_grad
         h = ctx.hmax
-        draw = F_.bn_bwd_sel(_dy(dy), y, raw, mean, invstd, ctx.count, True, GRAD_SCALE, ctx.sel, hmax=h)
+        draw = F_.bn_bwd_sel(_dy(dy), y, raw, mean, invstd, ctx.count, True, GRAD_SCALE, ctx.sel, hmax=h, world=ctx.world)
         dx1, _ = _conv_backward(ctx.op.conv1, x, draw[:, :h], ctx.ci, h, (0, 0), need[0], need[1])
         dx2, _ = _conv_backward(ctx.op.conv2, x, draw[:, h:], ctx.ci, h, (1, 1), need[0], need[2])
         dx = F_.add_inplace(dx2, dx1) if need[0] else None

@@ -121,7 +121,7 @@ int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const
                          float*, cudaStream_t, const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0);
 int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
                         const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t, int = 1,
-                        const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0);
+                        const fsb_bn_sel* = nullptr, const int* = nullptr, int = 0, const float* = nullptr);
 int relu_bwd_launch(int64_t, int, const void*, int, const void*, int, void*, int, cudaStream_t);
 fsb_conv_desc dgrad_as_fwd_desc(const fsb_conv_desc*, int, int);
 int pack_dgrad_launch(const fsb_conv_desc*, const float*, int64_t, int64_t, void*, cudaStream_t);
@@ -357,13 +357,14 @@ int fsb_bn_bwd_reduce_sel(int64_t pixels, int C, const void* dy, int dcs, const 
                               static_cast<cudaStream_t>(stream), sel, width_idx, hmax);
 }
 int fsb_bn_bwd_apply_sel(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
-                         int raw_is_f32, const float* mean, const float* invstd, const float* sums, double count, int relu, void* draw,
-                         int ocs, float gscale, const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream) {
+                         int raw_is_f32, const float* mean, const float* invstd, const float* sums, const float* local_sums,
+                         double count, int relu, void* draw, int ocs, float gscale, const fsb_bn_sel* sel, const int* width_idx,
+                         int hmax, void* stream) {
   if (pixels <= 0 || C <= 0 || !dy || !raw || !mean || !invstd || !sums || !draw || count <= 0 || gscale <= 0 || (relu && !y) || !sel ||
       !width_idx)
     return set_error(FSB_ERR_INVALID, "bn_bwd_apply_sel: bad argument");
   return bn_bwd_apply_launch(pixels, C, dy, dcs, y, ycs, raw, rcs, raw_is_f32, mean, invstd, nullptr, sums, count, relu, draw, ocs,
-                             nullptr, nullptr, gscale, static_cast<cudaStream_t>(stream), 1, sel, width_idx, hmax);
+                             nullptr, nullptr, gscale, static_cast<cudaStream_t>(stream), 1, sel, width_idx, hmax, local_sums);
 }
 
 int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, void* dx, int xcs, void* stream) {

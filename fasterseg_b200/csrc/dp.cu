@@ -69,10 +69,19 @@ int load_nccl() {
 }
 }  // namespace
 
-int dp_world() { return (g_dp.comm && g_dp.enabled) ? g_dp.world : 1; }
+bool peer_ready();                                       // peer.cu
+int peer_world();
+int peer_allreduce_f32(float*, int64_t, cudaStream_t);
 
-// in-place sum over ranks of n floats, enqueued on `stream`; no-op for a single process
+int dp_world() {
+  if (peer_ready()) return peer_world();
+  return (g_dp.comm && g_dp.enabled) ? g_dp.world : 1;
+}
+
+// in-place sum over ranks of n floats, enqueued on `stream`; no-op for a single process.  Small vectors (the per-unit SyncBN
+// statistics) go through NVLink peer memory when the launcher set it up (peer.cu), everything else through NCCL.
 int dp_allreduce_f32(float* buf, int64_t n, cudaStream_t stream) {
+  if (peer_ready() && n <= 4096) return peer_allreduce_f32(buf, n, stream);
   if (!g_dp.comm || !g_dp.enabled || g_dp.world <= 1 || n <= 0) return FSB_OK;
   const int rc = g_dp.all_reduce(buf, buf, static_cast<size_t>(n), kNcclFloat32, kNcclSum, g_dp.comm, stream);
   if (rc != 0) return nccl_error(rc, "ncclAllReduce");

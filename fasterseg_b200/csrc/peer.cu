@@ -1,0 +1,227 @@
+// peer.cu -- SyncBN statistics exchange over NVLink peer memory, usable inside captured CUDA graphs.
+//
+// A data-parallel supernet step exchanges ~7 000 vectors of <= 1 536 floats (per-channel BatchNorm sums, forward and
+// backward, of every training unit).  A library collective per vector costs 10-20 us of latency each and the calls of the
+// independent ops -- which run on side streams inside the captured passes -- would serialise on one communicator.  Here every
+// rank owns an exchange buffer allocated with cudaMalloc and mapped into its peers through CUDA IPC (one process per GPU;
+// NVSwitch gives every peer full bandwidth), and the all-reduce is a single-block kernel:
+//     write my vector into my buffer's slot  ->  __threadfence_system  ->  st.release.sys flag[slot] = epoch
+//     for every peer, in RANK ORDER: spin on ld.acquire.sys peer.flag[slot] >= epoch, add its vector (volatile loads)
+// The sum order is the rank order on every rank, so all ranks hold bit-identical statistics (and the result is
+// deterministic).  Slots are handed out in call order inside a REGION (one region per captured graph; the call order is the
+// capture order and identical on every rank); `epoch` is a per-region device counter bumped by the first node of the graph, so
+// a replay needs no host involvement.  Payloads are double-buffered by epoch parity: a rank can only be one replay ahead of a
+// peer (it needs the peer's flags of the previous graph to finish it).
+// The flat gradient all-reduce (1 GB once per step) stays on NCCL (csrc/dp.cu); this file is for the latency-bound part.
+#include "fsb_common.cuh"
+#include "fsb_internal.h"
+
+namespace fsb {
+
+namespace {
+constexpr int kMaxWorld = 8;
+constexpr int kMaxRegions = 64;
+constexpr int kMaxSlots = 32768;          // flags
+constexpr size_t kPayloadFloats = 24u << 20;  // 96 MB of payload per rank (2 parities inside)
+constexpr int kMaxVec = 4096;             // floats per exchange (one block, 256 threads)
+
+struct Slot {
+  uint32_t off;  // float offset of parity 0 inside the payload area; parity 1 follows at off + n
+  uint32_t n;
+};
+
+struct PeerState {
+  int world = 1, rank = 0;
+  bool ready = false, enabled = true;
+  uint8_t* local = nullptr;
+  uint8_t* base[kMaxWorld] = {nullptr};
+  unsigned* epochs = nullptr;  // device, [kMaxRegions], private to this rank
+  Slot slots[kMaxSlots];
+  int n_slots = 0;
+  size_t used = 0;
+  int region_first[kMaxRegions];
+  int region_count[kMaxRegions];
+  int region = -1, cursor = 0;
+} g_peer;
+
+constexpr size_t kFlagBytes = static_cast<size_t>(kMaxSlots) * sizeof(unsigned);
+constexpr size_t kBufferBytes = kFlagBytes + kPayloadFloats * sizeof(float);
+
+struct PeerPtrs {
+  uint8_t* base[kMaxWorld];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_volatile_f32(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void epoch_bump_kernel(unsigned* e) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *e += 1;
+}
+
+// v[0..n) <- sum over ranks of v, in rank order
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(float* __restrict__ v, int n, PeerPtrs pp, int rank, int world, uint32_t slot, uint32_t off,
+                      const unsigned* __restrict__ epoch_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned e = *epoch_ptr;
+  const size_t par = static_cast<size_t>(e & 1u) * n;
+  float* mine = reinterpret_cast<float*>(pp.base[rank] + kFlagBytes) + off + par;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = v[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned*>(pp.base[rank]) + slot, e);
+  if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) {
+    const unsigned* flag = reinterpret_cast<const unsigned*>(pp.base[threadIdx.x]) + slot;
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys(flag) - e) < 0) {
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a rank that never arrives must surface as a launch failure, not a hang
+        printf("fsb200: peer exchange timed out (rank %d waiting for rank %d, slot %u, epoch %u)\n", rank, threadIdx.x, slot, e);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < world; ++p) {
+      const float* src = reinterpret_cast<const float*>(pp.base[p] + kFlagBytes) + off + par;
+      acc += (p == rank) ? v[i] : ld_volatile_f32(src + i);
+    }
+    v[i] = acc;
+  }
+}
+}  // namespace
+
+bool peer_ready() { return g_peer.ready && g_peer.enabled && g_peer.world > 1; }
+int peer_world() { return peer_ready() ? g_peer.world : 1; }
+
+int peer_allreduce_f32(float* buf, int64_t n, cudaStream_t stream) {
+  if (!peer_ready() || n <= 0) return FSB_OK;
+  if (n > kMaxVec) return set_error(FSB_ERR_INVALID, "peer exchange: vector longer than 4096 floats");
+  if (g_peer.region < 0) return set_error(FSB_ERR_INVALID, "peer exchange outside a region (fsb_peer_begin)");
+  const int r = g_peer.region;
+  int slot;
+  if (g_peer.cursor < g_peer.region_count[r]) {
+    slot = g_peer.region_first[r] + g_peer.cursor;
+    if (g_peer.slots[slot].n != static_cast<uint32_t>(n))
+      return set_error(FSB_ERR_INVALID, "peer exchange: the call sequence of this region changed (vector length differs)");
+  } else {
+    // new slot: regions are built one at a time, so a region's slots are contiguous
+    if (g_peer.region_count[r] == 0) g_peer.region_first[r] = g_peer.n_slots;
+    if (g_peer.region_first[r] + g_peer.region_count[r] != g_peer.n_slots)
+      return set_error(FSB_ERR_INVALID, "peer exchange: region grew after another region was started");
+    if (g_peer.n_slots >= kMaxSlots || g_peer.used + 2 * static_cast<size_t>(n) > kPayloadFloats)
+      return set_error(FSB_ERR_INVALID, "peer exchange: out of slots / payload space");
+    slot = g_peer.n_slots++;
+    g_peer.slots[slot].off = static_cast<uint32_t>(g_peer.used);
+    g_peer.slots[slot].n = static_cast<uint32_t>(n);
+    g_peer.used += 2 * static_cast<size_t>(n);
+    g_peer.region_count[r]++;
+  }
+  g_peer.cursor++;
+  PeerPtrs pp;
+  for (int i = 0; i < kMaxWorld; ++i) pp.base[i] = g_peer.base[i];
+  FSB_LAUNCH(peer_allreduce_kernel, dim3(1), dim3(256), 0, stream, buf, static_cast<int>(n), pp, g_peer.rank, g_peer.world,
+             static_cast<uint32_t>(slot), g_peer.slots[slot].off, static_cast<const unsigned*>(g_peer.epochs + r));
+  cudaError_t e = last_launch_error();
+  if (e != cudaSuccess) return set_cuda_error(e, "peer_allreduce launch");
+  return FSB_OK;
+}
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" {
+
+/* allocate this rank's exchange buffer; handle_out: 64 bytes (cudaIpcMemHandle_t) to be all-gathered by the launcher */
+int fsb_peer_alloc(void* handle_out64) {
+  if (!handle_out64) return set_error(FSB_ERR_INVALID, "fsb_peer_alloc: null handle buffer");
+  if (g_peer.local) return set_error(FSB_ERR_INVALID, "fsb_peer_alloc: already allocated");
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g_peer.local), kBufferBytes);
+  if (e != cudaSuccess) return set_cuda_error(e, "fsb_peer_alloc: cudaMalloc");
+  e = cudaMemset(g_peer.local, 0, kBufferBytes);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g_peer.epochs), kMaxRegions * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(g_peer.epochs, 0, kMaxRegions * sizeof(unsigned));
+  if (e != cudaSuccess) return set_cuda_error(e, "fsb_peer_alloc: init");
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, g_peer.local);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaIpcGetMemHandle");
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out64, &h, 64);
+  return FSB_OK;
+}
+
+/* handles: world x 64 bytes in rank order (entry `rank` is this rank's own).  Collective in spirit: every rank calls it after
+ * the all-gather and must not exchange before all ranks returned (the launcher barriers). */
+int fsb_peer_open(const void* handles, int rank, int world) {
+  if (!handles || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !g_peer.local)
+    return set_error(FSB_ERR_INVALID, "fsb_peer_open: bad arguments (call fsb_peer_alloc first; world <= 8)");
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      g_peer.base[p] = g_peer.local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const uint8_t*>(handles) + 64 * p, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaIpcOpenMemHandle");
+    g_peer.base[p] = static_cast<uint8_t*>(ptr);
+  }
+  g_peer.rank = rank;
+  g_peer.world = world;
+  for (int i = 0; i < kMaxRegions; ++i) g_peer.region_first[i] = g_peer.region_count[i] = 0;
+  g_peer.ready = true;
+  return FSB_OK;
+}
+
+int fsb_peer_world(void) { return peer_world(); }
+int fsb_peer_enable(int on) {
+  g_peer.enabled = on != 0;
+  return FSB_OK;
+}
+
+/* Start (or restart) issuing the exchanges of `region` on `stream`: bumps the region's epoch on the device (captured as a
+ * graph node) and rewinds its slot cursor.  Every rank must issue the same regions with the same exchange sequence. */
+int fsb_peer_begin(int region, void* stream) {
+  if (!peer_ready()) return FSB_OK;
+  if (region < 0 || region >= kMaxRegions) return set_error(FSB_ERR_INVALID, "fsb_peer_begin: region out of range");
+  g_peer.region = region;
+  g_peer.cursor = 0;
+  FSB_LAUNCH(epoch_bump_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), g_peer.epochs + region);
+  cudaError_t e = last_launch_error();
+  if (e != cudaSuccess) return set_cuda_error(e, "epoch_bump launch");
+  return FSB_OK;
+}
+
+/* in-place sum over ranks of n <= 4096 floats through peer memory (rank-ordered, deterministic); no-op for a single process */
+int fsb_peer_allreduce_f32(void* buf, int64_t n, void* stream) {
+  if (!buf && n > 0) return set_error(FSB_ERR_INVALID, "fsb_peer_allreduce_f32: null buffer");
+  return peer_allreduce_f32(static_cast<float*>(buf), n, static_cast<cudaStream_t>(stream));
+}
+
+int fsb_peer_shutdown(void) {
+  for (int p = 0; p < g_peer.world; ++p)
+    if (p != g_peer.rank && g_peer.base[p]) cudaIpcCloseMemHandle(g_peer.base[p]);
+  if (g_peer.local) cudaFree(g_peer.local);
+  if (g_peer.epochs) cudaFree(g_peer.epochs);
+  g_peer = PeerState();
+  return FSB_OK;
+}
+
+}  // extern "C"

@@ -137,7 +137,7 @@ bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dc
                     const TR* __restrict__ raw, int rcs, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int relu,
                     __half* __restrict__ draw, int ocs, float* __restrict__ dgamma, float* __restrict__ dbeta, float inv_gscale,
-                    int accumulate, const fsb_bn_sel* sel, const int* width_idx, int hmax) {
+                    int accumulate, const fsb_bn_sel* sel, const int* width_idx, int hmax, const float* __restrict__ psums) {
   pdl_launch_dependents();
   pdl_wait();
   const int cvec = C >> 3;
@@ -149,10 +149,13 @@ bn_bwd_apply_kernel(int64_t pixels, int C, const __half* __restrict__ dy, int dc
     dbeta = sl.dbeta;
     active = sl.C;
   }
-  if (blockIdx.x == 0) {
+  // gamma / beta gradients: accumulate = 1 add, 0 assign, -1 none.  psums: the rank-LOCAL sums under data parallelism (the
+  // gradient average over ranks divides by the world size afterwards), `sums` then being the all-reduced ones.
+  if (blockIdx.x == 0 && accumulate >= 0) {
+    const float* ps = psums ? psums : sums;
     for (int c = threadIdx.x; c < active; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sums[c] * inv_gscale;
-      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sums[C + c] * inv_gscale;
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + ps[c] * inv_gscale;
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + ps[C + c] * inv_gscale;
     }
   }
   const int64_t total = pixels * cvec;
@@ -235,7 +238,7 @@ int bn_bwd_reduce_launch(int64_t pixels, int C, const void* dy, int dcs, const v
 int bn_bwd_apply_launch(int64_t pixels, int C, const void* dy, int dcs, const void* y, int ycs, const void* raw, int rcs,
                         int raw_f32, const float* mean, const float* invstd, const float* gamma, const float* sums, double count, int relu,
                         void* draw, int ocs, float* dgamma, float* dbeta, float gscale, cudaStream_t stream, int accumulate,
-                        const fsb_bn_sel* sel, const int* width_idx, int hmax) {
+                        const fsb_bn_sel* sel, const int* width_idx, int hmax, const float* psums) {
   if (hmax > 0 && (!sel || !width_idx || hmax % 8 || C != 2 * hmax)) return set_error(FSB_ERR_INVALID, "bn_bwd_apply: bad split arguments");
   if (!vec_ok(C, dcs, dy) || !vec_ok(C, rcs, raw) || !vec_ok(C, ocs, draw) || (relu && !vec_ok(C, ycs, y)))
     return set_error(FSB_ERR_INVALID, "bn_bwd_apply: C/strides multiples of 8, pointers 16B aligned");
@@ -243,12 +246,12 @@ int bn_bwd_apply_launch(int64_t pixels, int C, const void* dy, int dcs, const vo
     FSB_LAUNCH(bn_bwd_apply_kernel<float>, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const float*>(raw), rcs, mean,
                invstd, gamma, sums, static_cast<float>(1.0 / count), relu, static_cast<__half*>(draw), ocs, dgamma, dbeta,
-               1.0f / gscale, accumulate, sel, width_idx, hmax);
+               1.0f / gscale, accumulate, sel, width_idx, hmax, psums);
   else
     FSB_LAUNCH(bn_bwd_apply_kernel<__half>, dim3(grid_for(pixels * (C / 8), 256)), dim3(256), 0, stream, pixels, C,
                static_cast<const __half*>(dy), dcs, static_cast<const __half*>(y), ycs, static_cast<const __half*>(raw), rcs, mean,
                invstd, gamma, sums, static_cast<float>(1.0 / count), relu, static_cast<__half*>(draw), ocs, dgamma, dbeta,
-               1.0f / gscale, accumulate, sel, width_idx, hmax);
+               1.0f / gscale, accumulate, sel, width_idx, hmax, psums);
   cudaError_t e = last_launch_error();
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd_apply launch");
   return FSB_OK;

@@ -13,7 +13,7 @@ int bn_bwd_reduce_launch(int64_t, int, const void*, int, const void*, int, const
                          float*, cudaStream_t, const fsb_bn_sel*, const int*, int);
 int bn_bwd_apply_launch(int64_t, int, const void*, int, const void*, int, const void*, int, int, const float*, const float*,
                         const float*, const float*, double, int, void*, int, float*, float*, float, cudaStream_t, int,
-                        const fsb_bn_sel*, const int*, int);
+                        const fsb_bn_sel*, const int*, int, const float*);
 int rowsum_launch(int, const float*, int, int, float*, cudaStream_t);
 int conv_tc_m_tiles(const fsb_conv_desc*);
 int conv_tc2_ctas(const fsb_conv_desc*);
@@ -115,11 +115,11 @@ int fsb_conv_bn_act_train_bwd(const fsb_conv_desc* d, const void* x, const void*
     rc = dp_allreduce_f32(vec_bwd, 2 * C, st);
     if (rc) return rc;
     rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
-                             static_cast<double>(pixels) * world, relu, draw, draw_cstride, nullptr, nullptr, gscale, st, 0, sel ? sel : nullptr,
-                             width_idx, 0);
+                             static_cast<double>(pixels) * world, relu, draw, draw_cstride, nullptr, nullptr, gscale, st, -1, sel, width_idx, 0,
+                             nullptr);
   } else {
     rc = bn_bwd_apply_launch(pixels, C, dy, dy_cstride, y, y_cstride, raw_f32, raw_cstride, 1, vec_fwd + 4 * C, vec_fwd + 5 * C, gamma, vec_bwd,
-                             static_cast<double>(pixels), relu, draw, draw_cstride, dgamma, dbeta, gscale, st, sel ? 1 : 0, sel, width_idx, 0);
+                             static_cast<double>(pixels), relu, draw, draw_cstride, dgamma, dbeta, gscale, st, sel ? 1 : 0, sel, width_idx, 0, nullptr);
   }
   if (rc) return rc;
   if (dx) {

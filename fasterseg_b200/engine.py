@@ -180,6 +180,7 @@ def enable_sync_bn(enabled=True, group=None):
     if _SYNC_BN["native"]:   # the library's own communicator follows the switch (a rank-0-only reference run must not all-reduce)
         from . import _lib
         _lib.check(_lib.lib().fsb_dp_enable(1 if enabled else 0), "fsb_dp_enable")
+        _lib.check(_lib.lib().fsb_peer_enable(1 if enabled else 0), "fsb_peer_enable")
 
 
 def dp_world_size():

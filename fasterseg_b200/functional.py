@@ -577,9 +577,18 @@ def affine_act_sel(x, scale, shift, sel, hmax, relu=False):
     return out
 
 
-def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0):
+def dp_allreduce(t):
+    """in-place sum over the data-parallel ranks through the library's own exchange (peer memory for small vectors, NCCL
+    otherwise; csrc/peer.cu, csrc/dp.cu) on the current stream -- capturable, no host synchronisation"""
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    check(_lib.lib().fsb_dp_allreduce_f32(_ptr(t), t.numel(), _stream()), "fsb_dp_allreduce_f32")
+    return t
+
+
+def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0, world=1):
     """BatchNorm(+ReLU) backward of a device-selected set -> draw (raw channel order when hmax > 0); gamma / beta gradients are
-    accumulated into the selected set's gradient slots by the kernel."""
+    accumulated into the selected set's gradient slots by the kernel.  world > 1 (SyncBN): the sums are exchanged between the
+    two kernels, `count` is the global pixel count, and the parameter gradients come from the rank-local sums."""
     N, Cc, H, W, dcs = nhwc_info(dy)
     _, _, _, _, rcs = nhwc_info(raw, raw.dtype)
     rf32 = int(raw.dtype == torch.float32)
@@ -589,8 +598,12 @@ def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0):
     check(_lib.lib().fsb_bn_bwd_reduce_sel(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
                                            _ptr(invstd), int(relu), _ptr(sums), sel.table_ptr, sel.idx_ptr, int(hmax), _stream()),
           "fsb_bn_bwd_reduce_sel")
+    local = None
+    if world > 1:
+        local = sums[0].clone()
+        dp_allreduce(sums[0])
     draw = empty_nhwc(N, Cc, H, W, dy.device)
     check(_lib.lib().fsb_bn_bwd_apply_sel(N * H * W, Cc, _ptr(dy), dcs, _ptr(y) if relu else None, ycs, _ptr(raw), rcs, rf32, _ptr(mean),
-                                          _ptr(invstd), _ptr(sums), float(count), int(relu), _ptr(draw), nhwc_info(draw)[4],
+                                          _ptr(invstd), _ptr(sums), _ptr(local), float(count), int(relu), _ptr(draw), nhwc_info(draw)[4],
                                           float(gscale), sel.table_ptr, sel.idx_ptr, int(hmax), _stream()), "fsb_bn_bwd_apply_sel")
     return draw

@@ -111,8 +111,8 @@ class _PlanAlpha:
 class PassContext:
     """Everything static about one (architecture, input shape): slots, device tables, packed weights, graphs."""
 
-    def __init__(self, model, arch_idx, flat, x_shape, capture):
-        self.model, self.arch_idx, self.flat, self.capture = model, arch_idx, flat, capture
+    def __init__(self, model, arch_idx, flat, x_shape, capture, index=0):
+        self.model, self.arch_idx, self.flat, self.capture, self.index = model, arch_idx, flat, capture, index
         self.dev = flat.S.device
         L = model._layers
         self.rows = (L - 1, L - 1, L - 2)
@@ -134,7 +134,7 @@ class PassContext:
         # independent ops of a MixedOp / the two MixedOps of a Cell run on side streams (GPU only): the pass is a chain of ~8 000
         # kernels that each occupy a fraction of the machine for a few microseconds
         self.use_streams = self.dev.type == "cuda" and os.environ.get("FSB_GRAPH_STREAMS", "1") != "0"
-        self._streams, self._stream_cursor, self._par_depth = [], 0, 0
+        self._streams, self._stream_cursor, self._child_top = [], 0, 0
         self.built = False
         self.graphs = None
         self._pack_versions = None
@@ -219,16 +219,18 @@ class PassContext:
         return self._bslots[i]
 
     def parallel(self, thunks):
-        """run independent pieces of the pass concurrently: thunk i on side stream (cursor + i), forked from and joined to the
-        current stream with events.  The stream assignment depends only on the call structure, so the same module always runs
-        on the same stream (twice-invoked cells update their BatchNorm statistics and weight gradients in program order)."""
+        """run independent pieces of the pass concurrently: thunk i on its own side stream, forked from and joined to the
+        current stream with events.  Stream indices are assigned by CALL STRUCTURE: the thunks of one call get consecutive
+        indices, everything a thunk forks in turn is numbered above all indices its earlier siblings used, and two calls made one
+        after the other inside the same thunk get the SAME indices.  So a module always runs on the same stream: the two
+        invocations of a twice-run cell (model_search.py:326-329) stay ordered -- BatchNorm running statistics are updated in
+        program order and the in-place gradient accumulations of the backward never race."""
         if not self.use_streams or len(thunks) < 2:
             return [t() for t in thunks]
         base = self._stream_cursor
-        while len(self._streams) < base + len(thunks):
+        top = base + len(thunks)
+        while len(self._streams) < top:
             self._streams.append(torch.cuda.Stream(device=self.dev))
-        self._stream_cursor = base + len(thunks)
-        self._par_depth += 1
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(main)
@@ -237,22 +239,30 @@ class PassContext:
             for i, t in enumerate(thunks):
                 s = self._streams[base + i]
                 s.wait_event(fork)
+                self._stream_cursor = top          # whatever this thunk forks is numbered above its earlier siblings' forks
+                self._child_top = top
                 with torch.cuda.stream(s):
                     outs.append(t())
                     e = torch.cuda.Event()
                     e.record(s)
                     joins.append(e)
+                top = max(top, self._child_top)
         finally:
-            self._par_depth -= 1
-            if self._par_depth == 0:
-                self._stream_cursor = 0
+            self._stream_cursor = base
+            self._child_top = max(getattr(self, "_child_top", 0), top)
         for e in joins:
             main.wait_event(e)
         return outs
 
     # ---- one planned forward + backward on the tape ------------------------------------------------------------------
+    def _peer_begin(self, direction):
+        """data parallel: the SyncBN exchanges of this pass belong to one region of the peer-memory protocol (csrc/peer.cu)"""
+        if engine.dp_native():
+            _lib.check(_lib.lib().fsb_peer_begin(2 * self.index + direction, F_._stream()), "fsb_peer_begin")
+
     def _run_forward(self):
         self._wcount = self._bcount = 0
+        self._peer_begin(0)
         tape = AG.Tape(streams=self.use_streams)
         prev_tape, prev_ctx = AG._TAPE, engine._GRAPH_CTX
         AG._TAPE, engine._GRAPH_CTX = tape, self
@@ -264,6 +274,7 @@ class PassContext:
         return tape, list(outs)
 
     def _run_backward(self, tape, outs, dlogits):
+        self._peer_begin(1)
         prev_ctx = engine._GRAPH_CTX
         engine._GRAPH_CTX = self
         try:
@@ -409,7 +420,7 @@ class GraphedLoss:
         key = (arch_idx, tuple(x.shape))
         ctx = self.contexts.get(key)
         if ctx is None:
-            ctx = PassContext(self.model, arch_idx, self.flat, tuple(x.shape), self.capture)
+            ctx = PassContext(self.model, arch_idx, self.flat, tuple(x.shape), self.capture, index=len(self.contexts))
             with torch.no_grad():
                 ctx.X.copy_(x)
             ctx.build()
@@ -493,5 +504,15 @@ class GraphedLoss:
                 w = idx.cpu().numpy()[ctx.sel_slots]
                 touched[ctx.sel_param_index[np.arange(len(w)), w].reshape(-1)] = True
         params = self.flat.params
+        world = engine.dp_world_size()
+        if world > 1:
+            # data parallel: ONE all-reduce of the flat staging buffer (the whole step's gradients, 4 bytes per parameter) and the
+            # mean over ranks folded into the release scale; mixing-weight gradients likewise (tiny)
+            torch.distributed.all_reduce(self.flat.S)
+            scale = scale / world
+            for g in grads:
+                if g is not None:
+                    torch.distributed.all_reduce(g)
+                    g.div_(world)
         self.flat.release([params[i] for i in np.nonzero(touched)[0]], scale)
         return grads

@@ -38,15 +38,38 @@ def init_from_env(backend: Optional[str] = None, sync_bn: bool = True):
             dist.init_process_group(backend)
     if sync_bn:
         engine.enable_sync_bn(world > 1)
-    if world > 1 and os.environ.get("FSB_NATIVE_DP", "0") == "1" and torch.cuda.is_available():
-        init_native_dp()   # EXPERIMENTAL (default off): SyncBN exchange inside the fused training units
+    if world > 1 and os.environ.get("FSB_NATIVE_DP", "1") == "1" and torch.cuda.is_available() and dist.get_backend() == "nccl":
+        init_native_dp()   # SyncBN exchange inside the fused training units, over NVLink peer memory
     return rank, local_rank, world
 
 
 def init_native_dp(group=None):
-    """Give libfsb200 its own NCCL communicator over the ranks of `group`: rank 0 creates the 128-byte id, it travels through
-    torch.distributed, every rank joins with its current device.  Afterwards `engine.dp_native()` is True and the fused
-    training units all-reduce their BatchNorm statistics themselves (no host work per unit)."""
+    """Library-owned SyncBN exchange over NVLink peer memory (csrc/peer.cu): every rank allocates its exchange buffer, the
+    64-byte CUDA IPC handles are all-gathered through torch.distributed, every rank maps its peers.  Afterwards
+    `engine.dp_native()` is True: the fused training units exchange their BatchNorm statistics themselves, on the stream, with
+    no host work -- also inside the captured passes of graphed.py.  (Gradients go through ONE torch.distributed / NCCL
+    all-reduce of the flat staging buffer per step.)"""
+    import ctypes
+
+    from . import _lib
+    lib = _lib.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    handle = (ctypes.c_char * 64)()
+    _lib.check(lib.fsb_peer_alloc(handle), "fsb_peer_alloc")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    blob = b"".join(bytes(t.cpu().tolist()) for t in gathered)
+    _lib.check(lib.fsb_peer_open(blob, rank, world), "fsb_peer_open")
+    dist.barrier(group=group)
+    engine._SYNC_BN["native"] = True
+    return world
+
+
+def init_native_dp_nccl(group=None):
+    """(superseded by init_native_dp) give libfsb200 its own NCCL communicator for fsb_dp_allreduce_f32 on large buffers"""
     import ctypes
 
     from . import _lib

@@ -227,10 +227,12 @@ int fsb_affine_act_sel(int64_t pixels, int C, const void* x, int x_cstride, cons
 int fsb_bn_bwd_reduce_sel(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
                           int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, int relu, float* sums,
                           const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream);
+/* local_sums (may be NULL): under data parallelism `sums` are the all-reduced sums (they shape draw) while gamma / beta
+ * gradients must come from this rank's own sums -- the gradient average over ranks divides by the world size afterwards. */
 int fsb_bn_bwd_apply_sel(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, const void* raw,
-                         int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, const float* sums, double count,
-                         int relu, void* draw, int draw_cstride, float gscale, const fsb_bn_sel* sel, const int* width_idx, int hmax,
-                         void* stream);
+                         int raw_cstride, int raw_is_f32, const float* mean, const float* invstd, const float* sums,
+                         const float* local_sums, double count, int relu, void* draw, int draw_cstride, float gscale,
+                         const fsb_bn_sel* sel, const int* width_idx, int hmax, void* stream);
 /* dy_in = dy * (y > 0)  (ReLU backward for affine-free paths) */
 int fsb_relu_bwd(int64_t pixels, int C, const void* dy, int dy_cstride, const void* y, int y_cstride, void* dx, int dx_cstride,
                  void* stream);
@@ -310,6 +312,22 @@ int fsb_dp_world(void);
 int fsb_dp_enable(int on); /* 0: keep the communicator but behave single-process (fsb_dp_world() == 1) until re-enabled */
 int fsb_dp_allreduce_f32(void* buf, int64_t n, void* stream);
 int fsb_dp_shutdown(void);
+
+/* Peer-memory exchange for the latency-bound part of data parallelism: the per-unit SyncBN statistics (<= 4096 floats each,
+ * ~7 000 per supernet step), summed over the ranks IN RANK ORDER by a single-block kernel through buffers the ranks map into
+ * each other with CUDA IPC (NVLink / NVSwitch peer access) -- no host involvement, capturable in CUDA graphs, bit-identical
+ * results on every rank.  Launcher: every rank calls fsb_peer_alloc (64-byte IPC handle out), all-gathers the handles by any
+ * means, calls fsb_peer_open(all handles, rank, world) and barriers.  From then on fsb_dp_world() == world, the fused training
+ * units exchange through peer memory, and fsb_dp_allreduce_f32 still serves large buffers (NCCL, if fsb_dp_init was called).
+ * Exchanges are issued inside REGIONS (fsb_peer_begin(region, stream): one per captured graph / eager pass); every rank must
+ * issue the same regions with the same sequence of exchanges. */
+int fsb_peer_alloc(void* handle_out64);
+int fsb_peer_open(const void* handles, int rank, int world);
+int fsb_peer_world(void);
+int fsb_peer_enable(int on);
+int fsb_peer_begin(int region, void* stream);
+int fsb_peer_allreduce_f32(void* buf, int64_t n, void* stream);
+int fsb_peer_shutdown(void);
 
 #ifdef __cplusplus
 }

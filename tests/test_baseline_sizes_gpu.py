@@ -157,10 +157,10 @@ def test_supernet_16_layer_loss_and_gradients_at_baseline_size(case):
     for k in sel:
         g = grads[k].detach().float().cpu().numpy()
         ref = z["%s.ref/grad:%s" % (case, k)]
-        if g.ndim == 4 and g.shape != ref.shape:
+        if g.ndim == 4 and g.nbytes > 150_000:       # the strides oracle/make_golden_baseline.py:_strided applied
             g = g[::4, ::4]
-            if g.shape != ref.shape:
-                g = g[::2, ::2]
+        if g.ndim == 4 and g.nbytes > 40_000:
+            g = g[::2, ::2]
         assert g.shape == ref.shape, (k, g.shape, ref.shape)
         e_ours.append(H.rel_err(g, ref))
     e_ours = np.array(e_ours)

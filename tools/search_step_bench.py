@@ -78,7 +78,11 @@ def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape
     if criterion == "ohem":
         from fasterseg_b200.losses import ProbOhemCrossEntropy2d
         model._criterion = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=int(B * (H // 8) * (W // 8) // 16))
-    sync = parallel.GradSync(list(model.parameters())).install() if world > 1 else None
+    from fasterseg_b200 import engine
+    # captured passes with the library-owned exchange all-reduce their flat gradient buffer themselves (graphed.py); the
+    # hook-based GradSync is for the eager per-unit path
+    graph_dp = world > 1 and engine.dp_native() and graph is not False
+    sync = parallel.GradSync(list(model.parameters())).install() if (world > 1 and not graph_dp) else None
 
     def step():
         if args.mode == "search":
