@@ -422,7 +422,8 @@ def affine_act_sel(x, scale, shift, sel, hmax, relu=False):
     return affine_act(x, scale, shift, relu=relu)
 
 
-def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0):
+def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0, world=1):
+    assert world == 1, "the CPU stand-in has no peer exchange (SyncBN over sel kernels is covered on the GPU)"
     bn = _sel_bn(sel)
     Ca, Cc = bn.num_features, dy.shape[1]
     perm = _split_perm(Ca // 2, hmax) if hmax else None

@@ -131,6 +131,55 @@ def test_conv_tc3_channel_major_kernel(case, lib_option):
     assert float((y0.float() - y.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
+# CTA-pair row-rolling kernel (conv_tc4.cu): 3x3 stride-1, Cin % 64 == 0, Cout % 64 == 0, >= 96 output columns; forced on so the
+# small cases below reach it.  The cases cover: resident weights (64->64) and streamed weights with lagged row pairs
+# (128->128), recycled input-row slots (many rows per CTA), ragged strips (Wo % 128 != 0), an odd job count (inert
+# partner CTA), batch > 1, Cin = 192 (3 channel chunks), Cout = 192 / 256.
+TC4_CASES = [
+    # N, Cin, Cout, H, W
+    (1, 128, 128, 16, 256),    # heads8-like: streamed weights, R rows in lagged pairs
+    (1, 64, 64, 40, 256),      # stem.1.conv2-like: resident weights
+    (1, 64, 64, 600, 128),     # R = 5 rows per CTA at 148 SMs: every input row loaded once, 120 jobs
+    (1, 64, 64, 1500, 128),    # R = 11 > row slots: the input-row ring recycles
+    (1, 128, 128, 700, 128),   # streamed weights, R = 5 (groups of 2 + a single row), recycled rows
+    (2, 64, 128, 9, 200),      # ragged strip (200 = 128 + 72), batch 2, 18 x 2 = 36 jobs
+    (1, 64, 64, 7, 130),       # 2 strips x 7 rows = 14 jobs, second strip 2 columns wide
+    (3, 64, 64, 5, 128),       # 15 jobs: odd -> one inert partner CTA
+    (1, 192, 128, 12, 128),    # 3 channel chunks
+    (1, 128, 256, 6, 128),     # N = 256 (one accumulator), 2 channel chunks
+    (1, 64, 192, 10, 256),     # N = 192
+]
+
+
+@pytest.mark.parametrize("case", TC4_CASES)
+def test_conv_tc4_cta_pair_kernel(case, lib_option):
+    F_ = _F()
+    from fasterseg_b200 import _lib
+    import ctypes as C
+    lib_option("FSB_CONV_TC4", 2)
+    N, Cin, Cout, Hh, Ww = case
+    seed = hash(case) % 100000
+    x = _rand((N, Cin, Hh, Ww), seed).half().float()
+    w = (_rand((Cout, Cin, 3, 3), seed + 1) * (2.0 / (Cin * 9)) ** 0.5).half().float()
+    scale = torch.from_numpy(np.random.RandomState(seed + 2).uniform(0.5, 1.5, Cout).astype(np.float32))
+    shift = _rand((Cout,), seed + 3, 0.2)
+    ref = torch.relu(orc.conv2d(x, w, None, 1, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    wp = F_.pack_conv_weight(w.cuda(), Cin, Cout, 3)
+    cat = F_.empty_nhwc(N, Cout + 64, Hh, Ww, "cuda")
+    cat.fill_(7.0)
+    out = cat[:, 32:32 + Cout]
+    d = _lib.ConvDesc(N, Hh, Ww, Cin, Cout, 3, 1, 1, 1, 0, 0, Hh, Ww, Cin, Cout + 64, _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE)
+    assert _lib.lib().fsb_conv_kernel_id(C.byref(d), C.c_void_p(out.data_ptr()), 0) == 4, "case does not reach the pair kernel"
+    y = F_.conv_fwd(_nhwc(x), wp, Cout, 3, 1, 1, scale.cuda(), shift.cuda(), relu=True, out=out)
+    torch.cuda.synchronize()
+    _close(y.float().cpu(), ref)
+    assert float((cat[:, :32] - 7.0).abs().max()) == 0.0 and float((cat[:, 32 + Cout:] - 7.0).abs().max()) == 0.0
+    lib_option("FSB_CONV_TC4", 0)
+    y0 = F_.conv_fwd(_nhwc(x), wp, Cout, 3, 1, 1, scale.cuda(), shift.cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert float((y0.float() - y.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
 def test_statistics_are_bit_reproducible():
     """conv with fused statistics, bn_stats, bn_bwd sums and wsum scalar gradients: no floating-point atomics -> the same call
     gives the same bits every time (round 1 differed run to run)."""
