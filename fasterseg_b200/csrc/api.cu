@@ -40,7 +40,7 @@ int sm_count() {
 
 static const char* const kOptNames[OPT_COUNT] = {"FSB_CONV_TC2", "FSB_TC2_R", "FSB_TC2_ASTAGES", "FSB_NO_TMA_STORE",
                                                  "FSB_DGRAD_S2_DIRECT", "FSB_WGRAD_TC", "FSB_CONV_PERSIST", "FSB_PERSIST_OCC",
-                                                 "FSB_PERSIST_STAGES", "FSB_UPSAMPLE_V2", "FSB_DETERMINISTIC", "FSB_CONV_TC3", "FSB_CONV_TC4"};
+                                                 "FSB_PERSIST_STAGES", "FSB_UPSAMPLE_V2", "FSB_DETERMINISTIC", "FSB_CONV_TC3", "FSB_CONV_TC4", "FSB_CONV_TC5"};
 static int g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void load_opts() {
@@ -197,6 +197,7 @@ int fsb_conv_stats_rows(const fsb_conv_desc* d) {
 int fsb_conv_kernel_id(const fsb_conv_desc* d, const void* y, int with_stats) {
   if (check_desc(d)) return -1;
   if ((d->flags & FSB_CONV_FORCE_DIRECT) || !conv_tc_supported(d)) return 0;
+  if (!with_stats && conv_tc5_supported(d, y)) return 5;
   if (!with_stats && conv_tc4_supported(d, y)) return 4;
   if (!with_stats && conv_tc3_supported(d, y)) return 3;
   if (conv_tc2_supported(d)) return 2;

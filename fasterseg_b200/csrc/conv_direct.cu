@@ -317,13 +317,16 @@ stem_conv_tc_kernel(int N, int H, int W, int Cout, int npad, const TIn* __restri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  if (t == 0) {
+  if (t < 32) {   // converged warp 0, elected lane issues (uniform operands: no per-instruction waterfall)
     const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(npad));
     const uint64_t da = umma_desc_kmajor(smem_u32(s_a), 64);
     const uint64_t db = umma_desc_kmajor(smem_u32(s_b), 64);
-    umma_f16_ss(tmem, da, db, idesc, 0u);
-    umma_f16_ss(tmem, da + 2, db + 2, idesc, 1u);
-    umma_commit(&s_bar);
+    if (elect_one()) {
+      umma_f16_ss(tmem, da, db, idesc, 0u);
+      umma_f16_ss(tmem, da + 2, db + 2, idesc, 1u);
+      umma_commit(&s_bar);
+    }
+    __syncwarp();
   }
   mbar_wait(&s_bar, 0);
   tc_fence_after();

@@ -55,7 +55,7 @@ struct ConvTcParams {
 };
 
 template <int BK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)   // <= 170 registers: two CTAs per SM (96 KB pipelines) on the large maps
 conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -111,48 +111,58 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // Issue style (tools/umma_rate.cu): the producer and MMA warps stay CONVERGED and only the TMA / MMA instructions themselves
+  // sit under elect.sync.  Inside an `if (lane == 0)` region the compiler has to wrap every uniform-datapath instruction
+  // (UTMALDG, UTCHMMA, UTCBAR) into an ELECT / R2UR / BRA.U.ANY waterfall, which cost ~130 cycles per MMA in round 1.
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int it = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
-        const int cw = w0 + p.tap_dw[tap];
-        const int chh = h0 + p.tap_dh[tap];
-        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-          const int s = it % p.stages;
-          const int round = it / p.stages;
-          if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-          uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-          tma_load_4d(sa, ma, &full_bar[s], kc * BK, cw, chh, img);
-          tma_load_3d(sb, &p.tmap_b, &full_bar[s], kc * BK, n0, p.tap_widx[tap]);
+    RingPos rp;
+    uint8_t* sa = smem;
+    for (int tap = 0; tap < p.taps; ++tap) {
+      const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
+      const int cw = w0 + p.tap_dw[tap];
+      const int chh = h0 + p.tap_dh[tap];
+      const int wi = p.tap_widx[tap];
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&empty_bar[rp.s], rp.phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[rp.s], stage_bytes);
+          tma_load_4d(sa, ma, &full_bar[rp.s], kc * BK, cw, chh, img);
+          tma_load_3d(sa + kABytes, &p.tmap_b, &full_bar[rp.s], kc * BK, n0, wi);
         }
+        __syncwarp();
+        sa += stage_bytes;
+        rp.advance(p.stages);
+        if (rp.s == 0) sa = smem;
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(p.n_tile));
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % p.stages;
-        const int round = it / p.stages;
-        mbar_wait(&full_bar[s], round & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t sb = sa + kABytes;
-        const uint64_t da = umma_desc_kmajor(sa, BK * 2);
-        const uint64_t db = umma_desc_kmajor(sb, BK * 2);
+    // ================= MMA issuer (converged warp, one elected lane issues) =================
+    // Lean loop: no integer division, descriptors of stage s = descriptors of stage 0 + s * (stage_bytes >> 4) in the
+    // start-address field (shared-memory addresses stay below 256 KB, so the 14-bit field never carries).
+    const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(p.n_tile));
+    const uint32_t sa0 = smem_u32(smem);
+    const uint64_t da0 = umma_desc_kmajor(sa0, BK * 2);
+    const uint64_t db0 = umma_desc_kmajor(sa0 + kABytes, BK * 2);
+    const uint32_t dstep = stage_bytes >> 4;
+    RingPos rp;
+    uint32_t doff = 0;
+    for (int it = 0; it < k_iters; ++it) {
+      mbar_wait(&full_bar[rp.s], rp.phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = da0 + doff, db = db0 + doff;
+        // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+        umma_f16_ss(tmem_base, da, db, idesc, it > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_f16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+        for (int k = 1; k < BK / 16; ++k) umma_f16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, 1u);
+        umma_commit(&empty_bar[rp.s]);  // smem slot reusable once these MMAs retire
+        if (it == k_iters - 1) umma_commit(&tmem_full_bar);   // accumulator complete
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
+      __syncwarp();
+      doff += dstep;
+      rp.advance(p.stages);
+      if (rp.s == 0) doff = 0;
     }
   } else {
     // ================= epilogue warps 2..5 =================
@@ -373,60 +383,62 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvTcParams p) {
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ================= TMA producer: one ring across all tiles of this CTA =================
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * p.n_tile;
-        int t = tile / p.n_tiles;
-        const int w0 = (t % p.tiles_w) * p.tw;
-        t /= p.tiles_w;
-        const int h0 = (t % p.tiles_h) * p.th;
-        const int img = t / p.tiles_h;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
-          const int cw = w0 + p.tap_dw[tap];
-          const int chh = h0 + p.tap_dh[tap];
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-            const int s = it % p.stages;
-            const int round = it / p.stages;
-            if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-            uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
-            uint8_t* sb = sa + kABytes;
+    // ================= TMA producer: one ring across all tiles of this CTA (converged warp, elected issue) =================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.n_tiles) * p.n_tile;
+      int t = tile / p.n_tiles;
+      const int w0 = (t % p.tiles_w) * p.tw;
+      t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * p.th;
+      const int img = t / p.tiles_h;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
+        const int cw = w0 + p.tap_dw[tap];
+        const int chh = h0 + p.tap_dh[tap];
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          const int round = it / p.stages;
+          if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+          uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
             tma_load_4d(sa, ma, &full_bar[s], kc * BK, cw, chh, img);
             tma_load_3d(sb, &p.tmap_b, &full_bar[s], kc * BK, n0, p.tap_widx[tap]);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer: alternates between the two TMEM accumulators =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(p.n_tile));
-      int it = 0;
-      int lt = 0;  // tiles done by this CTA
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        const int use = lt >> 1;  // how often this accumulator has been used before
-        if (use > 0) mbar_wait(&tmem_empty_bar[buf], (use - 1) & 1);  // epilogue of its previous tile has drained it
+    const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(p.n_tile));
+    int it = 0;
+    int lt = 0;  // tiles done by this CTA
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int use = lt >> 1;  // how often this accumulator has been used before
+      if (use > 0) mbar_wait(&tmem_empty_bar[buf], (use - 1) & 1);  // epilogue of its previous tile has drained it
+      tc_fence_after();
+      const uint32_t acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
+      for (int ki = 0; ki < k_iters; ++ki, ++it) {
+        const int s = it % p.stages;
+        const int round = it / p.stages;
+        mbar_wait(&full_bar[s], round & 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
-        for (int ki = 0; ki < k_iters; ++ki, ++it) {
-          const int s = it % p.stages;
-          const int round = it / p.stages;
-          mbar_wait(&full_bar[s], round & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t da = umma_desc_kmajor(sa, BK * 2);
-          const uint64_t db = umma_desc_kmajor(sb, BK * 2);
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t sb = sa + kABytes;
+        const uint64_t da = umma_desc_kmajor(sa, BK * 2);
+        const uint64_t db = umma_desc_kmajor(sb, BK * 2);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_ss(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
+          if (ki == k_iters - 1) umma_commit(&tmem_full_bar[buf]);
         }
-        umma_commit(&tmem_full_bar[buf]);
+        __syncwarp();
       }
     }
   } else {

@@ -115,60 +115,66 @@ conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
   if (threadIdx.x == 0) T2_STAMP(1);
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int bit = 0;
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
-        const int as = kc % p.a_stages;
-        const int around = kc / p.a_stages;
-        if (around > 0) mbar_wait(&a_empty[as], (around - 1) & 1);
-        uint8_t* sa = smem + static_cast<size_t>(as) * a_stage_bytes;
-        mbar_arrive_expect_tx(&a_full[as], static_cast<uint32_t>(rows_in) * kT2Halo * kPix);
+    // ================= TMA producer (converged warp; only the TMA issue is under elect.sync, see conv_tc.cu) =================
+    RingPos ra, rb;
+    for (int kc = 0; kc < p.k_chunks; ++kc) {
+      mbar_wait(&a_empty[ra.s], ra.phase ^ 1u);
+      uint8_t* sa = smem + static_cast<size_t>(ra.s) * a_stage_bytes;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&a_full[ra.s], static_cast<uint32_t>(rows_in) * kT2Halo * kPix);
         for (int i = 0; i < rows_in; ++i)
-          tma_load_4d(sa + static_cast<size_t>(i) * p.rowb, &p.tmap_a, &a_full[as], kc * BK, w0 - 1, h0 - 1 + i, img);
-        for (int tap = 0; tap < 9; ++tap, ++bit) {
-          const int bs = bit % p.b_stages;
-          const int bround = bit / p.b_stages;
-          if (bround > 0) mbar_wait(&b_empty[bs], (bround - 1) & 1);
-          mbar_arrive_expect_tx(&b_full[bs], b_bytes);
-          tma_load_3d(smem_b + static_cast<size_t>(bs) * b_bytes, &p.tmap_b, &b_full[bs], kc * BK, 0, tap);
+          tma_load_4d(sa + static_cast<size_t>(i) * p.rowb, &p.tmap_a, &a_full[ra.s], kc * BK, w0 - 1, h0 - 1 + i, img);
+      }
+      __syncwarp();
+      ra.advance(p.a_stages);
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_wait(&b_empty[rb.s], rb.phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[rb.s], b_bytes);
+          tma_load_3d(smem_b + static_cast<size_t>(rb.s) * b_bytes, &p.tmap_b, &b_full[rb.s], kc * BK, 0, tap);
         }
+        __syncwarp();
+        rb.advance(p.b_stages);
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(p.n_tile));
-      int bit = 0;
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
-        const int as = kc % p.a_stages;
-        mbar_wait(&a_full[as], (kc / p.a_stages) & 1);
-        tc_fence_after();
-        T2_STAMP(2 + kc * 10);
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(as) * a_stage_bytes);
-        for (int tap = 0; tap < 9; ++tap, ++bit) {
-          const int bs = bit % p.b_stages;
-          mbar_wait(&b_full[bs], (bit / p.b_stages) & 1);
+    // ================= MMA issuer (converged warp, elected lane issues, division-free rings) =================
+    const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(p.n_tile));
+    const uint64_t db0 = umma_desc_kmajor(smem_u32(smem_b), kPix);
+    const uint32_t bstep = b_bytes >> 4;
+    RingPos ra, rb;
+    for (int kc = 0; kc < p.k_chunks; ++kc) {
+      mbar_wait(&a_full[ra.s], ra.phase);
+      tc_fence_after();
+      if (lane == 0) T2_STAMP(2 + kc * 10);
+      const uint32_t sa = smem_u32(smem + static_cast<size_t>(ra.s) * a_stage_bytes);
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(&b_full[rb.s], rb.phase);
           tc_fence_after();
-          if (kc < 2) T2_STAMP(3 + kc * 10 + tap);
-          const int r = tap / 3, s = tap % 3;
-          const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + static_cast<size_t>(bs) * b_bytes), kPix);
-          for (int j = 0; j < p.R; ++j) {
-            const uint32_t a_addr = sa + static_cast<uint32_t>(j + r) * p.rowb + static_cast<uint32_t>(s) * kPix;
-            const uint64_t da = umma_desc_kmajor(a_addr, kPix);
-            const uint32_t tm = tmem_base + static_cast<uint32_t>(j * p.n_tile);
+          const uint64_t db = db0 + static_cast<uint32_t>(rb.s) * bstep;
+          if (elect_one()) {
+            uint32_t a_addr = sa + static_cast<uint32_t>(r) * p.rowb + static_cast<uint32_t>(s) * kPix;
+            uint32_t tm = tmem_base;
+            for (int j = 0; j < p.R; ++j, a_addr += p.rowb, tm += p.n_tile) {
+              const uint64_t da = umma_desc_kmajor(a_addr, kPix);
+              umma_f16_ss(tm, da, db, idesc, (kc > 0 || r > 0 || s > 0) ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_f16_ss(tm, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                          (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for (int k = 1; k < BK / 16; ++k)
+                umma_f16_ss(tm, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, 1u);
+            }
+            umma_commit(&b_empty[rb.s]);
+            if (r == 2 && s == 2) {
+              umma_commit(&a_empty[ra.s]);
+              if (kc == p.k_chunks - 1) umma_commit(&tmem_full_bar);
+            }
           }
-          umma_commit(&b_empty[bs]);
+          __syncwarp();
+          rb.advance(p.b_stages);
         }
-        umma_commit(&a_empty[as]);
-      }
-      umma_commit(&tmem_full_bar);
-      T2_STAMP(40);
+      ra.advance(p.a_stages);
     }
+    if (lane == 0) T2_STAMP(40);
   } else {
     // ================= epilogue warps 2..5 =================
     const int q = warp & 3;

@@ -87,42 +87,51 @@ conv_tc3_kernel(const __grid_constant__ ConvTc3Params p) {
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int it = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const CUtensorMap* mx = &p.tmap_x[p.tap_map[tap]];
-        const int cw = w0 + p.tap_dw[tap];
-        const int chh = h0 + p.tap_dh[tap];
-        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-          const int s = it % p.stages;
-          const int round = it / p.stages;
-          if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-          uint8_t* sw = smem + static_cast<size_t>(s) * k3StageBytes;
-          uint8_t* sx = sw + k3WBytes;
-          mbar_arrive_expect_tx(&full_bar[s], k3StageBytes);
-          tma_load_3d(sw, &p.tmap_w, &full_bar[s], kc * k3BK, m0, p.tap_widx[tap]);
-          tma_load_4d(sx, mx, &full_bar[s], kc * k3BK, cw, chh, img);
+    // ================= TMA producer (converged warp, elected issue, division-free ring: see conv_tc.cu) =================
+    RingPos rp;
+    uint8_t* sw = smem;
+    for (int tap = 0; tap < p.taps; ++tap) {
+      const CUtensorMap* mx = &p.tmap_x[p.tap_map[tap]];
+      const int cw = w0 + p.tap_dw[tap];
+      const int chh = h0 + p.tap_dh[tap];
+      const int wi = p.tap_widx[tap];
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&empty_bar[rp.s], rp.phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[rp.s], k3StageBytes);
+          tma_load_3d(sw, &p.tmap_w, &full_bar[rp.s], kc * k3BK, m0, wi);
+          tma_load_4d(sw + k3WBytes, mx, &full_bar[rp.s], kc * k3BK, cw, chh, img);
         }
+        __syncwarp();
+        sw += k3StageBytes;
+        rp.advance(p.stages);
+        if (rp.s == 0) sw = smem;
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer: D[co, pixel] += W[co, k] * X[pixel, k]^T =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(128, k3TilePix);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % p.stages;
-        mbar_wait(&full_bar[s], (it / p.stages) & 1);
-        tc_fence_after();
-        const uint32_t sw = smem_u32(smem + static_cast<size_t>(s) * k3StageBytes);
-        const uint64_t da = umma_desc_kmajor(sw, 128);
-        const uint64_t db = umma_desc_kmajor(sw + k3WBytes, 128);
+    const uint32_t idesc = umma_idesc_f16(128, k3TilePix);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t da0 = umma_desc_kmajor(s0, 128);
+    const uint64_t db0 = umma_desc_kmajor(s0 + k3WBytes, 128);
+    RingPos rp;
+    uint32_t doff = 0;
+    for (int it = 0; it < k_iters; ++it) {
+      mbar_wait(&full_bar[rp.s], rp.phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = da0 + doff, db = db0 + doff;
+        umma_f16_ss(tmem_base, da, db, idesc, it > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < k3BK / 16; ++k)
-          umma_f16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
+        for (int k = 1; k < k3BK / 16; ++k)
+          umma_f16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, 1u);
+        umma_commit(&empty_bar[rp.s]);
+        if (it == k_iters - 1) umma_commit(&tmem_full_bar);
       }
-      umma_commit(&tmem_full_bar);
+      __syncwarp();
+      doff += k3StageBytes >> 4;
+      rp.advance(p.stages);
+      if (rp.s == 0) doff = 0;
     }
   } else {
     // ================= epilogue warps 2..5: thread = output channel (TMEM lane), columns = pixels =================

@@ -157,46 +157,53 @@ conv_tc4_kernel(const __grid_constant__ ConvTc4Params p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // Issue style: the three issuing warps stay converged; only the TMA / MMA / commit instructions are under elect.sync (inside an
+  // `if (lane == 0)` region every uniform-datapath instruction becomes an ELECT / R2UR / BRA.U.ANY waterfall, ~130 cycles per MMA).
   if (warp == 0) {
     // ================= input-row producer (both CTAs, own pixels) =================
-    if (lane == 0) {
-      const int first = in_rows < p.NR ? in_rows : p.NR;
-      // initial fill: chunk-major so the first MMAs (chunk 0 of rows 0..2) can start early
-      for (int kc = 0; kc < p.kch; ++kc)
-        for (int i = 0; i < first; ++i) {
-          uint64_t* bar = &a_full[i * p.kch + kc];
+    const int first = in_rows < p.NR ? in_rows : p.NR;
+    // initial fill: chunk-major so the first MMAs (chunk 0 of rows 0..2) can start early
+    for (int kc = 0; kc < p.kch; ++kc)
+      for (int i = 0; i < first; ++i) {
+        uint64_t* bar = &a_full[i * p.kch + kc];
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(bar, 2 * k4RowTx);
           tma_load_4d_2sm(smem_a + static_cast<size_t>(i) * slot_bytes + static_cast<size_t>(kc) * k4RowBytes, &p.tmap_x, bar, kc * 64,
                           w0 - 1, h0 - 1 + i, img);
         }
-      for (int i = first; i < in_rows; ++i) {
-        const int slot = i % p.NR, use = i / p.NR;
-        mbar_wait(&a_empty[slot], (use - 1) & 1);
-        for (int kc = 0; kc < p.kch; ++kc) {
-          uint64_t* bar = &a_full[slot * p.kch + kc];
+        __syncwarp();
+      }
+    for (int i = first; i < in_rows; ++i) {
+      const int slot = i % p.NR, use = i / p.NR;
+      mbar_wait(&a_empty[slot], (use - 1) & 1);
+      for (int kc = 0; kc < p.kch; ++kc) {
+        uint64_t* bar = &a_full[slot * p.kch + kc];
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(bar, 2 * k4RowTx);
           tma_load_4d_2sm(smem_a + static_cast<size_t>(slot) * slot_bytes + static_cast<size_t>(kc) * k4RowBytes, &p.tmap_x, bar, kc * 64,
                           w0 - 1, h0 - 1 + i, img);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
     // ================= weight producer (both CTAs, own half of the output channels) =================
-    if (lane == 0) {
-      const int passes = p.resident ? 1 : groups;
-      int idx = 0;
-      for (int ps = 0; ps < passes; ++ps)
-        for (int tt = 0; tt < p.T; ++tt, ++idx) {
-          const int bs = idx % p.NB, use = idx / p.NB;
-          if (use > 0) mbar_wait(&b_empty[bs], (use - 1) & 1);
+    const int passes = p.resident ? 1 : groups;
+    int idx = 0;
+    for (int ps = 0; ps < passes; ++ps)
+      for (int tt = 0; tt < p.T; ++tt, ++idx) {
+        const int bs = idx % p.NB, use = idx / p.NB;
+        if (use > 0) mbar_wait(&b_empty[bs], (use - 1) & 1);
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * b_bytes);
           tma_load_3d_2sm(smem_b + static_cast<size_t>(bs) * b_bytes, &p.tmap_w, &b_full[bs], (tt / 9) * 64, static_cast<int>(rank) * p.n_half,
                           tt % 9);
         }
-    }
+        __syncwarp();
+      }
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA, one thread) =================
-    if (lane == 0 && rank == 0) {
+    // ================= MMA issuer (leader CTA; converged warp, one elected lane issues) =================
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_f16(256, static_cast<uint32_t>(p.Cout));
       const bool recycle = in_rows > p.NR;
       for (int grp = 0; grp < groups; ++grp) {
@@ -226,14 +233,17 @@ conv_tc4_kernel(const __grid_constant__ ConvTc4Params p) {
                                                      static_cast<uint32_t>(s) * 128u, 128);
             const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + static_cast<size_t>(bs) * b_bytes), 128);
             const uint32_t acc = tmem_base + static_cast<uint32_t>(a * p.Cout);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (tt > 0 || k > 0) ? 1u : 0u);
-            if (!p.resident && g == gcur - 1) umma_commit_2sm(&b_empty[bs]);   // last row of the pass has consumed this tile
-            if (tt == p.T - 1) {
-              umma_commit_2sm(&tmem_full[a]);
-              if (recycle) umma_commit_2sm(&a_empty[j % p.NR]);   // input row j is not needed by any later output row
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ss_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (tt > 0 || k > 0) ? 1u : 0u);
+              if (!p.resident && g == gcur - 1) umma_commit_2sm(&b_empty[bs]);   // last row of the pass has consumed this tile
+              if (tt == p.T - 1) {
+                umma_commit_2sm(&tmem_full[a]);
+                if (recycle) umma_commit_2sm(&a_empty[j % p.NR]);   // input row j is not needed by any later output row
+              }
             }
+            __syncwarp();
           }
         }
       }
@@ -339,7 +349,7 @@ static Tc4Plan conv_tc4_plan(const fsb_conv_desc* d) {
   const size_t slot = static_cast<size_t>(q.kch) * k4RowBytes;
   const size_t b_bytes = static_cast<size_t>(q.n_half) * 128;
   const size_t staging = static_cast<size_t>(d->Cout / 64) * (k4Cols * 128);
-  const size_t budget = 222 * 1024 - staging - 1024;
+  const size_t budget = 220 * 1024 - staging - 1024;   // dynamic + 3.2 KB static <= 227 KB opt-in limit
   const int in_rows = R + 2;
   // resident weights when they leave room for at least 4 row slots (or every input row of the job)
   const int need_rows = in_rows < 4 ? in_rows : 4;
@@ -430,7 +440,7 @@ int conv_tc4_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
     const uint32_t box[4] = {64u, static_cast<uint32_t>(k4Cols), 1u, 1u};
     if (int rc = encode_tiled_generic(&p.tmap_y, y, 4, dims, str, box, 128)) return rc;
   }
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc4_kernel), 227 * 1024, "cudaFuncSetAttribute(conv_tc4)")) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc4_kernel), 222 * 1024, "cudaFuncSetAttribute(conv_tc4)")) return rc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>((q.jobs + 1) & ~1));

@@ -60,9 +60,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The slow path lives out of line: the
+// waits sit inside the single-warp TMA / MMA issue loops, whose instruction count per iteration bounds the tensor-pipe feed
+// rate (tools/umma_rate.cu: ~50 dependent instructions cost as much as two 128x128x16 MMAs).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
@@ -71,6 +72,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
+// Position in a ring of `n` stages with the phase parity of the current round; advanced without integer division.
+// Consumer side: wait(full[s], phase).  Producer side: wait(empty[s], phase ^ 1) -- on a freshly initialised barrier the
+// "previous" phase counts as complete, so the first round does not block.
+struct RingPos {
+  int s;
+  uint32_t phase;
+  __device__ __forceinline__ RingPos() : s(0), phase(0) {}
+  __device__ __forceinline__ void advance(int n) {
+    if (++s == n) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, global -> shared, completion on an mbarrier

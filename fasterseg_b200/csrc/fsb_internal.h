@@ -47,6 +47,7 @@ enum Opt {
   OPT_DETERMINISTIC,     // FSB_DETERMINISTIC: 1 = weight gradients without split-K atomics (bit-reproducible steps)
   OPT_CONV_TC3,          // FSB_CONV_TC3: 0 = never use the channel-major 128x256 kernel, 2 = force it wherever it is supported
   OPT_CONV_TC4,          // FSB_CONV_TC4: 0 = never use the CTA-pair row-rolling kernel, 2 = force it wherever it is supported
+  OPT_CONV_TC5,          // FSB_CONV_TC5: 0 = never use the tap-concatenated kernel (Cout <= 64), 2 = force it wherever it is supported
   OPT_COUNT
 };
 int opt(Opt o);
@@ -103,6 +104,9 @@ int conv_tc2_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
 int conv_tc3_supported(const fsb_conv_desc* d, const void* y);
 int conv_tc3_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift, void* y,
                     cudaStream_t stream);
+int conv_tc5_supported(const fsb_conv_desc* d, const void* y);
+int conv_tc5_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift, void* y,
+                    cudaStream_t stream);
 int conv_tc4_supported(const fsb_conv_desc* d, const void* y);
 int conv_tc4_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift, void* y,
                     cudaStream_t stream);
@@ -110,6 +114,7 @@ int conv_tc4_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
 // convs with few output channels, the per-tap kernel otherwise
 inline int conv_tc_dispatch(const fsb_conv_desc* d, const void* x, const void* wpacked, const float* scale, const float* shift,
                             void* y, float* stats, cudaStream_t stream) {
+  if (!stats && conv_tc5_supported(d, y)) return conv_tc5_launch(d, x, wpacked, scale, shift, y, stream);
   if (!stats && conv_tc4_supported(d, y)) return conv_tc4_launch(d, x, wpacked, scale, shift, y, stream);
   if (!stats && conv_tc3_supported(d, y)) return conv_tc3_launch(d, x, wpacked, scale, shift, y, stream);
   if (conv_tc2_supported(d)) return conv_tc2_launch(d, x, wpacked, scale, shift, y, stats, stream);

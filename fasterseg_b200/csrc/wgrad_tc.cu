@@ -104,35 +104,45 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
   if (n_iters <= 0) {
     // nothing to do for this chunk (more chunks than tiles): fall through to the common teardown
   } else if (warp == 0) {
-    if (lane == 0) {
-      const CUtensorMap* mx = &p.tmap_x[p.tap_map[tap]];
-      for (int it = 0; it < n_iters; ++it) {
-        int t = t_begin + it;
-        const int tile_w = t % p.tiles_w;
-        t /= p.tiles_w;
-        const int tile_h = t % p.tiles_h;
-        const int img = t / p.tiles_h;
-        const int w0 = tile_w * p.tw, h0 = tile_h * p.th;
-        const int s = it % p.stages;
-        const int round = it / p.stages;
-        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_4d(st, &p.tmap_dy, &full_bar[s], co0, w0, h0, img);
-        tma_load_4d(st + kWgSub, &p.tmap_dy, &full_bar[s], co0 + 64, w0, h0, img);
+    // converged warp, only the TMA issue under elect.sync (see conv_tc.cu: a divergent single-lane region turns every
+    // uniform-datapath instruction into an ELECT / R2UR / BRA.U.ANY waterfall)
+    const CUtensorMap* mx = &p.tmap_x[p.tap_map[tap]];
+    RingPos rp;
+    uint8_t* st = smem;
+    int tile_w = t_begin % p.tiles_w, tile_h = (t_begin / p.tiles_w) % p.tiles_h, img = t_begin / (p.tiles_w * p.tiles_h);
+    for (int it = 0; it < n_iters; ++it) {
+      const int w0 = tile_w * p.tw, h0 = tile_h * p.th;
+      mbar_wait(&empty_bar[rp.s], rp.phase ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[rp.s], stage_bytes);
+        tma_load_4d(st, &p.tmap_dy, &full_bar[rp.s], co0, w0, h0, img);
+        tma_load_4d(st + kWgSub, &p.tmap_dy, &full_bar[rp.s], co0 + 64, w0, h0, img);
         for (int j = 0; j < n_sub; ++j)
-          tma_load_4d(st + static_cast<size_t>(2 + j) * kWgSub, mx, &full_bar[s], ci0 + j * 64, w0 + p.tap_dw[tap],
+          tma_load_4d(st + static_cast<size_t>(2 + j) * kWgSub, mx, &full_bar[rp.s], ci0 + j * 64, w0 + p.tap_dw[tap],
                       h0 + p.tap_dh[tap], img);
+      }
+      __syncwarp();
+      st += stage_bytes;
+      rp.advance(p.stages);
+      if (rp.s == 0) st = smem;
+      if (++tile_w == p.tiles_w) {   // next spatial tile without integer division
+        tile_w = 0;
+        if (++tile_h == p.tiles_h) {
+          tile_h = 0;
+          ++img;
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16_mn(128, static_cast<uint32_t>(p.ci_tile));
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % p.stages;
-        mbar_wait(&full_bar[s], (it / p.stages) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+    const uint32_t idesc = umma_idesc_f16_mn(128, static_cast<uint32_t>(p.ci_tile));
+    const uint32_t s0 = smem_u32(smem);
+    RingPos rp;
+    uint32_t soff = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(&full_bar[rp.s], rp.phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = s0 + soff;
         const uint32_t sb = sa + 2 * kWgSub;
 #pragma unroll
         for (int k = 0; k < kWgPix / 16; ++k) {
@@ -141,9 +151,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
           const uint64_t db = umma_desc_mnmajor_sw128(sb + k * 2048, kWgSub);
           umma_f16_ss(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&empty_bar[rp.s]);
+        if (it == n_iters - 1) umma_commit(&tmem_full_bar);
       }
-      umma_commit(&tmem_full_bar);
+      __syncwarp();
+      soff += stage_bytes;
+      rp.advance(p.stages);
+      if (rp.s == 0) soff = 0;
     }
   } else {
     const int q = warp & 3;

@@ -180,6 +180,52 @@ def test_conv_tc4_cta_pair_kernel(case, lib_option):
     assert float((y0.float() - y.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
+# tap-concatenated kernel (conv_tc5.cu): 3x3 stride-1, Cin % 64 == 0, Cout in {16, 32, 48, 64}; flattened-pixel tiles of 126 outputs.
+# Cases: tiles crossing image rows (W not a multiple of 126), W smaller than a tile (several rows per tile), single-row images,
+# batch > 1 (tile -> image mapping), 1..4 channel chunks, every supported Cout, more tiles than SMs (persistent loop + both TMEM
+# accumulators reused), zero-copy concat destination.
+TC5_CASES = [
+    # N, Cin, Cout, H, W
+    (1, 64, 64, 24, 256),      # stem.1.conv2-like
+    (1, 64, 32, 33, 100),      # cell0.conv1-like, W < tile
+    (2, 64, 64, 7, 130),       # batch 2, ragged
+    (1, 128, 64, 9, 64),       # two channel chunks, 4.6 rows per tile
+    (1, 192, 48, 5, 37),       # three chunks, Cout = 48, odd sizes
+    (1, 256, 16, 3, 500),      # four chunks, Cout = 16
+    (1, 64, 64, 1, 300),       # a single image row (top and bottom padding in every tile)
+    (3, 64, 64, 160, 128),     # 3 x 163 = 489 tiles > 148 SMs: persistent walk, accumulator ring
+]
+
+
+@pytest.mark.parametrize("case", TC5_CASES)
+def test_conv_tc5_tap_concatenated_kernel(case, lib_option):
+    F_ = _F()
+    from fasterseg_b200 import _lib
+    import ctypes as C
+    lib_option("FSB_CONV_TC5", 2)
+    N, Cin, Cout, Hh, Ww = case
+    seed = hash(case) % 100000
+    x = _rand((N, Cin, Hh, Ww), seed).half().float()
+    w = (_rand((Cout, Cin, 3, 3), seed + 1) * (2.0 / (Cin * 9)) ** 0.5).half().float()
+    scale = torch.from_numpy(np.random.RandomState(seed + 2).uniform(0.5, 1.5, Cout).astype(np.float32))
+    shift = _rand((Cout,), seed + 3, 0.2)
+    ref = torch.relu(orc.conv2d(x, w, None, 1, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    wp = F_.pack_conv_weight(w.cuda(), Cin, Cout, 3)
+    cat = F_.empty_nhwc(N, Cout + 64, Hh, Ww, "cuda")
+    cat.fill_(7.0)
+    out = cat[:, 32:32 + Cout]
+    d = _lib.ConvDesc(N, Hh, Ww, Cin, Cout, 3, 1, 1, 1, 0, 0, Hh, Ww, Cin, Cout + 64, _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE)
+    assert _lib.lib().fsb_conv_kernel_id(C.byref(d), C.c_void_p(out.data_ptr()), 0) == 5, "case does not reach the tap-concatenated kernel"
+    y = F_.conv_fwd(_nhwc(x), wp, Cout, 3, 1, 1, scale.cuda(), shift.cuda(), relu=True, out=out)
+    torch.cuda.synchronize()
+    _close(y.float().cpu(), ref)
+    assert float((cat[:, :32] - 7.0).abs().max()) == 0.0 and float((cat[:, 32 + Cout:] - 7.0).abs().max()) == 0.0
+    lib_option("FSB_CONV_TC5", 0)
+    y0 = F_.conv_fwd(_nhwc(x), wp, Cout, 3, 1, 1, scale.cuda(), shift.cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert float((y0.float() - y.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
 def test_statistics_are_bit_reproducible():
     """conv with fused statistics, bn_stats, bn_bwd sums and wsum scalar gradients: no floating-point atomics -> the same call
     gives the same bits every time (round 1 differed run to run)."""

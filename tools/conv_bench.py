@@ -8,6 +8,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fasterseg_b200 import _lib  # noqa: E402
 from fasterseg_b200 import functional as F_  # noqa: E402
 
 # name, Cin, Cout, k, stride, H, W (input)
@@ -83,8 +84,11 @@ def main():
         flops = 2.0 * k * k * ci * co * ho * wo
         byts = in_b + out_b + k * k * ci * co * 2
         tot += us
-        print("%2d %-18s %3d->%3d k%d s%d %4dx%-4d %8.2f us  %7.1f TFLOP/s %7.1f GB/s  (roof %.1f us)" % (
-            li, name, ci, co, k, s, h, w, us, flops / us / 1e6, byts / us / 1e3, max(flops / 1694e12, byts / 6568e9) * 1e6))
+        import ctypes as C
+        d = _lib.ConvDesc(1, h, w, ci, co, k, s, pad, 1, 0, 0, ho, wo, ci, co, _lib.FSB_CONV_RELU | _lib.FSB_CONV_AFFINE)
+        kid = _lib.lib().fsb_conv_kernel_id(C.byref(d), C.c_void_p(ys[0].data_ptr()), 0)
+        print("%2d %-18s %3d->%3d k%d s%d %4dx%-4d %8.2f us  %7.1f TFLOP/s %7.1f GB/s  (roof %.1f us)  K%d" % (
+            li, name, ci, co, k, s, h, w, us, flops / us / 1e6, byts / us / 1e3, max(flops / 1694e12, byts / 6568e9) * 1e6, kid))
     print("total %.1f us" % tot)
 
 

@@ -3,6 +3,10 @@
 //   * the instruction shape (M = 128 with cta_group::1, M = 256 with cta_group::2; N in {64, 128, 256}),
 //   * the shared-memory WRITE traffic that TMA adds while the tensor pipe reads its operands (per-stage A and/or B loads,
 //     A every `a_every`-th stage = the row-strip reuse of the conv kernels).
+// Issue style matters: a tcgen05.mma inside an `if (lane == 0)` region is compiled into a per-instruction "waterfall" (ELECT / R2UR /
+// BRA.U.ANY loop, ~130-230 cycles per MMA -- the figure the first version of this benchmark and every kernel of round 1
+// measured); here the issuing warp stays converged and only the instruction itself sits under elect.sync, so the operands
+// live in uniform registers and consecutive UTCHMMAs are back to back in the SASS.
 // One CTA (pair) per SM, synthetic mainloop with the same mbarrier ring a real kernel uses.  Standalone: built with
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_rate tools/umma_rate.cu -lcuda
 // Output: one line per configuration with cycles per MMA (median over CTAs) and the implied TFLOP/s at the SM clock.
@@ -31,6 +35,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t par) {
     if (clock64() - t0 > 2000000000LL) { printf("umma_rate: barrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
+__device__ __forceinline__ bool elect() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -54,6 +63,11 @@ struct Params {
   int kblocks;        // pipeline iterations; 4 MMAs each
   int load_a;         // 0: never, n>0: every n-th k-block
   int load_b;         // 0/1
+  int nacc;           // accumulators used round-robin by consecutive MMAs (1 = one dependent chain)
+  int commit_every;   // no-load mode only: tcgen05.commit to a barrier nobody waits on every n MMAs (0 = never)
+  int kblock;         // MMAs per pipeline stage (4 = one 64-wide k-block; 8 re-reads the stage twice)
+  int M;              // instruction M per CTA: 128 or 64
+  int flags;          // 1: no tcgen05.fence::after_thread_sync after the full-barrier wait; 2: handshake only (producer arrives, no TMA)
   long long* cycles;  // per CTA
 };
 
@@ -65,6 +79,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const __grid_constant__ Pa
   __shared__ __align__(8) uint64_t full[8];
   __shared__ __align__(8) uint64_t empty[8];
   __shared__ __align__(8) uint64_t done;
+  __shared__ __align__(8) uint64_t dummy;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,15 +93,16 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const __grid_constant__ Pa
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&done, 1);
+    mbar_init(&dummy, 1 << 20);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
     if (CG == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
   }
@@ -97,13 +113,16 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const __grid_constant__ Pa
   const uint32_t tmem = tmem_slot;
   const bool loads = p.load_a || p.load_b;
 
-  if (warp == 0 && lane == 0 && loads) {
+  if (warp == 0 && loads) {
     // ---------------- producer (every CTA loads its own operands; completion lands on the leader's barrier) ----------
     for (int kb = 0; kb < p.kblocks; ++kb) {
       const int s = kb % p.stages, round = kb / p.stages;
       if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-      const bool la = p.load_a && (kb % p.load_a) == 0;
-      const uint32_t tx = (la ? a_bytes : 0) + (p.load_b ? b_bytes : 0);
+      const bool hs = (p.flags & 2) != 0;
+      const bool la = !hs && p.load_a && (kb % p.load_a) == 0;
+      const bool lbb = !hs && p.load_b;
+      const uint32_t tx = (la ? a_bytes : 0) + (lbb ? b_bytes : 0);
+      if (elect()) {
       if (rank == 0) mbar_expect_tx(&full[s], tx * CG);
       uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
       const uint32_t bar = CG == 2 ? (smem_u32(&full[s]) & kPeerMask) : smem_u32(&full[s]);
@@ -115,7 +134,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const __grid_constant__ Pa
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                        ::"r"(smem_u32(sa)), "l"(reinterpret_cast<uint64_t>(&p.tm_a)), "r"(bar), "r"(0), "r"(0) : "memory");
       }
-      if (p.load_b) {
+      if (lbb) {
         if (CG == 2)
           asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                        ::"r"(smem_u32(sa + a_bytes)), "l"(reinterpret_cast<uint64_t>(&p.tm_b)), "r"(bar), "r"(0), "r"(0) : "memory");
@@ -123,56 +142,88 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const __grid_constant__ Pa
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                        ::"r"(smem_u32(sa + a_bytes)), "l"(reinterpret_cast<uint64_t>(&p.tm_b)), "r"(bar), "r"(0), "r"(0) : "memory");
       }
+      }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
     // ---------------- MMA issuer (leader CTA) ----------------
-    const uint32_t idesc = idesc_f16(128 * CG, static_cast<uint32_t>(p.N));
+    const uint32_t idesc = idesc_f16(static_cast<uint32_t>(p.M) * CG, static_cast<uint32_t>(p.N));
     const long long t0 = clock64();
+    int n_blocks = 0;
+    const int nacc_mask = p.nacc - 1;   // nacc in {1, 2, 4}
+    const bool commit_each = !loads && p.commit_every == 1;
+    const bool commit_blocks = !loads && p.commit_every >= 4;
+    const int commit_block_mask = p.commit_every >= 4 ? p.commit_every / 4 - 1 : 0;
     for (int kb = 0; kb < p.kblocks; ++kb) {
       const int s = kb % p.stages;
       if (loads) {
         mbar_wait(&full[s], (kb / p.stages) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!(p.flags & 1)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
       const uint64_t da = desc_sw128(sa), db = desc_sw128(sa + a_bytes);
+      for (int j = 0; j < p.kblock / 4; ++j, ++n_blocks) {
+        if (elect()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-        if (CG == 1) {
-          asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}\n"
-                       ::"r"(tmem), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(acc) : "memory");
-        } else {
-          asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, q;\n\t}\n"
-                       ::"r"(tmem), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(acc) : "memory");
+        for (int k = 0; k < 4; ++k) {
+          // accumulator of MMA number n = 4 * n_blocks + k: n % nacc (nacc in {1, 2, 4}) = k & (nacc - 1), a per-k constant
+          const uint32_t td = tmem + static_cast<uint32_t>((k & nacc_mask) * p.N);
+          const uint32_t acc = (n_blocks > 0 || k > nacc_mask) ? 1u : 0u;
+          if (CG == 1) {
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}\n"
+                         ::"r"(td), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(acc) : "memory");
+          } else {
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, q;\n\t}\n"
+                         ::"r"(td), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(acc) : "memory");
+          }
+          if (commit_each) {
+            if (CG == 1)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy)) : "memory");
+            else
+              asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                           ::"r"(smem_u32(&dummy)), "h"(static_cast<uint16_t>(3)) : "memory");
+          }
         }
+        if (commit_blocks && ((n_blocks + 1) & commit_block_mask) == 0) {
+          if (CG == 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy)) : "memory");
+          else
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(smem_u32(&dummy)), "h"(static_cast<uint16_t>(3)) : "memory");
+        }
+        }
+        __syncwarp();
       }
-      if (loads) {
+      if (loads && elect()) {
         if (CG == 1)
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
         else
           asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                        ::"r"(smem_u32(&empty[s])), "h"(static_cast<uint16_t>(3)) : "memory");
       }
+      __syncwarp();
     }
+    if (elect()) {
     if (CG == 1)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done)) : "memory");
     else
       asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                    ::"r"(smem_u32(&done)), "h"(static_cast<uint16_t>(3)) : "memory");
+    }
+    __syncwarp();
     mbar_wait(&done, 0);
     const long long t1 = clock64();
-    p.cycles[blockIdx.x] = t1 - t0;
+    if (lane == 0) p.cycles[blockIdx.x] = t1 - t0;
   }
-  if (!(warp == 1 && lane == 0 && rank == 0) && threadIdx.x == 64) {
+  if (!(warp == 1 && rank == 0) && threadIdx.x == 64) {
     mbar_wait(&done, 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (CG == 2) cluster_sync_all();
   if (warp == 1) {
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
@@ -214,24 +265,69 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int kblocks = 2048;
   printf("# cg  M   N  loadA(every) loadB | cycles/MMA (median CTA, min..max) | floor M*N/256/cg' | smem read B/cyc/SM | tma write B/cyc/SM | TFLOP/s chip @event time\n");
-  struct Cfg { int cg, N, la, lb; };
+  struct Cfg { int cg, N, la, lb, nacc, ce, kblock, stages; int M = 128; int flags = 0; };
   std::vector<Cfg> cfgs;
-  for (int cg = 1; cg <= 2; ++cg)
-    for (int N : {64, 128, 256})
-      for (int mode = 0; mode < 5; ++mode) {
-        Cfg c{cg, N, 0, 0};
-        if (mode == 1) { c.la = 1; c.lb = 1; }
-        if (mode == 2) { c.la = 1; c.lb = 0; }
-        if (mode == 3) { c.la = 0; c.lb = 1; }
-        if (mode == 4) { c.la = 9; c.lb = 0; }
+  const int set = argc > 1 ? atoi(argv[1]) : 0;
+  if (set == 1) {
+    // (5) M = 64 per CTA: does the instruction time follow M (rows streamed) rather than N?
+    for (int cg = 1; cg <= 2; ++cg)
+      for (int N : {64, 128, 256}) {
+        Cfg c{cg, N, 0, 0, 1, 0, 4, 4};
+        c.M = 64;
+        cfgs.push_back(c);
+        c.M = 128;
         cfgs.push_back(c);
       }
+    // (6) where does the per-stage bubble come from?  handshake only (no TMA) / no fence / deeper k-blocks
+    for (int N : {128, 256})
+      for (int kblock : {4, 8, 16})
+        for (int flags : {0, 1, 2, 3}) {
+          Cfg c{1, N, 1, 1, 1, 0, kblock, 4};
+          c.flags = flags;
+          cfgs.push_back(c);
+        }
+    for (int kblock : {4, 8, 16})
+      for (int flags : {0, 2}) {
+        Cfg c{2, 256, 1, 1, 1, 0, kblock, 4};
+        c.flags = flags;
+        cfgs.push_back(c);
+      }
+  }
+  if (set == 0) {
+    // (1) is the ~131-cycle figure a dependency latency?  round-robin over independent accumulators, no loads, no commits
+    for (int cg = 1; cg <= 2; ++cg)
+      for (int N : {64, 128, 256})
+        for (int nacc : {1, 2, 4}) {
+          if (nacc * N > 512) continue;
+          cfgs.push_back(Cfg{cg, N, 0, 0, nacc, 0, 4, 4});
+        }
+    // (2) what does a tcgen05.commit cost?  no loads, commit every n MMAs to a barrier nobody waits on
+    for (int N : {128, 256})
+      for (int ce : {1, 4, 8, 16})
+        cfgs.push_back(Cfg{1, N, 0, 0, 1, ce, 4, 4});
+    for (int ce : {4, 16}) cfgs.push_back(Cfg{1, 128, 0, 0, 2, ce, 4, 4});
+    // (3) the full producer/consumer ring: stages x MMAs per stage, operands re-loaded every stage
+    for (int cg = 1; cg <= 2; ++cg)
+      for (int N : {128, 256})
+        for (int nacc : {1, 2}) {
+          if (nacc * N > 512) continue;
+          for (int kblock : {4, 8})
+            for (int stages : {2, 4})
+              cfgs.push_back(Cfg{cg, N, 1, 1, nacc, 0, kblock, stages});
+        }
+    // (4) conv-like: A every 9th stage only (row-strip reuse), B every stage / never (resident weights)
+    for (int cg = 1; cg <= 2; ++cg)
+      for (int N : {64, 128})
+        for (int lb : {0, 1})
+          cfgs.push_back(Cfg{cg, N, 9, lb, 2, 0, 8, 4});
+  }
   for (const Cfg& c : cfgs) {
     Params p;
     memset(&p, 0, sizeof(p));
     make_map(enc, &p.tm_a, src, 128, 128);
     make_map(enc, &p.tm_b, src, 256, c.N / c.cg);
-    p.N = c.N; p.stages = 4; p.kblocks = kblocks; p.load_a = c.la; p.load_b = c.lb; p.cycles = cyc;
+    p.N = c.N; p.stages = c.stages; p.kblocks = kblocks * 4 / c.kblock; p.load_a = c.la; p.load_b = c.lb; p.cycles = cyc;
+    p.nacc = c.nacc; p.commit_every = c.ce; p.kblock = c.kblock; p.M = c.M; p.flags = c.flags;
     CK(cudaMemset(cyc, 0, sizeof(long long) * 512));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -259,9 +355,10 @@ int main(int argc, char** argv) {
     std::sort(per.begin(), per.end());
     const double med = per[per.size() / 2];
     const double read_b = (128 * 32 + (c.N / c.cg) * 32) / med;
-    const double wr_b = ((c.la ? 128.0 * 128 / c.la : 0.0) + (c.lb ? (c.N / c.cg) * 128.0 : 0.0)) / 4.0 / med;
-    const double flop = 2.0 * 128 * c.cg * c.N * 16 * 4.0 * kblocks * (grid / c.cg);
-    printf("  %d  %3d %3d   %d        %d   | %7.1f (%6.1f..%6.1f) | %5.0f | %6.1f | %6.1f | %8.1f\n", c.cg, 128 * c.cg, c.N, c.la, c.lb, med, per.front(), per.back(),
+    const double wr_b = ((c.la ? 128.0 * 128 / c.la : 0.0) + (c.lb ? (c.N / c.cg) * 128.0 : 0.0)) / c.kblock / med;
+    const double flop = 2.0 * c.M * c.cg * c.N * 16 * 4.0 * kblocks * (grid / c.cg);
+    printf("  %d  %3d %3d   %d        %d  nacc %d commit/%-2d kblk %2d st %d fl %d | %7.1f (%6.1f..%6.1f) | %5.0f | %6.1f | %6.1f | %8.1f\n", c.cg, c.M * c.cg, c.N, c.la, c.lb,
+           c.nacc, c.ce, c.kblock, c.stages, c.flags, med, per.front(), per.back(),
            128.0 * c.N / 256.0, read_b, wr_b, flop / (best_ms * 1e-3) / 1e12);
     fflush(stdout);
   }
