@@ -152,7 +152,8 @@ def measured_peaks():
 
 
 KERNEL_NAMES = {0: "conv_direct_kernel", 1: "conv_tc_kernel (per-tap, 128 px x Cout tile)", 2: "conv_tc2_kernel (row strip)",
-                3: "conv_tc3_kernel (channel-major 128 x 256 MMA)"}
+                3: "conv_tc3_kernel (channel-major 128 x 256 MMA)", 4: "conv_tc4_kernel (CTA pair, cta_group::2)",
+                5: "conv_tc5_kernel (tap-concatenated N = 3*Cout, flattened-pixel tiles)"}
 
 
 def _time_conv_layer(device, Cin, Cout, h, w, reps=5):
@@ -213,10 +214,11 @@ def dominant_kernel_roofline(device):
                        "algorithmic_flops": flops, "algorithmic_bytes": abytes})
     worst = dict(min(layers, key=lambda r: r["frac"]))
     worst.update({"traffic": traffic if "heads8" in worst["kernel"] else None, "peak_source": pk["source"], "layers": layers,
-                  "note": "worse of the two 9.66-GFLOP launches of the frame; heads8 runs the channel-major kernel (weights as the "
-                          "M = 128 operand, 256 pixels as N: 96 B/clk of shared-memory operand traffic instead of 128 B/clk for "
-                          "128 x 128 tiles); stem.1.conv2 has only 64 output channels (N = 64 per MMA) and sits at the "
-                          "tensor/HBM ridge"})
+                  "note": "worse of the two 9.66-GFLOP launches of the frame.  A tcgen05.mma costs ~130-180 cycles whatever N is "
+                          "(tools/umma_rate.cu), so heads8 runs channel-major (weights as M = 128, 256 pixels as N) and "
+                          "stem.1.conv2 (64 output channels) concatenates the three horizontal taps along N (N = 192, 12 MMAs per "
+                          "120 pixels instead of 36 per 128) and applies the horizontal shift in the epilogue; with K = 576 the "
+                          "accumulator drain (TMEM -> registers, 98 KB per tile) is as long as the MMAs themselves"})
     return worst
 
 

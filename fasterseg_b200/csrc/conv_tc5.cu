@@ -10,30 +10,34 @@
 // UN-shifted input row, so
 //      D[p, (s, c)] = sum_{r, ci} X[pixel p of input row y+r-1, ci] * W[c, ci, r, s]          (12 MMAs instead of 36 for Cin = 64)
 // and the horizontal shift moves into the epilogue:  y[p, c] = D[p-1, (0,c)] + D[p, (1,c)] + D[p+1, (2,c)]
-// (thread = pixel = TMEM lane; the two neighbour terms come from the adjacent lanes by warp shuffle, across warp borders
-// through a 2 KB shared-memory patch).  Pixels are addressed on the FLATTENED H*W axis of the NHWC tensor: a tile is 128
-// consecutive pixels (126 outputs + one halo pixel on either side), kernel row r is the same window shifted by (r-1)*W
-// pixels, TMA zero-fills what falls off either end of the image (= top/bottom padding) and the epilogue drops the
-// left/right neighbour term of pixels in the first/last image column (= left/right padding), so tiles need not align with
-// image rows and no output column is wasted.
+// (thread = pixel = TMEM lane; the two neighbour terms come from the adjacent lanes by warp shuffle).  Pixels are addressed on
+// the FLATTENED H*W axis of the NHWC tensor.  A tile is four groups of 32 consecutive pixels, one group per TMEM lane quarter
+// = per epilogue warp, consecutive groups overlapping by two pixels: every warp holds its own halo pixel on either side, so
+// the shifted sum needs NO data from another warp (a first version that exchanged the border terms through shared memory
+// spent 8 us per tile in divergent edge code and named barriers; profiles/r2_tc5_timeline_v1.log).  120 outputs per tile.
+// Kernel row r is the same window shifted by (r-1)*W pixels; TMA zero-fills what falls off either end of the image (= top /
+// bottom padding) and the epilogue drops the left/right neighbour term of pixels in the first/last image column (= left /
+// right padding), so tiles need not align with image rows.
 // Persistent CTAs (one per SM) walk tiles; all 3 * Cin/64 weight stacks stay resident in shared memory; two TMEM accumulators
-// let the epilogue of tile t run under the MMAs of tile t+1.  Issue loops follow conv_tc.cu (converged warps, elect.sync,
-// division-free rings).
+// and TWO sets of four epilogue warps (even / odd tiles, each warp with its own staging slab and TMA store, software-pipelined
+// tcgen05.ld) keep the epilogue off the critical path.  Issue loops follow conv_tc.cu (converged warps, elect.sync, division-free rings).
 #include "fsb_common.cuh"
 #include "fsb_internal.h"
 
 namespace fsb {
 
-constexpr int k5Threads = 192;     // warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..5 epilogue
+constexpr int k5Threads = 320;     // warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2..5 / 6..9 epilogue of even / odd tiles
 constexpr int k5MaxStages = 10;
-constexpr int k5Lanes = 128;       // pixels per tile incl. the two halo pixels
-constexpr int k5Out = 126;         // outputs per tile
+constexpr int k5Lanes = 128;       // TMEM lanes = rows of the A operand
+constexpr int k5GroupOut = 30;     // outputs per 32-pixel group (one halo pixel on either side)
+constexpr int k5Out = 4 * k5GroupOut;   // outputs per tile
+constexpr uint32_t k5StageSlab = 4096;  // per-warp staging slab (30 rows x <= 128 B, 1024-aligned)
 constexpr uint32_t k5ABytes = k5Lanes * 128;   // one (kernel row, 64-channel chunk) slab of the input window
 
 struct ConvTc5Params {
-  CUtensorMap tmap_x;   // {Cin, H*W, N}, box {64, 128, 1}, SW128
+  CUtensorMap tmap_x;   // {Cin, H*W, N}, box {64, 32, 1}, SW128
   CUtensorMap tmap_w;   // packed weights {Kpad, Npad, 9}, box {64, Cout, 3}, SW128
-  CUtensorMap tmap_y;   // {Cout, H*W, N}, box {Cout, 126, 1}, SW128 when Cout == 64 else dense rows
+  CUtensorMap tmap_y;   // {Cout, H*W, N}, box {Cout, 30, 1}, SW128 when Cout == 64 else dense rows
   int kch;              // Cin / 64
   int W, P;             // image width, pixels per image (H * W)
   int tiles_per_img, tiles;
@@ -43,7 +47,75 @@ struct ConvTc5Params {
   uint32_t flags, tmem_cols, acc_cols;
   const float* scale;
   const float* shift;
+  unsigned long long* dbg;   // optional timeline buffer (fsb_debug_set_buffer): 64 stamps of CTA 0
 };
+
+extern unsigned long long* g_dbg_buffer;
+__device__ __forceinline__ unsigned long long gtimer5() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define T5_STAMP(i) do { if (p.dbg && blockIdx.x == 0 && (i) < 64) p.dbg[(i)] = gtimer5(); } while (0)
+
+// One warp drains its 32 lanes of an accumulator: CH channels per pass (three tcgen05.ld of CH columns, ONE wait), the shifted
+// three-term sum by warp shuffle, BN scale/shift, ReLU, fp16, into the warp's staging slab (rows = output pixels).
+template <int CH>
+__device__ __forceinline__ void tc5_drain(const ConvTc5Params& p, uint32_t taddr, uint8_t* slab, int lane, float keep0, float keep2,
+                                          bool relu, const float* s_scale, const float* s_shift, uint64_t* empty_bar) {
+  const uint32_t row_bytes = static_cast<uint32_t>(p.Cout) * 2u;
+  for (int c0 = 0; c0 < p.Cout; c0 += CH) {
+    uint32_t v0[CH], v1[CH], v2[CH];
+    if constexpr (CH == 32) {
+      tmem_ld32(taddr + c0, v0);
+      tmem_ld32(taddr + p.Cout + c0, v1);
+      tmem_ld32(taddr + 2 * p.Cout + c0, v2);
+    } else {
+      tmem_ld16(taddr + c0, v0);
+      tmem_ld16(taddr + p.Cout + c0, v1);
+      tmem_ld16(taddr + 2 * p.Cout + c0, v2);
+    }
+    tmem_ld_wait();
+    if (c0 + CH >= p.Cout) {   // that was this warp's last TMEM read of the tile: hand the accumulator back before the arithmetic
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(empty_bar);
+    }
+#pragma unroll
+    for (int h = 0; h < CH / 16; ++h) {
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int c = h * 16 + e;
+        const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[c]), 1);
+        const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 1);
+        const float acc = fmaf(left, keep0, fmaf(right, keep2, __uint_as_float(v1[c])));
+        const float x = fmaf(acc, s_scale[c0 + c], s_shift[c0 + c]);
+        f[e] = relu ? fmaxf(x, 0.f) : x;
+      }
+      if (lane >= 1 && lane <= k5GroupOut) {
+        uint4 o0, o1;
+        o0.x = pack_half2(f[0], f[1]);
+        o0.y = pack_half2(f[2], f[3]);
+        o0.z = pack_half2(f[4], f[5]);
+        o0.w = pack_half2(f[6], f[7]);
+        o1.x = pack_half2(f[8], f[9]);
+        o1.y = pack_half2(f[10], f[11]);
+        o1.z = pack_half2(f[12], f[13]);
+        o1.w = pack_half2(f[14], f[15]);
+        const int row = lane - 1;
+        uint8_t* dst = slab + static_cast<size_t>(row) * row_bytes;
+        const int ch16 = (c0 >> 3) + 2 * h;
+        if (p.y_swizzled) {
+          *reinterpret_cast<uint4*>(dst + ((ch16 ^ (row & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4*>(dst + (((ch16 + 1) ^ (row & 7)) << 4)) = o1;
+        } else {
+          *reinterpret_cast<uint4*>(dst + (ch16 << 4)) = o0;
+          *reinterpret_cast<uint4*>(dst + ((ch16 + 1) << 4)) = o1;
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(k5Threads, 1)
 conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
@@ -56,11 +128,11 @@ conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_scale[64];
   __shared__ float s_shift[64];
-  __shared__ float s_edge[4][4][2][16];   // [16-channel chunk][warp][0: lane 31's s=0 terms, 1: lane 0's s=2 terms][channel]
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) T5_STAMP(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t w_tile = static_cast<uint32_t>(p.NT) * 128u;            // one (kernel row, chunk) weight stack
   const uint32_t w_bytes = 3u * static_cast<uint32_t>(p.kch) * w_tile;
@@ -80,7 +152,7 @@ conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
     mbar_init(&w_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp of the set that drains this accumulator
     }
     mbar_fence_init();
   }
@@ -98,6 +170,7 @@ conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) T5_STAMP(1);
 
   if (warp == 0) {
     // ================= TMA producer: resident weights once, then the input windows of every tile of this CTA =================
@@ -119,7 +192,9 @@ conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
           mbar_wait(&a_empty[rp.s], rp.phase ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[rp.s], k5ABytes);
-            tma_load_3d(sa, &p.tmap_x, &a_full[rp.s], kc * 64, pix, img);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)   // lane quarter g holds pixels pix + 30 g .. + 31
+              tma_load_3d(sa + g * 4096, &p.tmap_x, &a_full[rp.s], kc * 64, pix + g * k5GroupOut, img);
           }
           __syncwarp();
           sa += k5ABytes;
@@ -140,14 +215,17 @@ conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
     uint32_t aoff = 0;
     int buf = 0;
     uint32_t acc_phase = 0;   // parity of the accumulator round: tmem_empty is waited with (acc_phase ^ 1) like a producer ring
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    int lt_m = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt_m) {
       mbar_wait(&tmem_empty[buf], acc_phase ^ 1u);   // epilogue of the tile that used this accumulator two tiles ago
       tc_fence_after();
+      if (lane == 0) T5_STAMP(2 + lt_m * 8 + 0);
       const uint32_t acc = tmem_base + static_cast<uint32_t>(buf) * p.acc_cols;
       uint32_t woff = 0;
       for (int ks = 0; ks < k_steps; ++ks) {
         mbar_wait(&a_full[rp.s], rp.phase);
         tc_fence_after();
+        if (lane == 0 && ks == 0) T5_STAMP(2 + lt_m * 8 + 1);
         if (elect_one()) {
           const uint64_t da = da0 + aoff, db = db0 + woff;
           umma_f16_ss(acc, da, db, idesc, ks > 0 ? 1u : 0u);
@@ -162,98 +240,53 @@ conv_tc5_kernel(const __grid_constant__ ConvTc5Params p) {
         rp.advance(p.stages);
         if (rp.s == 0) aoff = 0;
       }
+      if (lane == 0) T5_STAMP(2 + lt_m * 8 + 2);
       buf ^= 1;
       if (buf == 0) acc_phase ^= 1u;
     }
   } else {
-    // ================= epilogue warps 2..5: thread = pixel lane m; out[m] = D[m-1](s=0) + D[m](s=1) + D[m+1](s=2) =================
-    const int q = warp & 3;          // TMEM lane quarter
-    const int m = q * 32 + lane;
+    // ================= epilogue: warps 2..5 take the even tiles of this CTA, warps 6..9 the odd ones; thread = pixel lane ===========
+    // out[l] = D[l-1](s=0) + D[l](s=1) + D[l+1](s=2) inside the warp's own 32 lanes (lanes 0 and 31 are the group's halo pixels).
+    // (Splitting the channel chunks of ONE tile over both warp sets was measured slower: 2.0 vs 1.4 us per tile -- eight warps
+    // reading the accumulator that the tensor pipe is about to need contend for TMEM; profiles/r2_tc5_timeline_v3.log.)
+    const int set = (warp - 2) >> 2;   // 0: even local tiles (accumulator 0), 1: odd local tiles (accumulator 1)
+    const int q = warp & 3;            // TMEM lane quarter
     const bool relu = (p.flags & FSB_CONV_RELU) != 0;
-    const bool storer = (warp == 2 && lane == 0);
-    const int chunks = p.Cout >> 4;
-    const uint32_t row_bytes = static_cast<uint32_t>(p.Cout) * 2u;
-    int buf = 0;
+    uint8_t* slab = staging + static_cast<size_t>(set * 4 + q) * k5StageSlab;
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(set) * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t acc_phase = 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+    int lt = set;
+    for (int tile = blockIdx.x + set * gridDim.x; tile < p.tiles; tile += 2 * gridDim.x, lt += 2) {
       const int img = tile / p.tiles_per_img;
       const int i0 = (tile - img * p.tiles_per_img) * k5Out;
-      const int idx = i0 + m - 1;                 // flattened output pixel of this lane (lanes 0 and 127 are halo)
+      const int g0 = i0 + q * k5GroupOut;         // first output pixel of this warp's group
+      const int idx = g0 + lane - 1;              // flattened pixel of this lane
       const int xcol = idx >= 0 ? idx % p.W : 0;
       const float keep0 = xcol == 0 ? 0.f : 1.f;          // no left neighbour in the first image column
       const float keep2 = xcol == p.W - 1 ? 0.f : 1.f;    // no right neighbour in the last image column
-      mbar_wait(&tmem_full[buf], acc_phase);
+      mbar_wait(&tmem_full[set], acc_phase);
       tc_fence_after();
-      if (lt > 0) {
-        if (storer) tma_store_wait_read();   // the staging tile still feeds the previous tile's bulk store
-        named_bar_sync(1, 128);
+      if (threadIdx.x == 64) T5_STAMP(2 + lt * 8 + 3);
+      if (lt >= 2) {   // this warp's slab still feeds its previous bulk store until that store has READ it
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
       }
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf) * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16);
-      for (int cb = 0; cb < chunks; ++cb) {
-        uint32_t v0[16], v1[16], v2[16];
-        tmem_ld16(taddr + cb * 16, v0);
-        tmem_ld16(taddr + p.Cout + cb * 16, v1);
-        tmem_ld16(taddr + 2 * p.Cout + cb * 16, v2);
-        tmem_ld_wait();
-        if (cb == chunks - 1) {   // last TMEM read of this tile by this warp: hand the accumulator back
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-        }
-        // warp-border patch: lane 31's s=0 terms feed lane 0 of the next warp, lane 0's s=2 terms feed lane 31 of the previous
-        if (lane == 31) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) s_edge[cb][q][0][e] = __uint_as_float(v0[e]);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) s_edge[cb][q][1][e] = __uint_as_float(v2[e]);
-        }
-        named_bar_sync(2, 128);
-        float f[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);
-          float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);
-          if (lane == 0) left = q > 0 ? s_edge[cb][q - 1][0][e] : 0.f;
-          if (lane == 31) right = q < 3 ? s_edge[cb][q + 1][1][e] : 0.f;
-          const float acc = left * keep0 + __uint_as_float(v1[e]) + right * keep2;
-          const float x = acc * s_scale[cb * 16 + e] + s_shift[cb * 16 + e];
-          f[e] = relu ? fmaxf(x, 0.f) : x;
-        }
-        if (m >= 1 && m <= k5Out) {
-          uint4 o0, o1;
-          o0.x = pack_half2(f[0], f[1]);
-          o0.y = pack_half2(f[2], f[3]);
-          o0.z = pack_half2(f[4], f[5]);
-          o0.w = pack_half2(f[6], f[7]);
-          o1.x = pack_half2(f[8], f[9]);
-          o1.y = pack_half2(f[10], f[11]);
-          o1.z = pack_half2(f[12], f[13]);
-          o1.w = pack_half2(f[14], f[15]);
-          const int row = m - 1;
-          uint8_t* dst = staging + static_cast<size_t>(row) * row_bytes;
-          const int ch16 = 2 * cb;
-          if (p.y_swizzled) {
-            *reinterpret_cast<uint4*>(dst + ((ch16 ^ (row & 7)) << 4)) = o0;
-            *reinterpret_cast<uint4*>(dst + (((ch16 + 1) ^ (row & 7)) << 4)) = o1;
-          } else {
-            *reinterpret_cast<uint4*>(dst + (ch16 << 4)) = o0;
-            *reinterpret_cast<uint4*>(dst + ((ch16 + 1) << 4)) = o1;
-          }
-        }
-      }
+      if ((p.Cout & 31) == 0)
+        tc5_drain<32>(p, taddr, slab, lane, keep0, keep2, relu, s_scale, s_shift, &tmem_empty[set]);
+      else
+        tc5_drain<16>(p, taddr, slab, lane, keep0, keep2, relu, s_scale, s_shift, &tmem_empty[set]);
+      if (threadIdx.x == 64) T5_STAMP(2 + lt * 8 + 4);
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (storer) {
+      __syncwarp();
+      if (lane == 0 && g0 < p.P) {
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                     ::"l"(reinterpret_cast<uint64_t>(&p.tmap_y)), "r"(smem_u32(staging)), "r"(0), "r"(i0), "r"(img) : "memory");
+                     ::"l"(reinterpret_cast<uint64_t>(&p.tmap_y)), "r"(smem_u32(slab)), "r"(0), "r"(g0), "r"(img) : "memory");
         tma_store_commit();
       }
-      buf ^= 1;
-      if (buf == 0) acc_phase ^= 1u;
+      if (threadIdx.x == 64) T5_STAMP(2 + lt * 8 + 5);
+      acc_phase ^= 1u;
     }
-    if (storer) tma_store_wait_read();
+    if (lane == 0) tma_store_wait_read();
     tc_fence_before();
   }
   __syncthreads();
@@ -279,7 +312,7 @@ static Tc5Plan conv_tc5_plan(const fsb_conv_desc* d) {
   q.kch = d->Cin / 64;
   const int NT = 3 * d->Cout;
   const size_t w_bytes = static_cast<size_t>(3) * q.kch * NT * 128;
-  const size_t staging = static_cast<size_t>(k5Lanes) * d->Cout * 2;
+  const size_t staging = 8 * k5StageSlab;
   const size_t budget = 220 * 1024 - 1024;
   if (w_bytes + staging + 3 * k5ABytes > budget) return q;
   int st = static_cast<int>((budget - w_bytes - staging) / k5ABytes);
@@ -293,21 +326,21 @@ static Tc5Plan conv_tc5_plan(const fsb_conv_desc* d) {
   q.acc_cols = acc;
   q.tmem_cols = 2 * acc;
   if (q.tmem_cols > 512) return q;
-  q.smem_bytes = w_bytes + static_cast<size_t>(st) * k5ABytes + ((staging + 1023) / 1024) * 1024 + 1024;
+  q.smem_bytes = w_bytes + static_cast<size_t>(st) * k5ABytes + staging + 1024;
   q.ok = 1;
   return q;
 }
 
 int conv_tc5_supported(const fsb_conv_desc* d, const void* y) {
   const int mode = opt(OPT_CONV_TC5);
-  if (mode <= 0) return 0;   // default off until the GPU suite has run with it
+  if (mode == 0) return 0;
   if (d->ksize != 3 || d->stride != 1 || d->dil != 1 || d->pad != 1 || d->off_h || d->off_w) return 0;
   if (d->Cin % 64 != 0 || d->Cin > 256) return 0;
   if (!(d->Cout == 16 || d->Cout == 32 || d->Cout == 48 || d->Cout == 64)) return 0;
   if ((d->x_cstride % 8) != 0 || (d->y_cstride % 8) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0) return 0;
   if (d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS | FSB_CONV_FORCE_DIRECT)) return 0;
   if (static_cast<int64_t>(d->H) * d->W >= (1ll << 31)) return 0;
-  if (mode != 2 && static_cast<int64_t>(d->N) * d->H * d->W < 126 * 96) return 0;   // fewer tiles than ~2/3 of the SMs
+  if (mode != 2 && static_cast<int64_t>(d->N) * d->H * d->W < k5Out * 96) return 0;   // fewer tiles than ~2/3 of the SMs
   return conv_tc5_plan(d).ok;
 }
 
@@ -334,12 +367,13 @@ int conv_tc5_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
   p.acc_cols = q.acc_cols;
   p.scale = scale;
   p.shift = shift;
+  p.dbg = g_dbg_buffer;
   const uint64_t P = static_cast<uint64_t>(d->H) * d->W;
   {
     const uint64_t cs = static_cast<uint64_t>(d->x_cstride) * 2;
     const uint64_t dims[3] = {static_cast<uint64_t>(d->Cin), P, static_cast<uint64_t>(d->N)};
     const uint64_t str[2] = {cs, cs * P};
-    const uint32_t box[3] = {64u, static_cast<uint32_t>(k5Lanes), 1u};
+    const uint32_t box[3] = {64u, 32u, 1u};
     if (int rc = encode_tiled_generic(&p.tmap_x, x, 3, dims, str, box, 128)) return rc;
   }
   {
@@ -352,7 +386,7 @@ int conv_tc5_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, 
     const uint64_t ycs = static_cast<uint64_t>(d->y_cstride) * 2;
     const uint64_t dims[3] = {static_cast<uint64_t>(d->Cout), P, static_cast<uint64_t>(d->N)};
     const uint64_t str[2] = {ycs, ycs * P};
-    const uint32_t box[3] = {static_cast<uint32_t>(d->Cout), static_cast<uint32_t>(k5Out), 1u};
+    const uint32_t box[3] = {static_cast<uint32_t>(d->Cout), static_cast<uint32_t>(k5GroupOut), 1u};
     if (int rc = encode_tiled_generic(&p.tmap_y, y, 3, dims, str, box, p.y_swizzled ? 128 : 0)) return rc;
   }
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc5_kernel), 222 * 1024, "cudaFuncSetAttribute(conv_tc5)")) return rc;

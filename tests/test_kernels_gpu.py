@@ -189,9 +189,10 @@ TC5_CASES = [
     (1, 64, 64, 24, 256),      # stem.1.conv2-like
     (1, 64, 32, 33, 100),      # cell0.conv1-like, W < tile
     (2, 64, 64, 7, 130),       # batch 2, ragged
-    (1, 128, 64, 9, 64),       # two channel chunks, 4.6 rows per tile
-    (1, 192, 48, 5, 37),       # three chunks, Cout = 48, odd sizes
+    (1, 128, 32, 9, 64),       # two channel chunks, 1.9 rows per tile
+    (1, 128, 48, 5, 37),       # Cout = 48, odd sizes
     (1, 256, 16, 3, 500),      # four chunks, Cout = 16
+    (1, 192, 32, 6, 90),       # three chunks
     (1, 64, 64, 1, 300),       # a single image row (top and bottom padding in every tile)
     (3, 64, 64, 160, 128),     # 3 x 163 = 489 tiles > 148 SMs: persistent walk, accumulator ring
 ]
