@@ -88,6 +88,14 @@ _SIGS = {
                                             C.c_int, _P, C.c_int, _P, _P, _P]),
     "fsb_conv_bn_act_train_bwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P,
                                             C.c_int64, C.c_int64, _P, C.c_int, _P, _P, C.c_int, _P, C.c_float, _P, _P, _P]),
+    "fsb_loss_logp_fwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "fsb_kth_workspace_bytes": (C.c_size_t, []),
+    "fsb_kth_smallest_f32": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "fsb_loss_rows": (C.c_int, []),
+    "fsb_ohem_reduce": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "fsb_loss_ce_bwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P]),
+    "fsb_loss_kl_fwd": (C.c_int, [C.c_int] * 8 + [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "fsb_loss_kl_bwd": (C.c_int, [C.c_int] * 8 + [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P]),
     "fsb_dp_unique_id": (C.c_int, [_P]),
     "fsb_dp_init": (C.c_int, [_P, C.c_int, C.c_int]),
     "fsb_dp_world": (C.c_int, []),

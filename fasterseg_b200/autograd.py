@@ -608,3 +608,66 @@ def grad_mode(*tensors):
     if _TAPE is not None:
         return any(_TAPE.needs(t) for t in tensors)
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class FusedOhemCEFn(torch.autograd.Function):
+    """ProbOhemCrossEntropy2d(F.interpolate(x, size, bilinear, align_corners=True), target) (tools/seg_opr/loss_opr.py:63-93 on
+    train/model_seg.py:357-362's upsampled logits) from the LOW-RESOLUTION NHWC fp16 logits x: csrc/loss.cu.  No tensor of label
+    resolution with a class axis exists in either direction; the OHEM threshold is an exact order statistic (no sort, no sync)."""
+
+    @staticmethod
+    def forward(ctx, x, target, size, ignore_label, thresh, min_kept):
+        import math
+        target = target.contiguous()
+        Cc = x.shape[1]
+        logp, lse = F_.loss_logp_fwd(x, target, size, ignore_label)
+        valid = (target != ignore_label) & (target >= 0) & (target < Cc)
+        num_valid = valid.sum()
+        thr = None
+        if min_kept > 0:
+            n = logp.numel()
+            kth = F_.kth_smallest(logp.view(-1), min(n, int(min_kept)))
+            thr = torch.clamp(kth, min=math.log(thresh))                         # max(k-th smallest prob, thresh), in log space
+            mining = (num_valid >= min_kept) & (num_valid > 0)                    # loss_opr.py:68-71: no mining with fewer valid pixels
+            thr = torch.where(mining, thr, torch.full_like(thr, float("inf"))).contiguous()
+        sums = F_.ohem_reduce(logp, target, ignore_label, Cc, thr)
+        loss = sums[0] / sums[1]
+        ctx.save_for_backward(x, target, lse, logp, thr if thr is not None else torch.empty(0, device=x.device), sums)
+        ctx.cfg = (tuple(int(v) for v in size), int(ignore_label), thr is not None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, target, lse, logp, thr, sums = ctx.saved_tensors
+        size, ignore_label, has_thr = ctx.cfg
+        coef = (dloss.float() / sums[1]).reshape(1).contiguous()
+        dx = F_.loss_ce_bwd(x, target, size, ignore_label, lse, logp, thr if has_thr else None, coef, GRAD_SCALE)
+        return dx, None, None, None, None, None
+
+
+class FusedKLFn(torch.autograd.Function):
+    """nn.KLDivLoss(reduction='mean')(log_softmax(up(xs)), softmax(up(xt))) (train/train.py:254-260) from the two low-resolution
+    NHWC fp16 logit maps; gradient w.r.t. the student only (the teacher runs under no_grad in the reference)."""
+
+    @staticmethod
+    def forward(ctx, xs, xt, size):
+        total, lse_s, lse_t = F_.loss_kl_fwd(xs, xt, size)
+        numel = float(xs.shape[0] * xs.shape[1] * int(size[0]) * int(size[1]))
+        ctx.save_for_backward(xs, xt, lse_s, lse_t)
+        ctx.cfg = (tuple(int(v) for v in size), numel)
+        return total / numel
+
+    @staticmethod
+    def backward(ctx, dloss):
+        xs, xt, lse_s, lse_t = ctx.saved_tensors
+        size, numel = ctx.cfg
+        coef = (dloss.float() / numel).reshape(1).contiguous()
+        return F_.loss_kl_bwd(xs, xt, size, lse_s, lse_t, coef, GRAD_SCALE), None, None
+
+
+def fused_ohem_ce(x, target, size, ignore_label, thresh, min_kept):
+    return call(FusedOhemCEFn, x, target, (int(size[0]), int(size[1])), int(ignore_label), float(thresh), int(min_kept))
+
+
+def fused_kl(xs, xt, size):
+    return call(FusedKLFn, xs, xt, (int(size[0]), int(size[1])))

@@ -129,6 +129,16 @@ int conv_dgrad_launch(const fsb_conv_desc*, const void*, int, const void*, const
 int conv_wgrad_launch(const fsb_conv_desc*, const void*, const void*, int, float*, int64_t, int64_t, int, float, cudaStream_t);
 int bilinear_bwd_launch(int, int, int, int, int, int, const void*, int, const void*, int, void*, int, cudaStream_t);
 int upsample_logits_bwd_launch(int, int, int, int, int, int, const void*, int, void*, int, float, cudaStream_t);
+int loss_logp_fwd_launch(int, int, int, int, int, int, const void*, int, const long long*, int, float*, float*, cudaStream_t);
+size_t kth_workspace_bytes();
+int kth_smallest_launch(const float*, int64_t, int64_t, float*, void*, cudaStream_t);
+int loss_rows();
+int ohem_reduce_launch(const float*, const long long*, int64_t, int, int, const float*, float*, float*, cudaStream_t);
+int loss_ce_bwd_launch(int, int, int, int, int, int, const void*, int, const long long*, int, const float*, const float*, const float*,
+                       const float*, void*, int, float, int, cudaStream_t);
+int loss_kl_fwd_launch(int, int, int, int, int, int, int, int, const void*, int, const void*, int, float*, float*, float*, float*, cudaStream_t);
+int loss_kl_bwd_launch(int, int, int, int, int, int, int, int, const void*, int, const void*, int, const float*, const float*, const float*,
+                       void*, int, float, int, cudaStream_t);
 int nchw_grad_to_nhwc_launch(int, int, int, int, const void*, int, void*, int, float, cudaStream_t);
 int wsum_fwd_launch(int, int64_t, int, const void* const*, const int*, const float*, void*, int, cudaStream_t);
 int wsum_bwd_launch(int, int64_t, int, const void*, int, const void* const*, const int*, const float*, void* const*, const int*,
@@ -213,6 +223,39 @@ int fsb_rowsum(int L, const float* src, int rows, int stride, float* out, void* 
 int fsb_debug_set_buffer(void* dev_u64x128) {
   g_dbg_buffer = static_cast<unsigned long long*>(dev_u64x128);
   return FSB_OK;
+}
+
+int fsb_loss_logp_fwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* logits, int cstride, const int64_t* target,
+                      int ignore_label, float* logp_t, float* lse, void* stream) {
+  return loss_logp_fwd_launch(N, C, Hi, Wi, Ho, Wo, logits, cstride, reinterpret_cast<const long long*>(target), ignore_label, logp_t, lse,
+                              static_cast<cudaStream_t>(stream));
+}
+size_t fsb_kth_workspace_bytes(void) { return kth_workspace_bytes(); }
+int fsb_kth_smallest_f32(const float* x, int64_t n, int64_t k, float* out, void* workspace, void* stream) {
+  return kth_smallest_launch(x, n, k, out, workspace, static_cast<cudaStream_t>(stream));
+}
+int fsb_loss_rows(void) { return loss_rows(); }
+int fsb_ohem_reduce(const float* logp_t, const int64_t* target, int64_t n, int ignore_label, int C, const float* thr, float* partial,
+                    float* out2, void* stream) {
+  return ohem_reduce_launch(logp_t, reinterpret_cast<const long long*>(target), n, ignore_label, C, thr, partial, out2,
+                            static_cast<cudaStream_t>(stream));
+}
+int fsb_loss_ce_bwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* logits, int cstride, const int64_t* target,
+                    int ignore_label, const float* lse, const float* logp_t, const float* thr, const float* coef, void* dlogits,
+                    int dcs, float gscale, int accumulate, void* stream) {
+  return loss_ce_bwd_launch(N, C, Hi, Wi, Ho, Wo, logits, cstride, reinterpret_cast<const long long*>(target), ignore_label, lse, logp_t, thr,
+                            coef, dlogits, dcs, gscale, accumulate, static_cast<cudaStream_t>(stream));
+}
+int fsb_loss_kl_fwd(int N, int C, int Hs, int Ws, int Ht, int Wt, int Ho, int Wo, const void* student, int scs, const void* teacher,
+                    int tcs, float* lse_s, float* lse_t, float* partial, float* out2, void* stream) {
+  return loss_kl_fwd_launch(N, C, Hs, Ws, Ht, Wt, Ho, Wo, student, scs, teacher, tcs, lse_s, lse_t, partial, out2,
+                            static_cast<cudaStream_t>(stream));
+}
+int fsb_loss_kl_bwd(int N, int C, int Hs, int Ws, int Ht, int Wt, int Ho, int Wo, const void* student, int scs, const void* teacher,
+                    int tcs, const float* lse_s, const float* lse_t, const float* coef, void* dstudent, int dcs, float gscale,
+                    int accumulate, void* stream) {
+  return loss_kl_bwd_launch(N, C, Hs, Ws, Ht, Wt, Ho, Wo, student, scs, teacher, tcs, lse_s, lse_t, coef, dstudent, dcs, gscale, accumulate,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int fsb_device_info(int* sm_count, int* cc_major, int* cc_minor) {

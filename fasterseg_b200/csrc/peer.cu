@@ -12,6 +12,11 @@
 // capture order and identical on every rank); `epoch` is a per-region device counter bumped by the first node of the graph, so
 // a replay needs no host involvement.  Payloads are double-buffered by epoch parity: a rank can only be one replay ahead of a
 // peer (it needs the peer's flags of the previous graph to finish it).
+// ORDER: an exchange kernel spins until every rank has arrived, so two ranks that start two DIFFERENT exchanges first (independent
+// branches of a captured pass on side streams) can each hold execution resources the other one's missing kernel needs -- the first
+// 2-GPU runs dead-locked exactly like that (profiles/r2_dp_2gpu_deadlock.log).  All exchanges are therefore issued on ONE internal
+// exchange stream in slot order, fenced to the caller's stream by an event before and an event after (fork / join, legal under
+// stream capture): every rank spins on the same slot at any time, and compute kernels never queue behind a spinning kernel.
 // The flat gradient all-reduce (1 GB once per step) stays on NCCL (csrc/dp.cu); this file is for the latency-bound part.
 #include "fsb_common.cuh"
 #include "fsb_internal.h"
@@ -42,6 +47,8 @@ struct PeerState {
   int region_first[kMaxRegions];
   int region_count[kMaxRegions];
   int region = -1, cursor = 0;
+  cudaStream_t xstream = nullptr;       // the ordered exchange stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 } g_peer;
 
 constexpr size_t kFlagBytes = static_cast<size_t>(kMaxSlots) * sizeof(unsigned);
@@ -135,10 +142,28 @@ int peer_allreduce_f32(float* buf, int64_t n, cudaStream_t stream) {
   g_peer.cursor++;
   PeerPtrs pp;
   for (int i = 0; i < kMaxWorld; ++i) pp.base[i] = g_peer.base[i];
-  FSB_LAUNCH(peer_allreduce_kernel, dim3(1), dim3(256), 0, stream, buf, static_cast<int>(n), pp, g_peer.rank, g_peer.world,
-             static_cast<uint32_t>(slot), g_peer.slots[slot].off, static_cast<const unsigned*>(g_peer.epochs + r));
-  cudaError_t e = last_launch_error();
+  cudaError_t e;
+  if (!g_peer.xstream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&g_peer.xstream, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_peer.ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_peer.ev_out, cudaEventDisableTiming);
+    if (e != cudaSuccess) return set_cuda_error(e, "peer exchange stream");
+  }
+  // fork: the exchange waits for everything the caller's stream has issued so far (the producer of buf) ...
+  e = cudaEventRecord(g_peer.ev_in, stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(g_peer.xstream, g_peer.ev_in, 0);
+  if (e != cudaSuccess) return set_cuda_error(e, "peer exchange fork");
+  // (no programmatic dependent launch here: the kernel must not start before the event edge is satisfied)
+  peer_allreduce_kernel<<<1, 256, 0, g_peer.xstream>>>(buf, static_cast<int>(n), pp, g_peer.rank, g_peer.world, static_cast<uint32_t>(slot),
+                                                      g_peer.slots[slot].off, static_cast<const unsigned*>(g_peer.epochs + r));
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "peer_allreduce launch");
+  // ... join: the caller's stream continues after the exchange
+  e = cudaEventRecord(g_peer.ev_out, g_peer.xstream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, g_peer.ev_out, 0);
+  if (e != cudaSuccess) return set_cuda_error(e, "peer exchange join");
   return FSB_OK;
 }
 
@@ -220,6 +245,9 @@ int fsb_peer_shutdown(void) {
     if (p != g_peer.rank && g_peer.base[p]) cudaIpcCloseMemHandle(g_peer.base[p]);
   if (g_peer.local) cudaFree(g_peer.local);
   if (g_peer.epochs) cudaFree(g_peer.epochs);
+  if (g_peer.ev_in) cudaEventDestroy(g_peer.ev_in);
+  if (g_peer.ev_out) cudaEventDestroy(g_peer.ev_out);
+  if (g_peer.xstream) cudaStreamDestroy(g_peer.xstream);
   g_peer = PeerState();
   return FSB_OK;
 }

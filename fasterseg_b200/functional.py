@@ -607,3 +607,72 @@ def bn_bwd_sel(dy, y, raw, mean, invstd, count, relu, gscale, sel, hmax=0, world
                                           _ptr(invstd), _ptr(sums), _ptr(local), float(count), int(relu), _ptr(draw), nhwc_info(draw)[4],
                                           float(gscale), sel.table_ptr, sel.idx_ptr, int(hmax), _stream()), "fsb_bn_bwd_apply_sel")
     return draw
+
+
+# ---- N1: criteria evaluated from the low-resolution logits (csrc/loss.cu) ---------------------------------------------------------------
+def loss_logp_fwd(x, target, size, ignore_label):
+    """x: NHWC fp16 logits (N, C, Hi, Wi); target int64 (N, Ho, Wo) -> (logp_t, lse), both fp32 (N, Ho, Wo): log-probability of the true
+    class of the bilinearly upsampled (align_corners=True) logits (0 where the label is ignored) and their log-sum-exp."""
+    N, Cc, Hi, Wi, xcs = nhwc_info(x)
+    Ho, Wo = int(size[0]), int(size[1])
+    assert target.dtype == torch.int64 and tuple(target.shape) == (N, Ho, Wo) and target.is_contiguous(), (target.dtype, tuple(target.shape))
+    logp = torch.empty((N, Ho, Wo), device=x.device, dtype=torch.float32)
+    lse = torch.empty((N, Ho, Wo), device=x.device, dtype=torch.float32)
+    check(_lib.lib().fsb_loss_logp_fwd(N, Cc, Hi, Wi, Ho, Wo, _ptr(x), xcs, _ptr(target), int(ignore_label), _ptr(logp), _ptr(lse),
+                                       _stream()), "fsb_loss_logp_fwd")
+    return logp, lse
+
+
+def kth_smallest(x, k):
+    """exact k-th smallest (1-based) element of a contiguous fp32 tensor as a 0-d device tensor; no sort, no host synchronisation"""
+    assert x.dtype == torch.float32 and x.is_contiguous() and 1 <= k <= x.numel()
+    out = torch.empty((), device=x.device, dtype=torch.float32)
+    ws = torch.empty((_lib.lib().fsb_kth_workspace_bytes(),), device=x.device, dtype=torch.uint8)
+    check(_lib.lib().fsb_kth_smallest_f32(_ptr(x), x.numel(), int(k), _ptr(out), _ptr(ws), _stream()), "fsb_kth_smallest_f32")
+    return out
+
+
+def ohem_reduce(logp_t, target, ignore_label, num_classes, thr=None):
+    """-> fp32 tensor [sum(-logp_t * kept), count(kept)], kept = valid label & (logp_t <= thr); thr: 0-d device tensor or None"""
+    out = torch.empty((2,), device=logp_t.device, dtype=torch.float32)
+    partial = torch.empty((2 * _lib.lib().fsb_loss_rows(),), device=logp_t.device, dtype=torch.float32)
+    check(_lib.lib().fsb_ohem_reduce(_ptr(logp_t), _ptr(target), logp_t.numel(), int(ignore_label), int(num_classes), _ptr(thr), _ptr(partial),
+                                     _ptr(out), _stream()), "fsb_ohem_reduce")
+    return out
+
+
+def loss_ce_bwd(x, target, size, ignore_label, lse, logp_t, thr, coef, gscale, out=None):
+    """gradient of sum over kept pixels of coef * (-logp_t) w.r.t. the low-resolution logits x: NHWC fp16, times gscale.  out: accumulate."""
+    N, Cc, Hi, Wi, xcs = nhwc_info(x)
+    Ho, Wo = int(size[0]), int(size[1])
+    acc = out is not None
+    dx = out if acc else empty_nhwc(N, Cc, Hi, Wi, x.device)
+    check(_lib.lib().fsb_loss_ce_bwd(N, Cc, Hi, Wi, Ho, Wo, _ptr(x), xcs, _ptr(target), int(ignore_label), _ptr(lse), _ptr(logp_t), _ptr(thr),
+                                     _ptr(coef), _ptr(dx), nhwc_info(dx)[4], float(gscale), int(acc), _stream()), "fsb_loss_ce_bwd")
+    return dx
+
+
+def loss_kl_fwd(xs, xt, size):
+    """sum over pixels and classes of q (log q - log p), p = softmax(up(xs)), q = softmax(up(xt)) -> (0-d sum, lse_s, lse_t)"""
+    N, Cc, Hs, Ws, scs = nhwc_info(xs)
+    Nt, Ct, Ht, Wt, tcs = nhwc_info(xt)
+    assert (N, Cc) == (Nt, Ct)
+    Ho, Wo = int(size[0]), int(size[1])
+    lse_s = torch.empty((N, Ho, Wo), device=xs.device, dtype=torch.float32)
+    lse_t = torch.empty((N, Ho, Wo), device=xs.device, dtype=torch.float32)
+    out = torch.empty((2,), device=xs.device, dtype=torch.float32)
+    partial = torch.empty((2 * _lib.lib().fsb_loss_rows(),), device=xs.device, dtype=torch.float32)
+    check(_lib.lib().fsb_loss_kl_fwd(N, Cc, Hs, Ws, Ht, Wt, Ho, Wo, _ptr(xs), scs, _ptr(xt), tcs, _ptr(lse_s), _ptr(lse_t), _ptr(partial),
+                                     _ptr(out), _stream()), "fsb_loss_kl_fwd")
+    return out[0], lse_s, lse_t
+
+
+def loss_kl_bwd(xs, xt, size, lse_s, lse_t, coef, gscale, out=None):
+    N, Cc, Hs, Ws, scs = nhwc_info(xs)
+    _, _, Ht, Wt, tcs = nhwc_info(xt)
+    Ho, Wo = int(size[0]), int(size[1])
+    acc = out is not None
+    dx = out if acc else empty_nhwc(N, Cc, Hs, Ws, xs.device)
+    check(_lib.lib().fsb_loss_kl_bwd(N, Cc, Hs, Ws, Ht, Wt, Ho, Wo, _ptr(xs), scs, _ptr(xt), tcs, _ptr(lse_s), _ptr(lse_t), _ptr(coef), _ptr(dx),
+                                     nhwc_info(dx)[4], float(gscale), int(acc), _stream()), "fsb_loss_kl_bwd")
+    return dx

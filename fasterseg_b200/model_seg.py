@@ -320,13 +320,20 @@ class Network_Multi_Path_Infer(nn.Module):
         return self._forward(input)
 
     def _forward(self, input):
+        lazy = self.__dict__.get("lazy_logits", False)   # N1: hand the criteria the low-resolution logits (losses.LazyLogits)
+        if lazy:
+            from .losses import LazyLogits
         if not self.training:
             pred8 = self._features(input)
-            return F_.upsample_logits(pred8, (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8), dtype=self.logits_dtype)
+            size = (int(pred8.size(2)) * 8, int(pred8.size(3)) * 8)
+            if lazy:
+                return LazyLogits(pred8, size, self.logits_dtype)
+            return F_.upsample_logits(pred8, size, dtype=self.logits_dtype)
         outs = []
         for pred, factor in zip(self._features(input), SCALES):   # (pred8, pred16, pred32)
             if pred is not None:
-                pred = _upsample_logits(pred, (pred.size(2) * factor, pred.size(3) * factor), self.logits_dtype)
+                size = (pred.size(2) * factor, pred.size(3) * factor)
+                pred = LazyLogits(pred, size, self.logits_dtype) if lazy else _upsample_logits(pred, size, self.logits_dtype)
             outs.append(pred)
         return tuple(outs)
 

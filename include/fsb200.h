@@ -329,6 +329,37 @@ int fsb_peer_begin(int region, void* stream);
 int fsb_peer_allreduce_f32(void* buf, int64_t n, void* stream);
 int fsb_peer_shutdown(void);
 
+/* N1: the drivers' training criteria evaluated from the LOW-RESOLUTION logits -- no label-resolution class tensor exists.
+ * Replaces, for the fused path, tools/seg_opr/loss_opr.py:63-93 (ProbOhemCrossEntropy2d on F.interpolate'd logits,
+ * train/model_seg.py:357-362) and train/train.py:254-260 (KLDivLoss(log_softmax(student), softmax(teacher))).
+ * logits: NHWC fp16 (N, Hi, Wi, C <= 32) with channel stride a multiple of 8 >= round8(C); labels int64 (N, Ho, Wo);
+ * the upsample is bilinear with align_corners=True to (Ho, Wo).
+ *   fsb_loss_logp_fwd : per label pixel, logp_t = log softmax(up(logits))[target] (0 for ignored / out-of-range labels, i.e.
+ *                       probability 1 like loss_opr.py:73) and lse = log-sum-exp of the interpolated logits.
+ *   fsb_kth_smallest_f32 : exact k-th smallest (1-based) of n floats into *out (device), three radix-histogram passes, no sort;
+ *                       workspace of fsb_kth_workspace_bytes() bytes.
+ *   fsb_ohem_reduce   : out2 = {sum(-logp_t * kept), count(kept)}, kept = valid label & logp_t <= *thr (thr NULL: every valid
+ *                       pixel); partial needs 2 * fsb_loss_rows() floats; fixed-order reduction.
+ *   fsb_loss_ce_bwd   : dlogits (NHWC fp16, stride dcs) (+)= gscale * *coef * sum over kept label pixels of
+ *                       bilinear weight * (softmax - onehot); gather form, no atomics.
+ *   fsb_loss_kl_fwd   : out2[0] = sum over label pixels and classes of q (log q - log p), p = softmax(up(student)),
+ *                       q = softmax(up(teacher)); stores both log-sum-exps.   fsb_loss_kl_bwd: dstudent (+)= gscale * *coef * (p - q)^T. */
+int fsb_loss_logp_fwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* logits, int cstride, const int64_t* target,
+                      int ignore_label, float* logp_t, float* lse, void* stream);
+size_t fsb_kth_workspace_bytes(void);
+int fsb_kth_smallest_f32(const float* x, int64_t n, int64_t k, float* out, void* workspace, void* stream);
+int fsb_loss_rows(void);
+int fsb_ohem_reduce(const float* logp_t, const int64_t* target, int64_t n, int ignore_label, int C, const float* thr, float* partial,
+                    float* out2, void* stream);
+int fsb_loss_ce_bwd(int N, int C, int Hi, int Wi, int Ho, int Wo, const void* logits, int cstride, const int64_t* target,
+                    int ignore_label, const float* lse, const float* logp_t, const float* thr, const float* coef, void* dlogits,
+                    int dcs, float gscale, int accumulate, void* stream);
+int fsb_loss_kl_fwd(int N, int C, int Hs, int Ws, int Ht, int Wt, int Ho, int Wo, const void* student, int scs, const void* teacher,
+                    int tcs, float* lse_s, float* lse_t, float* partial, float* out2, void* stream);
+int fsb_loss_kl_bwd(int N, int C, int Hs, int Ws, int Ht, int Wt, int Ho, int Wo, const void* student, int scs, const void* teacher,
+                    int tcs, const float* lse_s, const float* lse_t, const float* coef, void* dstudent, int dcs, float gscale,
+                    int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
