@@ -4,19 +4,27 @@
 // backward, of every training unit).  A library collective per vector costs 10-20 us of latency each and the calls of the
 // independent ops -- which run on side streams inside the captured passes -- would serialise on one communicator.  Here every
 // rank owns an exchange buffer allocated with cudaMalloc and mapped into its peers through CUDA IPC (one process per GPU;
-// NVSwitch gives every peer full bandwidth), and the all-reduce is a single-block kernel:
-//     write my vector into my buffer's slot  ->  __threadfence_system  ->  st.release.sys flag[slot] = epoch
-//     for every peer, in RANK ORDER: spin on ld.acquire.sys peer.flag[slot] >= epoch, add its vector (volatile loads)
-// The sum order is the rank order on every rank, so all ranks hold bit-identical statistics (and the result is
-// deterministic).  Slots are handed out in call order inside a REGION (one region per captured graph; the call order is the
+// NVSwitch gives every peer full bandwidth), and the all-reduce is a single-block kernel in the style of NCCL's LL protocol:
+//     PUSH: every thread stores its elements as 8-byte {value, epoch} words straight into EVERY PEER's buffer (one NVLink write
+//           each; an 8-byte store is a single transaction, so value and flag arrive together -- no fence, no separate flag)
+//     POLL: then spins on its OWN buffer (local memory) until the word of every peer carries this epoch, and adds the values
+//           in RANK ORDER
+// so an exchange costs one one-way NVLink write latency instead of the remote-read round trips of a pull design (the first version:
+// ~20 us per exchange in the step, profiles/r2_dp_2gpu_session10.log).  The sum order is the rank order on every rank, so all
+// ranks hold bit-identical statistics (and the result is deterministic).  Slots are handed out in call order inside a REGION (one region per captured graph; the call order is the
 // capture order and identical on every rank); `epoch` is a per-region device counter bumped by the first node of the graph, so
 // a replay needs no host involvement.  Payloads are double-buffered by epoch parity: a rank can only be one replay ahead of a
 // peer (it needs the peer's flags of the previous graph to finish it).
 // ORDER: an exchange kernel spins until every rank has arrived, so two ranks that start two DIFFERENT exchanges first (independent
 // branches of a captured pass on side streams) can each hold execution resources the other one's missing kernel needs -- the first
-// 2-GPU runs dead-locked exactly like that (profiles/r2_dp_2gpu_deadlock.log).  All exchanges are therefore issued on ONE internal
-// exchange stream in slot order, fenced to the caller's stream by an event before and an event after (fork / join, legal under
-// stream capture): every rank spins on the same slot at any time, and compute kernels never queue behind a spinning kernel.
+// 2-GPU runs dead-locked exactly like that (profiles/r2_dp_2gpu_deadlock.log).  An exchange is therefore TWO kernels:
+//   push (on the caller's stream, never waits): my {value, epoch} words into every peer's buffer;
+//   pull (spins on LOCAL memory until every peer's words of this epoch have landed, sums in rank order), issued on one of
+//        kPullStreams internal streams (slot % kPullStreams, slot order within a stream), forked from / joined to the caller's
+//        stream by events (legal under stream capture).
+// At most kPullStreams kernels of a rank can be spinning at any time -- far fewer than the device can keep resident -- so a push
+// (and any compute kernel) can always be scheduled; by induction over the slot order the oldest outstanding pull of every rank
+// completes.  One ordered exchange stream (first fix) was dead-lock free too but serialised ~7 000 exchanges per step.
 // The flat gradient all-reduce (1 GB once per step) stays on NCCL (csrc/dp.cu); this file is for the latency-bound part.
 #include "fsb_common.cuh"
 #include "fsb_internal.h"
@@ -25,13 +33,14 @@ namespace fsb {
 
 namespace {
 constexpr int kMaxWorld = 8;
-constexpr int kMaxRegions = 64;
+constexpr int kMaxRegions = 256;
 constexpr int kMaxSlots = 32768;          // flags
-constexpr size_t kPayloadFloats = 24u << 20;  // 96 MB of payload per rank (2 parities inside)
+constexpr size_t kPayloadWords = 96u << 20;   // 8-byte {value, epoch} words: 768 MB per rank (2 parities x world sources inside)
 constexpr int kMaxVec = 4096;             // floats per exchange (one block, 256 threads)
+constexpr int kPullStreams = 8;
 
 struct Slot {
-  uint32_t off;  // float offset of parity 0 inside the payload area; parity 1 follows at off + n
+  uint32_t off;  // word offset inside the payload area; layout [parity][source rank][n]
   uint32_t n;
 };
 
@@ -47,12 +56,12 @@ struct PeerState {
   int region_first[kMaxRegions];
   int region_count[kMaxRegions];
   int region = -1, cursor = 0;
-  cudaStream_t xstream = nullptr;       // the ordered exchange stream
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t xstream[kPullStreams] = {nullptr};   // the pull streams
+  cudaEvent_t ev_in[kPullStreams] = {nullptr}, ev_out[kPullStreams] = {nullptr};
 } g_peer;
 
 constexpr size_t kFlagBytes = static_cast<size_t>(kMaxSlots) * sizeof(unsigned);
-constexpr size_t kBufferBytes = kFlagBytes + kPayloadFloats * sizeof(float);
+constexpr size_t kBufferBytes = kFlagBytes + kPayloadWords * 8;
 
 struct PeerPtrs {
   uint8_t* base[kMaxWorld];
@@ -78,35 +87,48 @@ __global__ void epoch_bump_kernel(unsigned* e) {
   *e += 1;
 }
 
-// v[0..n) <- sum over ranks of v, in rank order
+// push: my elements, as {value, epoch} words, into slot [parity][source = rank] of every peer
 __global__ void __launch_bounds__(256)
-peer_allreduce_kernel(float* __restrict__ v, int n, PeerPtrs pp, int rank, int world, uint32_t slot, uint32_t off,
-                      const unsigned* __restrict__ epoch_ptr) {
+peer_push_kernel(const float* __restrict__ v, int n, PeerPtrs pp, int rank, int world, uint32_t off, const unsigned* __restrict__ epoch_ptr) {
   pdl_launch_dependents();
   pdl_wait();
   const unsigned e = *epoch_ptr;
-  const size_t par = static_cast<size_t>(e & 1u) * n;
-  float* mine = reinterpret_cast<float*>(pp.base[rank] + kFlagBytes) + off + par;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = v[i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned*>(pp.base[rank]) + slot, e);
-  if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) {
-    const unsigned* flag = reinterpret_cast<const unsigned*>(pp.base[threadIdx.x]) + slot;
-    const long long t0 = clock64();
-    while (static_cast<int>(ld_acquire_sys(flag) - e) < 0) {
-      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a rank that never arrives must surface as a launch failure, not a hang
-        printf("fsb200: peer exchange timed out (rank %d waiting for rank %d, slot %u, epoch %u)\n", rank, threadIdx.x, slot, e);
-        __trap();
-      }
+  const size_t par = static_cast<size_t>(e & 1u) * world * n;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) continue;
+    uint2* dst = reinterpret_cast<uint2*>(pp.base[p] + kFlagBytes) + off + par + static_cast<size_t>(rank) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint2 w = make_uint2(__float_as_uint(v[i]), e);
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + i), "r"(w.x), "r"(w.y) : "memory");
     }
   }
-  __syncthreads();
+}
+// pull: v[0..n) <- sum over ranks, in rank order; the peers' elements are polled in my own buffer
+__global__ void __launch_bounds__(256)
+peer_pull_kernel(float* __restrict__ v, int n, PeerPtrs pp, int rank, int world, uint32_t slot, uint32_t off,
+                 const unsigned* __restrict__ epoch_ptr) {
+  const unsigned e = *epoch_ptr;
+  const size_t par = static_cast<size_t>(e & 1u) * world * n;
+  const uint2* mine = reinterpret_cast<const uint2*>(pp.base[rank] + kFlagBytes) + off + par;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float acc = 0.f;
     for (int p = 0; p < world; ++p) {
-      const float* src = reinterpret_cast<const float*>(pp.base[p] + kFlagBytes) + off + par;
-      acc += (p == rank) ? v[i] : ld_volatile_f32(src + i);
+      if (p == rank) {
+        acc += v[i];
+        continue;
+      }
+      const uint2* src = mine + static_cast<size_t>(p) * n + i;
+      uint2 w;
+      const long long t0 = clock64();
+      for (;;) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(src) : "memory");
+        if (w.y == e) break;
+        if (clock64() - t0 > 20000000000LL) {  // ~10 s: a rank that never arrives must surface as a launch failure, not a hang
+          printf("fsb200: peer exchange timed out (rank %d waiting for rank %d, slot %u, epoch %u)\n", rank, p, slot, e);
+          __trap();
+        }
+      }
+      acc += __uint_as_float(w.x);
     }
     v[i] = acc;
   }
@@ -131,38 +153,45 @@ int peer_allreduce_f32(float* buf, int64_t n, cudaStream_t stream) {
     if (g_peer.region_count[r] == 0) g_peer.region_first[r] = g_peer.n_slots;
     if (g_peer.region_first[r] + g_peer.region_count[r] != g_peer.n_slots)
       return set_error(FSB_ERR_INVALID, "peer exchange: region grew after another region was started");
-    if (g_peer.n_slots >= kMaxSlots || g_peer.used + 2 * static_cast<size_t>(n) > kPayloadFloats)
+    if (g_peer.n_slots >= kMaxSlots || g_peer.used + 2 * static_cast<size_t>(n) * g_peer.world > kPayloadWords)
       return set_error(FSB_ERR_INVALID, "peer exchange: out of slots / payload space");
     slot = g_peer.n_slots++;
     g_peer.slots[slot].off = static_cast<uint32_t>(g_peer.used);
     g_peer.slots[slot].n = static_cast<uint32_t>(n);
-    g_peer.used += 2 * static_cast<size_t>(n);
+    g_peer.used += 2 * static_cast<size_t>(n) * g_peer.world;
     g_peer.region_count[r]++;
   }
   g_peer.cursor++;
   PeerPtrs pp;
   for (int i = 0; i < kMaxWorld; ++i) pp.base[i] = g_peer.base[i];
   cudaError_t e;
-  if (!g_peer.xstream) {
+  if (!g_peer.xstream[0]) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    e = cudaStreamCreateWithPriority(&g_peer.xstream, cudaStreamNonBlocking, hi);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_peer.ev_in, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_peer.ev_out, cudaEventDisableTiming);
-    if (e != cudaSuccess) return set_cuda_error(e, "peer exchange stream");
+    for (int i = 0; i < kPullStreams; ++i) {
+      e = cudaStreamCreateWithPriority(&g_peer.xstream[i], cudaStreamNonBlocking, hi);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_peer.ev_in[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_peer.ev_out[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return set_cuda_error(e, "peer exchange streams");
+    }
   }
-  // fork: the exchange waits for everything the caller's stream has issued so far (the producer of buf) ...
-  e = cudaEventRecord(g_peer.ev_in, stream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(g_peer.xstream, g_peer.ev_in, 0);
+  const int xs = slot % kPullStreams;
+  // push on the caller's stream (after the producer of buf, never waits) ...
+  FSB_LAUNCH(peer_push_kernel, dim3(1), dim3(256), 0, stream, static_cast<const float*>(buf), static_cast<int>(n), pp, g_peer.rank, g_peer.world,
+             g_peer.slots[slot].off, static_cast<const unsigned*>(g_peer.epochs + r));
+  e = last_launch_error();
+  if (e != cudaSuccess) return set_cuda_error(e, "peer push launch");
+  // ... fork: the pull waits for everything the caller's stream has issued so far ...
+  e = cudaEventRecord(g_peer.ev_in[xs], stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(g_peer.xstream[xs], g_peer.ev_in[xs], 0);
   if (e != cudaSuccess) return set_cuda_error(e, "peer exchange fork");
-  // (no programmatic dependent launch here: the kernel must not start before the event edge is satisfied)
-  peer_allreduce_kernel<<<1, 256, 0, g_peer.xstream>>>(buf, static_cast<int>(n), pp, g_peer.rank, g_peer.world, static_cast<uint32_t>(slot),
-                                                      g_peer.slots[slot].off, static_cast<const unsigned*>(g_peer.epochs + r));
+  peer_pull_kernel<<<1, 256, 0, g_peer.xstream[xs]>>>(buf, static_cast<int>(n), pp, g_peer.rank, g_peer.world, static_cast<uint32_t>(slot),
+                                                     g_peer.slots[slot].off, static_cast<const unsigned*>(g_peer.epochs + r));
   e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error(e, "peer_allreduce launch");
-  // ... join: the caller's stream continues after the exchange
-  e = cudaEventRecord(g_peer.ev_out, g_peer.xstream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, g_peer.ev_out, 0);
+  if (e != cudaSuccess) return set_cuda_error(e, "peer pull launch");
+  // ... join: the caller's stream continues after the pull
+  e = cudaEventRecord(g_peer.ev_out[xs], g_peer.xstream[xs]);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, g_peer.ev_out[xs], 0);
   if (e != cudaSuccess) return set_cuda_error(e, "peer exchange join");
   return FSB_OK;
 }
@@ -245,9 +274,11 @@ int fsb_peer_shutdown(void) {
     if (p != g_peer.rank && g_peer.base[p]) cudaIpcCloseMemHandle(g_peer.base[p]);
   if (g_peer.local) cudaFree(g_peer.local);
   if (g_peer.epochs) cudaFree(g_peer.epochs);
-  if (g_peer.ev_in) cudaEventDestroy(g_peer.ev_in);
-  if (g_peer.ev_out) cudaEventDestroy(g_peer.ev_out);
-  if (g_peer.xstream) cudaStreamDestroy(g_peer.xstream);
+  for (int i = 0; i < kPullStreams; ++i) {
+    if (g_peer.ev_in[i]) cudaEventDestroy(g_peer.ev_in[i]);
+    if (g_peer.ev_out[i]) cudaEventDestroy(g_peer.ev_out[i]);
+    if (g_peer.xstream[i]) cudaStreamDestroy(g_peer.xstream[i]);
+  }
   g_peer = PeerState();
   return FSB_OK;
 }

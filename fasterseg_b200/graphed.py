@@ -108,11 +108,19 @@ class _PlanAlpha:
         return self.ctx._next_wslot(self.scale, self.row, r_in, r_out)
 
 
+_PEER_REGIONS = 0
+
+
 class PassContext:
     """Everything static about one (architecture, input shape): slots, device tables, packed weights, graphs."""
 
     def __init__(self, model, arch_idx, flat, x_shape, capture, index=0):
         self.model, self.arch_idx, self.flat, self.capture, self.index = model, arch_idx, flat, capture, index
+        # peer-exchange regions (csrc/peer.cu) are process-wide: forward / backward of every pass context ever built get their own ids
+        # (the construction order is the same on every rank)
+        global _PEER_REGIONS
+        self._peer_regions = (_PEER_REGIONS, _PEER_REGIONS + 1)
+        _PEER_REGIONS += 2
         self.dev = flat.S.device
         L = model._layers
         self.rows = (L - 1, L - 1, L - 2)
@@ -258,7 +266,7 @@ class PassContext:
     def _peer_begin(self, direction):
         """data parallel: the SyncBN exchanges of this pass belong to one region of the peer-memory protocol (csrc/peer.cu)"""
         if engine.dp_native():
-            _lib.check(_lib.lib().fsb_peer_begin(2 * self.index + direction, F_._stream()), "fsb_peer_begin")
+            _lib.check(_lib.lib().fsb_peer_begin(self._peer_regions[direction], F_._stream()), "fsb_peer_begin")
 
     def _run_forward(self):
         self._wcount = self._bcount = 0
