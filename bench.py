@@ -191,13 +191,11 @@ def dominant_kernel_roofline(device):
     Algorithmic work per launch: 2*9*Cin*Cout*h*w FLOP; bytes = input + output + weights, each once, fp16.
     The line's `roofline` is the WORSE of the two; both are listed under `layers`."""
     pk = measured_peaks()
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of the heads8 launch
-    for name in ("r2_roofline_traffic.json", "r1_roofline_traffic.json"):
-        tj = os.path.join(ROOT, "profiles", name)
-        if os.path.isfile(tj):
-            with open(tj) as f:
-                traffic = json.load(f).get("traffic_bytes")
-            break
+    traffic = {}  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures, per layer
+    tj = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
+    if os.path.isfile(tj):
+        with open(tj) as f:
+            traffic = {k: v.get("traffic_bytes") for k, v in json.load(f).get("layers", {}).items()}
     layers = []
     for label, Cin, Cout, h, w in (("heads8.conv_3x3: 3x3 128->128 @128x256", 128, 128, 128, 256),
                                    ("stem.1.conv2: 3x3 64->64 @256x512", 64, 64, 256, 512)):
@@ -213,7 +211,7 @@ def dominant_kernel_roofline(device):
                        "us_per_launch": round(us, 2), "roofline_us": round(max(t_tensor, t_hbm) * 1e6, 2),
                        "algorithmic_flops": flops, "algorithmic_bytes": abytes})
     worst = dict(min(layers, key=lambda r: r["frac"]))
-    worst.update({"traffic": traffic if "heads8" in worst["kernel"] else None, "peak_source": pk["source"], "layers": layers,
+    worst.update({"traffic": next((v for k, v in traffic.items() if k in worst["kernel"]), None), "peak_source": pk["source"], "layers": layers,
                   "note": "worse of the two 9.66-GFLOP launches of the frame.  A tcgen05.mma costs ~130-180 cycles whatever N is "
                           "(tools/umma_rate.cu), so heads8 runs channel-major (weights as M = 128, 256 pixels as N) and "
                           "stem.1.conv2 (64 output channels) concatenates the three horizontal taps along N (N = 192, 12 MMAs per "
@@ -337,6 +335,62 @@ def supernet_cpu_step_ms(mode, threads):
     return (time.perf_counter() - t0) * 1e3
 
 
+def distill_cpu_step_ms(threads, batch=1, hw=(512, 1024)):
+    """The reference's CPU path for the teacher -> student distillation step (train/train.py:219-271) through the oracle port: teacher
+    forward (eval), student forward (train) -> 3 upsampled logits, OHEM x3 + KLDivLoss, backward.  Bounded sample: `batch` images
+    (the GPU number is for 12); returns ms for that batch."""
+    from oracle import fasterseg_oracle as orc
+    from tests import helpers as Hh
+    torch.set_num_threads(threads)
+    Hh_, Ww = hw
+    st_t, _ = Hh.student_structure(0)
+    st_s, _ = Hh.student_structure(1)
+    sd_t = orc.random_state_dict(orc.student_param_shapes(st_t, training=False), seed=1)
+    sd_s = orc.random_state_dict(orc.student_param_shapes(st_s, training=True), seed=2)
+    for k, v in sd_s.items():
+        if "running" not in k and v.dtype.is_floating_point:
+            v.requires_grad_(True)
+    x = orc.random_input((batch, 3, Hh_, Ww), seed=3)
+    t = torch.randint(0, 19, (batch, Hh_, Ww), generator=torch.Generator().manual_seed(4))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        tl = orc.student_forward(x, sd_t, st_t, training=False)
+    l8, l16, l32 = orc.student_forward(x, sd_s, st_s, training=True)
+    mk = int(batch * Hh_ * Ww // 16)
+    loss = (orc.ohem_cross_entropy(l8, t, 255, 0.7, mk) + 0.2 * orc.ohem_cross_entropy(l16, t, 255, 0.7, mk)
+            + 0.2 * orc.ohem_cross_entropy(l32, t, 255, 0.7, mk) + orc.distill_kl(l8, tl))
+    loss.backward()
+    return (time.perf_counter() - t0) * 1e3
+
+
+def distill_step_metric(with_cpu):
+    """BASELINE configs[3]: teacher -> student KL-distillation train step, 12 x 3 x 512 x 1024 per GPU, with the reference's criteria
+    (3 x ProbOhemCrossEntropy2d + KLDivLoss) -- fused on the low-resolution logits (N1, csrc/loss.cu) and, for comparison, on
+    materialised label-resolution logits.  Extra key, N = 1 only."""
+    out = {}
+    try:
+        mod = _load_tool("distill_step_bench")
+        for key, lazy in (("fused", True), ("materialised", False)):
+            try:
+                out[key] = mod.measure(12, (512, 1024), steps=5, warmup=2, lazy=lazy, criterion="ohem")
+            except Exception as e:  # noqa: BLE001
+                out[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+            finally:
+                torch.cuda.empty_cache()
+        if with_cpu:
+            try:
+                threads = min(os.cpu_count() or 1, 32)
+                ms = distill_cpu_step_ms(threads, batch=1, hw=(256, 512))
+                out["cpu_baseline"] = {"value": round(ms, 1), "unit": "ms per sample step", "cores": threads, "kind": "port",
+                                       "sample": "ONE step at batch 1 x 3 x 256 x 512 through the CPU oracle port = 1/48 of the pixels of "
+                                                 "the GPU step (12 x 3 x 512 x 1024); bounded to keep the bench within minutes"}
+            except Exception as e:  # noqa: BLE001
+                out["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    except Exception as e:  # noqa: BLE001
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
 def supernet_steps_metric(rank, world, with_cpu):
     """Second half of BASELINE.json's metric: supernet pretrain step (configs[2], 3x3x256x512 per GPU) and search step
     (configs[4], 2x3x224x448 per GPU) of the 16-layer / 252 M parameter supernet through the reference-facing classes:
@@ -379,7 +433,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supernet-step", action="store_true",
-                    help="skip the secondary metric (supernet pretrain / search step, BASELINE configs[2] / [4])")
+                    help="skip the secondary metrics (supernet pretrain / search step, BASELINE configs[2] / [4]; distillation "
+                         "step, configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 30:
@@ -470,10 +525,13 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     steps_metric = None
+    distill_metric = None
     if not args.no_supernet_step:
         del runner, pipe32
         torch.cuda.empty_cache()
         steps_metric = supernet_steps_metric(rank, world, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        if world == 1:
+            distill_metric = distill_step_metric(with_cpu=not args.no_cpu_baseline)
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -509,6 +567,8 @@ def main():
         line["supernet_steps"] = steps_metric
         if isinstance(steps_metric.get("pretrain"), dict) and "value" in steps_metric["pretrain"]:
             line["supernet_step"] = steps_metric["pretrain"]      # round-1 key: the pretrain step
+    if distill_metric is not None:
+        line["distill_step"] = distill_metric
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
         threads = best_cpu_threads(sd)

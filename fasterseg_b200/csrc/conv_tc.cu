@@ -50,6 +50,8 @@ struct ConvTcParams {
   float* stats;   // partial rows (one per spatial tile = blockIdx.x), see bn.cu "Deterministic statistics"
   int stats_C;    // row half-width (row stride = 2 * stats_C floats)
   int stats_off;  // channel offset of this conv's output inside a row
+  int ksplit;     // 1, or 3: a cluster of 3 CTAs (blockIdx.z) shares one output tile, CTA z accumulates kernel row z (3 of the 9 taps)
+  uint32_t part_off;  // byte offset (from the 1024-aligned smem base) of the (ksplit - 1) partial-sum buffers [n_tile][128] fp32 in CTA 0
   int m_tiles;  // persistent kernel only: spatial tiles (tiles_w * tiles_h * N) ...
   int n_tiles;  // ... x output-channel tiles; a CTA walks tile = blockIdx.x, += gridDim.x (n fastest)
 };
@@ -82,7 +84,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   const int w0 = tile_w * p.tw;
   const int h0 = tile_h * p.th;
   const int n0 = blockIdx.y * p.n_tile;
-  const int k_iters = p.taps * p.k_chunks;
+  // split-K over a cluster (K1 on small maps): a tcgen05.mma costs ~150 cycles whatever its N (tools/umma_rate.cu), so a tile's
+  // main loop is a serial chain of 9 * Cin / 16 instructions however small the map is.  With ksplit = 3 the three kernel rows
+  // run on three SMs; CTAs 1 and 2 hand their fp32 accumulators to CTA 0 through distributed shared memory.
+  const int kz = p.ksplit > 1 ? static_cast<int>(blockIdx.z) : 0;
+  const int taps_local = p.taps / p.ksplit;
+  const int tap0 = kz * taps_local;
+  const int k_iters = taps_local * p.k_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a[0]);
@@ -118,7 +126,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     // ================= TMA producer =================
     RingPos rp;
     uint8_t* sa = smem;
-    for (int tap = 0; tap < p.taps; ++tap) {
+    for (int tap = tap0; tap < tap0 + taps_local; ++tap) {
       const CUtensorMap* ma = &p.tmap_a[p.tap_map[tap]];
       const int cw = w0 + p.tap_dw[tap];
       const int chh = h0 + p.tap_dh[tap];
@@ -136,6 +144,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         if (rp.s == 0) sa = smem;
       }
     }
+    if (p.ksplit > 1) cluster_sync_all_threads();
   } else if (warp == 1) {
     // ================= MMA issuer (converged warp, one elected lane issues) =================
     // Lean loop: no integer division, descriptors of stage s = descriptors of stage 0 + s * (stage_bytes >> 4) in the
@@ -164,6 +173,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       rp.advance(p.stages);
       if (rp.s == 0) doff = 0;
     }
+    if (p.ksplit > 1) cluster_sync_all_threads();
   } else {
     // ================= epilogue warps 2..5 =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -181,6 +191,23 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float* part = reinterpret_cast<const float*>(smem + p.part_off);   // [ksplit - 1][n_tile][128] in CTA 0
+    if (p.ksplit > 1) {
+      if (kz > 0) {
+        // hand this CTA's partial accumulator to CTA 0: column-major [channel][pixel] so that a warp writes 128 contiguous bytes
+        const uint32_t remote = mapa_cluster(smem_u32(smem + p.part_off), 0) + static_cast<uint32_t>(kz - 1) * p.n_tile * 512u + m * 4u;
+        for (int c = 0; c < p.n_tile; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) st_cluster_u32(remote + static_cast<uint32_t>(c + j) * 512u, v[j]);
+        }
+        tc_fence_before();
+      }
+      cluster_sync_all_threads();   // release / acquire: the partial sums are visible in CTA 0
+    }
+    if (kz == 0) {
     // per-warp channel statistics of this tile: [4 warps][sum | sumsq][n_tile] in the (now idle) pipeline buffers
     float* s_stat = reinterpret_cast<float*>(smem);
     // TMEM loads are latency-bound (~250 ns per dependent tcgen05.ld + wait): issue up to four 16-column loads, wait once
@@ -199,6 +226,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.ksplit > 1) {
+        for (int z = 0; z < p.ksplit - 1; ++z) {
+          const float* pz = part + (static_cast<size_t>(z) * p.n_tile + c) * 128 + m;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += pz[j * 128];
+        }
+      }
       if (do_stats) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -305,6 +339,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         row[p.stats_C + n0 + ch] = b;
       }
     }
+    }  // kz == 0
     tc_fence_before();
   }
   __syncthreads();
@@ -640,8 +675,24 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > k_iters) stages = k_iters;
+  // ---- split-K over a 3-CTA cluster (one kernel row per CTA) for small maps: the serial MMA chain of a tile shrinks 3x ----
+  p.ksplit = 1;
+  if (!cu && g.taps == 9 && opt(OPT_CONV_KSPLIT) != 0 && m_tiles * n_tiles * 3 <= sms && n_tile <= 128) {
+    const size_t part_bytes = static_cast<size_t>(2) * n_tile * 512;
+    const size_t room = 216 * 1024 - part_bytes;
+    int st3 = static_cast<int>(room / stage_bytes);
+    const int k_local = 3 * p.k_chunks;
+    if (st3 > kMaxStages) st3 = kMaxStages;
+    if (st3 > k_local) st3 = k_local;
+    if (st3 >= 2 || (st3 >= 1 && k_local == 1)) {
+      p.ksplit = 3;
+      stages = st3;
+      p.part_off = static_cast<uint32_t>(stage_bytes * stages);
+    }
+  }
   p.stages = stages;
   size_t smem_bytes = stage_bytes * stages + 1024;
+  if (p.ksplit > 1) smem_bytes += static_cast<size_t>(2) * n_tile * 512;
   // ---- TMA-store epilogue: fp16 output whose pixels start on 16 B and whose channel count is a multiple of 8 ----
   p.tma_store = 0;
   if (!(d->flags & (FSB_CONV_OUT_F32 | FSB_CONV_STATS)) && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
@@ -764,12 +815,29 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
       return FSB_OK;
     }
   }
-  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
-  if (g.bk == 64) {
-    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel<64>), 220 * 1024, "cudaFuncSetAttribute(conv_tc<64>)")) return rc;
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(p.ksplit));
+  if (int rc = ensure_dyn_smem(g.bk == 64 ? reinterpret_cast<const void*>(conv_tc_kernel<64>) : reinterpret_cast<const void*>(conv_tc_kernel<32>),
+                               220 * 1024, "cudaFuncSetAttribute(conv_tc)")) return rc;
+  if (p.ksplit > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = static_cast<unsigned>(p.ksplit);
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    e = g.bk == 64 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<32>, p);
+  } else if (g.bk == 64) {
     e = launch_kernel(conv_tc_kernel<64>, grid, dim3(kThreads), smem_bytes, stream, p);
   } else {
-    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel<32>), 220 * 1024, "cudaFuncSetAttribute(conv_tc<32>)")) return rc;
     e = launch_kernel(conv_tc_kernel<32>, grid, dim3(kThreads), smem_bytes, stream, p);
   }
   if (e != cudaSuccess) return set_cuda_error(e, "conv_tc launch");

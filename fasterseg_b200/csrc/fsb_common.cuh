@@ -129,6 +129,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------------------
+// thread-block clusters: barrier over every thread of the cluster, distributed shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all_threads() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t cta_smem_addr, uint32_t target_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(target_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, load
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
