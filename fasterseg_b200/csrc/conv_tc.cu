@@ -677,7 +677,11 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   if (stages > k_iters) stages = k_iters;
   // ---- split-K over a 3-CTA cluster (one kernel row per CTA) for small maps: the serial MMA chain of a tile shrinks 3x ----
   p.ksplit = 1;
-  if (!cu && g.taps == 9 && opt(OPT_CONV_KSPLIT) != 0 && m_tiles * n_tiles * 3 <= sms && n_tile <= 128) {
+  // Default OFF (FSB_CONV_KSPLIT=1 turns it on): measured on B200 it shortens an isolated small conv by 15-30 % (cell9-0.conv2
+  // 10.3 -> 7.1 us) but inside the frame and the supernet step the small convs of independent branches already overlap on side
+  // streams, and tripling their CTA count costs more concurrency than the shorter chains win (frame 0.393 -> 0.411 ms, pretrain step
+  // 170 -> 191 ms; profiles/r2_conv_bench_ksplit.log).
+  if (!cu && g.taps == 9 && opt(OPT_CONV_KSPLIT) > 0 && m_tiles * n_tiles * 3 <= sms && n_tile <= 128) {
     const size_t part_bytes = static_cast<size_t>(2) * n_tile * 512;
     const size_t room = 216 * 1024 - part_bytes;
     int st3 = static_cast<int>(room / stage_bytes);

@@ -48,7 +48,7 @@ enum Opt {
   OPT_CONV_TC3,          // FSB_CONV_TC3: 0 = never use the channel-major 128x256 kernel, 2 = force it wherever it is supported
   OPT_CONV_TC4,          // FSB_CONV_TC4: 0 = never use the CTA-pair row-rolling kernel, 2 = force it wherever it is supported
   OPT_CONV_TC5,          // FSB_CONV_TC5: 0 = never use the tap-concatenated kernel (Cout <= 64), 2 = force it wherever it is supported
-  OPT_CONV_KSPLIT,       // FSB_CONV_KSPLIT: 0 = never split a 3x3 tile's K over a 3-CTA cluster (conv_tc on small maps)
+  OPT_CONV_KSPLIT,       // FSB_CONV_KSPLIT: 1 = split a 3x3 tile's K over a 3-CTA cluster (conv_tc on small maps); default off
   OPT_COUNT
 };
 int opt(Opt o);
