@@ -252,7 +252,9 @@ class Network_Multi_Path_Infer(nn.Module):
             if step.fork:
                 ctx.fork()
             with ctx.on(step.lead):
-                feat = self.cells[step.key](latest[step.lead])
+                src = latest[step.lead]
+                feat = self.cells[step.key](src)
+                ctx.hold(src, feat)
             stride = int(full_h // feat.size(2))
             for b in step.members:
                 latest[b] = feat
@@ -287,6 +289,7 @@ class Network_Multi_Path_Infer(nn.Module):
                     if training and n == 1:
                         aux[s_coarse].append(taps[s_coarse][b])   # the trunk's 1/16 feature, not the refined one
                     feat = self._arm_refine(arm, refine, coarse, taps[s_skip][b], out=slot if n == len(chain) - 1 else None)
+                    ctx.hold(coarse, taps[s_skip][b], feat)
                 if not chain:
                     feat = outputs8[b]
                     if not grad:
@@ -400,13 +403,21 @@ class _NullCtx:
 
 class _BranchCtx:
     """Routes the work of branch b to its own stream after `fork()`; `join()` makes the main stream wait for all.
-    Cross-stream tensors stay alive in the caller's `outputs*` lists until the forward returns, and every forward starts
-    with a fork-wait / ends with a join, so the caching allocator never hands a block to another stream while it is in use."""
+    Every tensor that work on a side stream reads or writes is parked in `self.keep` until `join()`: the caching allocator
+    frees a block on the stream it was ALLOCATED on, so a feature that a side-stream cell still reads must not lose its last
+    Python reference while that cell is only enqueued (e.g. two branches that stay at the same stride after the fork overwrite
+    `latest[b]` / `taps[..][b]` as they advance)."""
 
     def __init__(self, streams):
         self.streams, self.forked = streams, False
         self.main = torch.cuda.current_stream() if streams else None
         self.fused_in = None
+        self.keep = []
+
+    def hold(self, *tensors):
+        """keep these tensors alive until join() (no-op without side streams)"""
+        if self.streams and self.forked:
+            self.keep.extend(t for t in tensors if t is not None)
 
     def fork(self):
         if self.streams and not self.forked:
@@ -426,6 +437,7 @@ class _BranchCtx:
             for s in self.streams:
                 self.main.wait_stream(s)
             self.forked = False
+        self.keep = []   # after the join the main stream is ordered behind every side-stream reader
 
 
 def _upsample_logits(x, size, dtype):

@@ -114,6 +114,11 @@ class GradSync:
         self.group = group
         self._orig_backward = None
         self.syncs = 0
+        self.names = None      # optional parameter names (same order as params): hashed into the handshake
+
+    def set_names(self, names):
+        assert len(names) == len(self.params)
+        self.names = list(names)
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
@@ -124,16 +129,29 @@ class GradSync:
         if world == 1:
             return
         live = [(i, p) for i, p in enumerate(self.params) if p.grad is not None]
+        if live:
+            dev = live[0][1].grad.device
+        elif self.params:
+            dev = self.params[0].device
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        # fixed-size handshake first, ALWAYS (also with nothing live: a rank that returned early would leave the others hanging in
+        # the collective): count, index sum, and a hash of the NAMES and SHAPES of the live parameters, so that a rank-dependent
+        # parameter order cannot silently mix gradients of different tensors
+        import zlib
+        sig = "|".join("%s:%s" % (self.names[i] if self.names else i, tuple(p.shape)) for i, p in live)
+        h = zlib.crc32(sig.encode())
+        check = torch.tensor([float(len(live)), float(sum(i for i, _ in live) % 1000003), float(h & 0xFFFFF), float(h >> 20)],
+                             device=dev, dtype=torch.float64)
+        lo, hi = check.clone(), check.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        if not (torch.equal(lo, check) and torch.equal(hi, check)):
+            raise RuntimeError("ranks disagree on which parameters received gradients (count / order / names / shapes) -- the "
+                               "sampling RNG streams are not in lock-step (see seed_all_ranks_identically) or the parameter "
+                               "registries differ")
         if not live:
             return
-        dev = live[0][1].grad.device
-        # fixed-size handshake first: a differing participating set would otherwise be a collective size mismatch
-        check = torch.tensor([float(len(live)), float(sum(i for i, _ in live) % 1000003)], device=dev, dtype=torch.float32)
-        got = check.clone()
-        dist.all_reduce(got, group=self.group)
-        if not torch.allclose(got / world, check):
-            raise RuntimeError("ranks disagree on which parameters received gradients -- the sampling RNG streams "
-                               "are not in lock-step (see seed_all_ranks_identically)")
         buckets, cur, cur_bytes = [], [], 0
         for _, p in live:
             nbytes = p.grad.numel() * 4

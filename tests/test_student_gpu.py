@@ -198,3 +198,40 @@ def test_uint8_frame_path_and_device_confusion_matrix():
         k = (gt >= 0) & (gt < 19)
         want = np.bincount(19 * gt[k].astype(int) + p[k].astype(int), minlength=19 ** 2).reshape(19, 19)
         assert np.array_equal(hist, want) and labeled == int(k.sum()) and correct == int((p[k] == gt[k]).sum())
+
+
+@pytest.mark.parametrize("seed,lasts", [(1003, [0, 1, 2]), (1010, [2, 0]), (1031, [1, 0]), (1045, [2, 1]), (1052, [0, 1, 2]), (1059, [2, 1])])
+def test_multi_stream_branches_are_bit_identical_to_serial_on_random_structures(seed, lasts):
+    """branch cells run on side streams and read tensors allocated on the main stream; a feature that loses its last
+    reference while a side-stream cell is only enqueued could be handed to the next main-stream op.  Random 2- and 3-branch
+    structures (branches that stay at the same stride after the fork included), several forwards with allocator churn in between:
+    the multi-stream forward must equal the serial forward BIT FOR BIT (same kernels, only the streams differ)."""
+    import torch.nn as nn
+    from oracle import make_golden_decode as mk
+    from fasterseg_b200.model_seg import Network_Multi_Path_Infer
+    case = mk.draw_case(seed)
+    alphas, betas, ratios = mk.clone_params(case)
+    m = Network_Multi_Path_Infer(alphas, betas, ratios, num_classes=19, layers=case["layers"], Fch=12, width_mult_list=mk.WML,
+                                 stem_head_width=case["stem_head_width"], ignore_skip=case["ignore_skip"])
+    m.eval()
+    m.build_structure(list(lasts))
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, nn.Conv2d):
+                nn.init.kaiming_normal_(mod.weight, mode="fan_in", nonlinearity="relu")
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+    m = m.cuda()
+    x = torch.randn(1, 3, 256, 512, device="cuda")
+    with torch.no_grad():
+        m.parallel_branches = False
+        want = m(x).clone()
+        m.parallel_branches = True
+        for it in range(6):
+            junk = [torch.empty(int(1e6) * (1 + (it + j) % 3), device="cuda").normal_() for j in range(3)]   # allocator churn
+            got = m(x)
+            del junk
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), "multi-stream forward differs from the serial one (iteration %d)" % it
