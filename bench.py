@@ -524,6 +524,14 @@ def main():
     pipe32, e2e32_fps = run_e2e(pool[0], f32_frames)
     clocks = sampler.stop() if rank == 0 else None
 
+    # Everything the headline needs from the device is measured BEFORE the secondary metrics: a failure inside the data-parallel
+    # supernet steps (a peer that never arrives traps the exchange kernel and poisons the CUDA context) must not cost the line.
+    roof = frame_roof = sd_cpu = None
+    if rank == 0:
+        roof = dominant_kernel_roofline(device)
+        frame_roof = frame_sigma_roofline(model, pool[0], ms_total / args.steps * 1000.0)
+        if world == 1 and not args.no_cpu_baseline:
+            sd_cpu = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
     steps_metric = None
     distill_metric = None
     if not args.no_supernet_step:
@@ -534,11 +542,13 @@ def main():
             distill_metric = distill_step_metric(with_cpu=not args.no_cpu_baseline)
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception:  # noqa: BLE001 -- a failed secondary metric must not turn into a non-zero exit of this rank
+                pass
         return
 
-    roof = dominant_kernel_roofline(device)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -562,24 +572,26 @@ def main():
         "roofline": roof,
         "frame_tflops": round(STUDENT_GFLOP * value / world / 1000.0, 2),
     }
-    line["frame_roofline"] = frame_sigma_roofline(model, pool[0], ms_total / args.steps * 1000.0 )
+    line["frame_roofline"] = frame_roof
     if steps_metric is not None:
         line["supernet_steps"] = steps_metric
         if isinstance(steps_metric.get("pretrain"), dict) and "value" in steps_metric["pretrain"]:
             line["supernet_step"] = steps_metric["pretrain"]      # round-1 key: the pretrain step
     if distill_metric is not None:
         line["distill_step"] = distill_metric
-    if world == 1 and not args.no_cpu_baseline:
-        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-        threads = best_cpu_threads(sd)
+    if sd_cpu is not None:
+        threads = best_cpu_threads(sd_cpu)
         frames = 10
-        fps, dt = cpu_port_fps(sd, frames, threads)
+        fps, dt = cpu_port_fps(sd_cpu, frames, threads)
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%d frames of 1x3x1024x2048 through the CPU oracle port (torch CPU fp32), %.1f s" % (frames, dt)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 if __name__ == "__main__":

@@ -96,6 +96,10 @@ _SIGS = {
     "fsb_loss_ce_bwd": (C.c_int, [C.c_int] * 6 + [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P]),
     "fsb_loss_kl_fwd": (C.c_int, [C.c_int] * 8 + [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "fsb_loss_kl_bwd": (C.c_int, [C.c_int] * 8 + [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P]),
+    "fsb_flat_chunk": (C.c_int, []),
+    "fsb_flat_grad_norm": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_float, _P, _P]),
+    "fsb_flat_scale": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    "fsb_flat_sgd": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
     "fsb_dp_unique_id": (C.c_int, [_P]),
     "fsb_dp_init": (C.c_int, [_P, C.c_int, C.c_int]),
     "fsb_dp_world": (C.c_int, []),

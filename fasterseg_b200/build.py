@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfsb200.so")
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_tc4.cu", "conv_tc5.cu", "conv_direct.cu", "resize.cu", "bn.cu", "train.cu", "wgrad_tc.cu", "train_fused.cu", "loss.cu", "dp.cu", "peer.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_tc4.cu", "conv_tc5.cu", "conv_direct.cu", "resize.cu", "bn.cu", "train.cu", "wgrad_tc.cu", "train_fused.cu", "loss.cu", "optim.cu", "dp.cu", "peer.cu"]
 HEADERS = ["fsb_common.cuh", "fsb_internal.h", os.path.join("..", "..", "include", "fsb200.h")]
 
 

@@ -40,7 +40,7 @@ int sm_count() {
 
 static const char* const kOptNames[OPT_COUNT] = {"FSB_CONV_TC2", "FSB_TC2_R", "FSB_TC2_ASTAGES", "FSB_NO_TMA_STORE",
                                                  "FSB_DGRAD_S2_DIRECT", "FSB_WGRAD_TC", "FSB_CONV_PERSIST", "FSB_PERSIST_OCC",
-                                                 "FSB_PERSIST_STAGES", "FSB_UPSAMPLE_V2", "FSB_DETERMINISTIC", "FSB_CONV_TC3", "FSB_CONV_TC4", "FSB_CONV_TC5", "FSB_CONV_KSPLIT"};
+                                                 "FSB_PERSIST_STAGES", "FSB_UPSAMPLE_V2", "FSB_DETERMINISTIC", "FSB_CONV_TC3", "FSB_CONV_TC4", "FSB_CONV_TC5", "FSB_CONV_KSPLIT", "FSB_CONV_NTILE_MIN"};
 static int g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void load_opts() {

@@ -648,7 +648,10 @@ int conv_tc_launch(const fsb_conv_desc* d, const void* x, const void* wpacked, c
   int n_tiles = (g.npad + 255) / 256;
   int n_tile = ((g.npad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
   const int sms = sm_count();
-  while (m_tiles * n_tiles < sms && n_tile > 32) {
+  // FSB_CONV_NTILE_MIN: smallest N tile the split may produce (default 32).  An MMA costs about the same whatever its N,
+  // so splitting N does not shorten a CTA's main loop; it only spreads the weight loads and the epilogue over more SMs.
+  const int nt_min = opt(OPT_CONV_NTILE_MIN) >= 16 ? opt(OPT_CONV_NTILE_MIN) : 32;
+  while (m_tiles * n_tiles < sms && n_tile > nt_min) {
     n_tile = (n_tile / 2 + 15) / 16 * 16;
     n_tiles = (g.npad + n_tile - 1) / n_tile;
   }

@@ -49,6 +49,7 @@ enum Opt {
   OPT_CONV_TC4,          // FSB_CONV_TC4: 0 = never use the CTA-pair row-rolling kernel, 2 = force it wherever it is supported
   OPT_CONV_TC5,          // FSB_CONV_TC5: 0 = never use the tap-concatenated kernel (Cout <= 64), 2 = force it wherever it is supported
   OPT_CONV_KSPLIT,       // FSB_CONV_KSPLIT: 1 = split a 3x3 tile's K over a 3-CTA cluster (conv_tc on small maps); default off
+  OPT_CONV_NTILE_MIN,    // FSB_CONV_NTILE_MIN: lower bound of the output-channel tile when conv_tc splits N to occupy more SMs (default 32)
   OPT_COUNT
 };
 int opt(Opt o);

@@ -60,8 +60,16 @@ def graph_ctx():
     return _GRAPH_CTX
 
 
+WEIGHTS_EPOCH = 0      # bumped by optimizers that write parameters through raw pointers (optim.FlatSGD)
+
+
+def bump_weights_epoch():
+    global WEIGHTS_EPOCH
+    WEIGHTS_EPOCH += 1
+
+
 def _versions(*tensors):
-    return tuple(-1 if t is None else (t._version, t.data_ptr()) for t in tensors)
+    return (WEIGHTS_EPOCH,) + tuple(-1 if t is None else (t._version, t.data_ptr()) for t in tensors)
 
 
 def packed_weight(conv: nn.Conv2d, ci: int, co: int) -> torch.Tensor:
@@ -71,7 +79,7 @@ def packed_weight(conv: nn.Conv2d, ci: int, co: int) -> torch.Tensor:
     cache = conv.__dict__.setdefault("_fsb_wcache", {})
     key = (ci, co)
     weight = conv.weight
-    ver = (weight._version, weight.data_ptr())
+    ver = (weight._version, weight.data_ptr(), WEIGHTS_EPOCH)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]

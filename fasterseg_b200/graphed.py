@@ -37,6 +37,9 @@ from . import functional as F_
 ENABLED = os.environ.get("FSB_GRAPH", "1") != "0"
 
 
+FLAT_BY_PARAM = {}      # id(parameter) -> the FlatGrads that stages its gradient (optim.py looks the flat buffer up here)
+
+
 class FlatGrads:
     """Two flat fp32 buffers over all parameters of a model: `S` (staging: the captured kernels accumulate here) and `G`
     (what `param.grad` views point into after a release)."""
@@ -54,6 +57,12 @@ class FlatGrads:
         self.index = {id(p): i for i, p in enumerate(self.params)}
         self._sviews, self._gviews = {}, {}
         self.dirty = False      # S holds un-released gradients
+        # bookkeeping for the flat step tail (optim.py): which parameters the LAST release handed a gradient view of G, and whether G
+        # is exactly "scale * staging" (every other region zero) -- the precondition of the flat clip / SGD kernels
+        self.live_flags = np.zeros(len(self.params), dtype=np.uint8)
+        self.fresh_release = None
+        for p in self.params:
+            FLAT_BY_PARAM[id(p)] = self
 
     def _view(self, flat, cache, p):
         v = cache.get(id(p))
@@ -78,6 +87,10 @@ class FlatGrads:
     def release(self, touched, scale=1.0):
         """staged gradients -> param.grad of the `touched` parameters (list of Parameters)"""
         fresh = all(p.grad is None for p in touched)
+        self.fresh_release = bool(fresh)
+        self.live_flags[:] = 0
+        for p in touched:
+            self.live_flags[self.index[id(p)]] = 1
         if fresh:
             if scale == 1.0:
                 self.G.copy_(self.S)
@@ -307,7 +320,7 @@ class PassContext:
                 torch.stack([g if g is not None else zero2 for g in dB]) if dB else None)
 
     def _weight_versions(self):
-        return tuple(c.weight._version for c, _, _, _, _ in self._pack_list)
+        return (engine.WEIGHTS_EPOCH,) + tuple(c.weight._version for c, _, _, _, _ in self._pack_list)
 
     def _repack(self):
         for conv, ci, co, dgrad, t in self._pack_list:

@@ -212,6 +212,8 @@ def main(argv=None):
     install_compat_patches()
     install_shadow_modules()
     install_data_parallel()
+    from . import optim
+    optim.install()      # torch.optim.SGD / nn.utils.clip_grad_norm_ take the flat path after a captured `_loss` (torch's otherwise)
     script = argv[0]
     sys.argv = argv
     sys.path.insert(0, os.path.dirname(os.path.abspath(script)) or ".")

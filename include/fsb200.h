@@ -360,6 +360,20 @@ int fsb_loss_kl_bwd(int N, int C, int Hs, int Ws, int Ht, int Wt, int Ho, int Wo
                     int tcs, const float* lse_s, const float* lse_t, const float* coef, void* dstudent, int dcs, float gscale,
                     int accumulate, void* stream);
 
+/* Step tail on the flat gradient buffer of the captured passes: nn.utils.clip_grad_norm_ + torch.optim.SGD(momentum, weight_decay)
+ * (search/train_search.py:246-250, train/train.py:262-270) as table-driven kernels instead of a Python walk over ~5 000 tensors.
+ * segs: array of {float* param, uint32 offset into G / M, uint32 numel} (16 bytes each); map: int32 pairs {segment, chunk} for every
+ * fsb_flat_chunk()-element chunk of every segment; live: one byte per segment (parameters without a gradient this step are skipped,
+ * like torch skips `grad is None`).  fsb_flat_grad_norm: out2 = {total 2-norm of the live gradients (+ sqrt-folded *extra_sq),
+ * min(1, max_norm / (norm + 1e-6))}, fixed summation order; partial: nblocks floats.  fsb_flat_scale: G *= *coef on the live segments.
+ * fsb_flat_sgd: d = g + wd * p; m = momentum * m + d; p -= lr * m. */
+int fsb_flat_chunk(void);
+int fsb_flat_grad_norm(const void* map, int nblocks, const void* segs, const uint8_t* live, const float* G, float* partial,
+                       const float* extra_sq, float max_norm, float* out2, void* stream);
+int fsb_flat_scale(const void* map, int nblocks, const void* segs, const uint8_t* live, float* G, const float* coef, void* stream);
+int fsb_flat_sgd(const void* map, int nblocks, const void* segs, const uint8_t* live, const float* G, float* M, float lr, float momentum,
+                 float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,97 @@
+"""Flat step tail (csrc/optim.cu, fasterseg_b200/optim.py) against torch: clip_grad_norm_ + SGD(momentum, weight_decay) over the gradients
+of a captured supernet `_loss`, several steps, on two identically initialised models -- one driven by torch.optim.SGD /
+torch.nn.utils.clip_grad_norm_, one by FlatSGD / optim.clip_grad_norm_.  Same kernels produce the gradients, so the parameters must
+agree to fp32 rounding of the update arithmetic (FMA contraction differs between ATen's foreach kernels and ours)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _build():
+    from bench import synth_weights_
+    from fasterseg_b200.model_search import Network_Multi_Path
+    WML = [4. / 12, 6. / 12, 8. / 12, 10. / 12, 1.]
+    m = Network_Multi_Path(19, 6, nn.CrossEntropyLoss(ignore_index=255), Fch=12, width_mult_list=WML, prun_modes=['max', 'arch_ratio'],
+                           stem_head_width=[(1, 1), (8. / 12, 8. / 12)])
+    synth_weights_(m, 3)
+    return m.cuda().train()
+
+
+def _weights(m):
+    ps = []
+    for mod in (m.stem, m.cells, m.refine32, m.refine16, m.head0, m.head1, m.head2, m.head02, m.head12):
+        ps += list(mod.parameters())
+    return ps
+
+
+def test_flat_clip_and_sgd_match_torch_arithmetic_step_by_step():
+    """Three optimizer steps on the gradients of a captured `_loss`.  The network amplifies any last-bit difference of the weights from
+    one step to the next, so every step is checked in isolation: from the SAME gradients, parameters and momentum
+    the flat kernels must produce what clip_grad_norm_ + SGD(momentum, weight_decay) produce in torch arithmetic; parameters without
+    a gradient must not move at all (torch skips `grad is None`: no weight decay, no momentum)."""
+    from fasterseg_b200 import optim as FO
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 128, 256, device="cuda")
+    t = torch.randint(0, 19, (2, 16, 32), device="cuda")
+    np.random.seed(11)
+    torch.manual_seed(12)
+    m = _build()
+    ps = _weights(m)
+    lr, mom, wd, max_norm = 0.05, 0.9, 5e-4, 0.5
+    opt = FO.FlatSGD(ps, lr=lr, momentum=mom, weight_decay=wd)
+    named = dict(m.named_parameters())
+    momentum = {k: torch.zeros_like(p) for k, p in named.items()}
+    for step in range(3):
+        opt.zero_grad()
+        loss = m._loss(x, t, True)
+        loss.backward()
+        g0 = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in named.items()}
+        p0 = {k: p.detach().clone() for k, p in named.items()}
+        total = torch.sqrt(sum(g.double().pow(2).sum() for g in g0.values() if g is not None)).float()
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        got_norm = FO.clip_grad_norm_(m.parameters(), max_norm)      # small max_norm: the clip is active
+        assert float(got_norm) == pytest.approx(float(total), rel=2e-6)
+        for k, p in named.items():
+            if g0[k] is not None:
+                assert torch.allclose(p.grad, g0[k] * coef, rtol=2e-6, atol=1e-12), k
+        opt.step()
+        torch.cuda.synchronize()
+        moved = 0
+        for k, p in named.items():
+            mine = any(p is q for q in ps)
+            if g0[k] is None or not mine:
+                assert torch.equal(p.detach(), p0[k]), "%s has no gradient (or is not this optimizer's) but moved" % k
+                continue
+            d = g0[k] * coef + wd * p0[k]
+            momentum[k] = mom * momentum[k] + d
+            want = p0[k] - lr * momentum[k]
+            scale = float(p0[k].abs().max()) + 1e-12
+            assert float((p.detach() - want).abs().max()) <= 2e-6 * scale, (k, step)
+            mb = opt.momentum_buffer(p)
+            assert float((mb - momentum[k]).abs().max()) <= 2e-6 * (float(momentum[k].abs().max()) + 1e-12), (k, step)
+            momentum[k] = mb.clone()      # continue from the kernel's state so that rounding does not accumulate in the comparison
+            moved += 1
+        assert moved > 100
+    assert opt.flat_steps == 3, "the flat path was not taken"
+
+
+def test_flat_path_falls_back_when_gradients_are_not_the_released_views():
+    from fasterseg_b200 import optim as FO
+    lin = nn.Linear(8, 4).cuda()
+    opt = FO.FlatSGD(lin.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-3)
+    ref = nn.Linear(8, 4).cuda()
+    ref.load_state_dict(lin.state_dict())
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-3)
+    x = torch.randn(5, 8, device="cuda")
+    for _ in range(3):
+        for mod, o in ((lin, opt), (ref, ropt)):
+            o.zero_grad()
+            mod(x).pow(2).sum().backward()
+            FO.clip_grad_norm_(mod.parameters(), 1.0)
+            o.step()
+    assert opt.flat_steps == 0
+    for a, b in zip(lin.parameters(), ref.parameters()):
+        assert torch.equal(a, b)

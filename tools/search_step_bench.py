@@ -51,13 +51,20 @@ def weight_params(m):
     return ps
 
 
-def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape=None, graph=None, criterion="ohem"):
+def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape=None, graph=None, criterion="ohem", flat_optim=True):
     """Time `steps` optimizer steps; returns the result dict (identical on every rank).
     tape: None = whatever FSB_TAPE says; True / False = force the one-node-per-forward autograd mode of the EAGER path.
     graph: None = default (captured passes, fasterseg_b200/graphed.py); False = eager per-unit path."""
     from fasterseg_b200 import autograd as AG
+    from fasterseg_b200 import optim as FO
     if tape is not None:
         AG.TAPE_ENABLED = bool(tape)
+    # what fasterseg_b200.launch does for the unmodified drivers: torch.optim.SGD / nn.utils.clip_grad_norm_ become flat-aware
+    # (csrc/optim.cu); the step below keeps the reference's own lines (search/train_search.py:246-250)
+    if flat_optim:
+        FO.install()
+    else:
+        FO.uninstall()
     args = argparse.Namespace(mode=mode, layers=layers, steps=steps, warmup=warmup)
     parallel.seed_all_ranks_identically(12345)   # identical weights + lock-step width sampling / gumbel noise on every rank
     model = build(args.layers, criterion)
@@ -115,9 +122,11 @@ def measure(mode="pretrain", layers=16, steps=3, warmup=1, rank=0, world=1, tape
     dt, tmin, tmax = (float(v) for v in stat)  # median: the step is host-bound and shares the host with other tenants
     if sync:
         sync.uninstall()
+    FO.uninstall()
     return {"metric": "supernet_%s_step_ms" % args.mode, "value": round(dt * 1e3, 1), "min_ms": round(tmin * 1e3, 1),
             "max_ms": round(tmax * 1e3, 1), "unit": "ms/step", "n_gpus": world, "layers": args.layers, "steps": args.steps,
             "warmup": args.warmup, "criterion": criterion,
+            "step_tail": "flat clip_grad_norm_ + SGD kernels (%d flat steps)" % getattr(opt, "flat_steps", 0) if flat_optim else "torch clip_grad_norm_ + torch.optim.SGD",
             "autograd": "captured passes (CUDA graphs)" if model.__dict__.get("_fsb_graph_runner") is not None else ("tape" if AG.TAPE_ENABLED else "per-unit"), "batch_per_gpu": [B, 3, H, W], "images_per_s": round(B * world / dt, 2),
             "grad_syncs": sync.syncs if sync else 0, "loss": float(loss.detach()),
             "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
@@ -132,10 +141,12 @@ def main():
     ap.add_argument("--mode", default="pretrain", choices=["pretrain", "search"])
     ap.add_argument("--graph", type=int, default=1, help="1 = captured passes (default), 0 = eager per-unit path")
     ap.add_argument("--criterion", default="ohem", choices=["ohem", "ce"])
+    ap.add_argument("--flat-optim", type=int, default=1, help="1 = flat clip + SGD kernels (default, what the launcher installs), 0 = torch's")
     args = ap.parse_args()
     rank, local_rank, world = parallel.init_from_env()
     torch.cuda.set_device(local_rank)
-    res = measure(args.mode, args.layers, args.steps, args.warmup, rank, world, graph=bool(args.graph), criterion=args.criterion)
+    res = measure(args.mode, args.layers, args.steps, args.warmup, rank, world, graph=bool(args.graph), criterion=args.criterion,
+                  flat_optim=bool(args.flat_optim))
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
