@@ -241,6 +241,76 @@ def cpu_port_fps(model_state_cpu, frames, threads):
     return frames / dt, dt
 
 
+def reference_student_cpu():
+    """The UNMODIFIED reference's own student network (train/model_seg.py Network_Multi_Path_Infer built as train/train.py:95-118 builds
+    it) on CPU, from the mounted tree or the verbatim copy build() keeps under oracle/_ref -- or None where neither exists."""
+    try:
+        import contextlib
+        from oracle import ref_harness
+        if not ref_harness.reference_available():
+            return None
+        with contextlib.redirect_stdout(sys.stderr):      # the reference prints at import time; stdout carries the JSON line only
+            ns = ref_harness.load_reference("train", "model_seg")
+            model, _, _ = ref_harness.build_reference_student(ns, 1)
+        synth_weights_(model)
+        return model.eval()
+    except Exception:  # noqa: BLE001 -- the port is the fallback
+        return None
+
+
+def reference_fps(model, frames, threads):
+    torch.set_num_threads(threads)
+    x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(12345))
+    with torch.no_grad():
+        model(x)
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            model(x)
+        dt = time.perf_counter() - t0
+    return frames / dt, dt
+
+
+def bind_to_one_numa_node():
+    """Reference arm only: a batch-1 CPU forward is memory-bound and loses ~3x when its threads and buffers straddle two sockets
+    (14.5 vs 4.9 frames/s measured on the same box), so give the reference its best case -- every thread of this process on the
+    CPUs of ONE NUMA node.  Best effort; returns the number of CPUs kept (0 = nothing changed)."""
+    try:
+        have = os.sched_getaffinity(0)
+        best = set()
+        base = "/sys/devices/system/node"
+        for d in sorted(os.listdir(base)):
+            if not (d.startswith("node") and d[4:].isdigit()):
+                continue
+            cpus = set()
+            for part in open(os.path.join(base, d, "cpulist")).read().strip().split(","):
+                if part:
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= have
+            if len(cpus) > len(best):
+                best = cpus
+        if not best or best == have:
+            return 0
+        for tid in os.listdir("/proc/self/task"):
+            try:
+                os.sched_setaffinity(int(tid), best)
+            except OSError:
+                pass
+        return len(best)
+    except Exception:  # noqa: BLE001 -- best effort
+        return 0
+
+
+def best_reference_threads(model):
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best = (0.0, ncpu)
+    for t in sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+        fps, _ = reference_fps(model, 2, t)
+        if fps > best[0]:
+            best = (fps, t)
+    return best[1], best[0]
+
+
 def best_cpu_threads(model_state_cpu):
     """Batch-1 convolutions do not scale to every core of a large host: try a few thread counts on one frame each and keep
     the fastest (the reference arm may use all the host threads it can USE)."""
@@ -257,7 +327,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # nothing of the product (fasterseg_b200) is on this arm: structure, weights and arithmetic all come from oracle/
+    # nothing of the product (fasterseg_b200) is on this arm
+    bound = bind_to_one_numa_node()
+    ref = reference_student_cpu()
+    if ref is not None:      # the reference itself (kind "reference")
+        threads, _ = best_reference_threads(ref)
+        for _ in range(max(0, min(args.warmup, 3) - 1)):
+            reference_fps(ref, 1, threads)
+        fps, dt = reference_fps(ref, args.steps, threads)
+        line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(1000.0 / fps, 2), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "arithmetic": "UNMODIFIED reference (train/model_seg.py) on CPU: fp32 NCHW, torch CPU (ATen/oneDNN)"},
+                "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "reference",
+                                 "sample": "%d frames of 1x3x1024x2048 through the reference's own Network_Multi_Path_Infer (arch_1), torch CPU fp32, best of {all, 1/2, 32, 16, 8} threads = %d (host has %d CPUs; process bound to %s)" % (args.steps, threads, os.cpu_count() or 1, ("the %d CPUs of one NUMA node" % bound) if bound else "its inherited affinity")},
+                "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    # fallback: the oracle port (structure, weights and arithmetic all from oracle/)
     from oracle import fasterseg_oracle as orc
     from tests import helpers as Hh
     st, _ = Hh.student_structure(1)
@@ -580,11 +667,21 @@ def main():
     if distill_metric is not None:
         line["distill_step"] = distill_metric
     if sd_cpu is not None:
-        threads = best_cpu_threads(sd_cpu)
         frames = 10
-        fps, dt = cpu_port_fps(sd_cpu, frames, threads)
-        line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d frames of 1x3x1024x2048 through the CPU oracle port (torch CPU fp32), %.1f s" % (frames, dt)}
+        ref = reference_student_cpu()
+        if ref is not None:
+            ref.load_state_dict(sd_cpu)
+            threads, probe_fps = best_reference_threads(ref)
+            frames = int(min(200, max(10, 12.0 * probe_fps)))      # ~12 s of CPU work
+            fps, dt = reference_fps(ref, frames, threads)
+            line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "reference",
+                                    "sample": "%d frames of 1x3x1024x2048 through the UNMODIFIED reference network (train/model_seg.py, same "
+                                              "weights) on CPU, torch fp32, %.1f s" % (frames, dt)}
+        else:
+            threads = best_cpu_threads(sd_cpu)
+            fps, dt = cpu_port_fps(sd_cpu, frames, threads)
+            line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d frames of 1x3x1024x2048 through the CPU oracle port (torch CPU fp32), %.1f s" % (frames, dt)}
     print(json.dumps(line), flush=True)
     if world > 1:
         try:

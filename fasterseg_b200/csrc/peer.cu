@@ -35,7 +35,8 @@ namespace {
 constexpr int kMaxWorld = 8;
 constexpr int kMaxRegions = 256;
 constexpr int kMaxSlots = 32768;          // flags
-constexpr size_t kPayloadWords = 96u << 20;   // 8-byte {value, epoch} words: 768 MB per rank (2 parities x world sources inside)
+constexpr size_t kPayloadWords = 384u << 20;  // 8-byte {value, epoch} words: 3 GB per rank (2 parities x world sources inside); the 16-layer
+                                              // supernet's pretrain + search passes at world 8 need ~150 M of them, HBM is 180 GB
 constexpr int kMaxVec = 4096;             // floats per exchange (one block, 256 threads)
 constexpr int kPullStreams = 8;
 

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -37,7 +38,11 @@ from . import functional as F_
 ENABLED = os.environ.get("FSB_GRAPH", "1") != "0"
 
 
-FLAT_BY_PARAM = {}      # id(parameter) -> the FlatGrads that stages its gradient (optim.py looks the flat buffer up here)
+# Registries the flat step tail (optim.py) looks buffers up in.  Weak values: the runner of a model owns its FlatGrads, so a model that
+# goes away takes its flat buffers (2 x 4 bytes per parameter) and its registry entries with it -- and a FlatGrads keeps its parameters
+# alive, so an id() in here can never have been recycled for another tensor.
+FLAT_BY_PARAM = weakref.WeakValueDictionary()      # id(parameter) -> the FlatGrads that stages its gradient
+FLAT_BY_MODEL = weakref.WeakValueDictionary()      # id(model) -> its FlatGrads
 
 
 class FlatGrads:
@@ -60,9 +65,13 @@ class FlatGrads:
         # bookkeeping for the flat step tail (optim.py): which parameters the LAST release handed a gradient view of G, and whether G
         # is exactly "scale * staging" (every other region zero) -- the precondition of the flat clip / SGD kernels
         self.live_flags = np.zeros(len(self.params), dtype=np.uint8)
+        self.ever_live = np.zeros(len(self.params), dtype=np.uint8)
         self.fresh_release = None
         for p in self.params:
             FLAT_BY_PARAM[id(p)] = self
+        self.model_ref = weakref.ref(model)
+        self.other_params = [p for p in model.parameters() if not p.requires_grad]      # never carry gradients; kept for completeness
+        FLAT_BY_MODEL[id(model)] = self
 
     def _view(self, flat, cache, p):
         v = cache.get(id(p))
@@ -89,8 +98,8 @@ class FlatGrads:
         fresh = all(p.grad is None for p in touched)
         self.fresh_release = bool(fresh)
         self.live_flags[:] = 0
-        for p in touched:
-            self.live_flags[self.index[id(p)]] = 1
+        self.live_flags[[self.index[id(p)] for p in touched]] = 1
+        self.ever_live |= self.live_flags
         if fresh:
             if scale == 1.0:
                 self.G.copy_(self.S)

@@ -2,8 +2,8 @@
 
 The reference drivers end every step with
 
-    nn.utils.clip_grad_norm_(model.parameters(), config.grad_clip)        # search/train_search.py:248, train/train.py:266
-    optimizer.step()                                                     # torch.optim.SGD(lr, momentum, weight_decay)
+    nn.utils.clip_grad_norm_(model.parameters(), config.grad_clip)        # search/train_search.py:249
+    optimizer.step()                                                     # search/train_search.py:250, train/train.py:269; torch.optim.SGD(lr, momentum, weight_decay)
 
 and torch's implementations of both walk all ~5 000 Parameter objects of the supernet in Python on every step: 17 ms + 42 ms of host
 time with the GPU idle, a third of a 165 ms step (profiles/r2_step_census_pretrain.log).  After a `_loss` of graph mode every weight
@@ -95,20 +95,47 @@ def _flat_of(params):
     return None
 
 
+def _whole_model_generator(parameters):
+    """`model.parameters()` is a generator; consuming it walks ~5 000 modules (10 ms per step).  If the argument is exactly that
+    generator for a model whose gradients live in a flat buffer, return (flat, model) WITHOUT consuming it."""
+    import inspect
+    from . import graphed
+    if not inspect.isgenerator(parameters) or parameters.gi_code is not torch.nn.Module.parameters.__code__ or parameters.gi_frame is None:
+        return None
+    loc = parameters.gi_frame.f_locals
+    model = loc.get("self")
+    if model is None or not loc.get("recurse", True):
+        return None
+    flat = graphed.FLAT_BY_MODEL.get(id(model))
+    return (flat, model) if flat is not None and flat.model_ref() is model else None
+
+
 @torch.no_grad()
 def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=False, foreach=None):
     if isinstance(parameters, torch.Tensor):
         parameters = [parameters]
-    params = list(parameters)
-    flat = _flat_of(params) if float(norm_type) == 2.0 and not error_if_nonfinite else None
+    flat = None
+    whole = _whole_model_generator(parameters) if float(norm_type) == 2.0 and not error_if_nonfinite else None
+    if whole is not None:
+        cand = whole[0]
+        if _flat_of(cand.params[:1]) is cand:      # fresh release, gradients still the released views
+            flat = cand
+            live = flat.live_flags
+            # gradients outside the flat buffer: parameters the captured passes never stage (architecture parameters get theirs from
+            # torch autograd) -- only those that were never live can carry one
+            extra = [flat.params[i].grad for i in np.nonzero(flat.ever_live == 0)[0] if flat.params[i].grad is not None]
+            extra += [p.grad for p in flat.other_params if p.grad is not None]
     if flat is None:
-        return _TORCH_CLIP(params, max_norm, norm_type=norm_type, error_if_nonfinite=error_if_nonfinite, foreach=foreach)
-    live = flat.live_flags
-    inside = {id(p) for p, f in zip(flat.params, live) if f}
-    given = {id(p) for p in params}
-    if not inside.issubset(given):      # the caller clips a subset of the model: torch's semantics need the per-tensor path
-        return _TORCH_CLIP(params, max_norm, norm_type=norm_type, error_if_nonfinite=error_if_nonfinite, foreach=foreach)
-    extra = [p.grad for p in params if p.grad is not None and id(p) not in inside]
+        params = list(parameters)
+        flat = _flat_of(params) if float(norm_type) == 2.0 and not error_if_nonfinite else None
+        if flat is None:
+            return _TORCH_CLIP(params, max_norm, norm_type=norm_type, error_if_nonfinite=error_if_nonfinite, foreach=foreach)
+        live = flat.live_flags
+        inside = {id(p) for p, f in zip(flat.params, live) if f}
+        given = {id(p) for p in params}
+        if not inside.issubset(given):      # the caller clips a subset of the model: torch's semantics need the per-tensor path
+            return _TORCH_CLIP(params, max_norm, norm_type=norm_type, error_if_nonfinite=error_if_nonfinite, foreach=foreach)
+        extra = [p.grad for p in params if p.grad is not None and id(p) not in inside]
     t = _tables(flat)
     t.set_live(live)
     extra_sq = None
@@ -154,6 +181,8 @@ class FlatSGD(torch.optim.Optimizer):
         ok = flat is not None and group["dampening"] == 0 and not group["nesterov"] and not group.get("maximize", False) \
             and (self._fallback is None or not self._fallback.state)
         if not ok:
+            if self._M is not None:
+                self._spill_momentum()
             self._torch_sgd().step()
             return loss
         t = _tables(flat)
@@ -170,6 +199,21 @@ class FlatSGD(torch.optim.Optimizer):
         engine.bump_weights_epoch()
         self.flat_steps += 1
         return loss
+
+    def _spill_momentum(self):
+        """Leaving the flat path (gradients accumulated over several backward passes, a parameter replaced, ...): hand the momentum
+        to torch's per-parameter state so that the trajectory continues; from then on this optimizer stays on torch's path."""
+        from . import graphed
+        fb = self._torch_sgd()
+        for group in self.param_groups:
+            for p in group["params"]:
+                flat = graphed.FLAT_BY_PARAM.get(id(p))
+                if flat is None or id(p) not in flat.offsets or self._M.numel() != flat.G.numel():
+                    continue
+                off = flat.offsets[id(p)]
+                fb.state[p]["momentum_buffer"] = self._M[off:off + p.numel()].view(p.shape).clone()
+        self._M = None
+        self._member = None
 
     def momentum_buffer(self, p):
         """the momentum of parameter p (a view of the flat buffer), for tests / checkpoints"""

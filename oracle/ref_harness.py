@@ -25,7 +25,11 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("FASTERSEG_REFERENCE", "/root/reference")
+# The mounted tree, or -- on the GPU box, where /root/reference does not exist -- the verbatim copy that __graft_entry__.build() drops
+# into the git-ignored oracle/_ref/FasterSeg (build output, never committed; it only exists so that `bench.py --impl reference` and the
+# cpu_baseline leg can time the UNMODIFIED reference on the box's host cores).
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "FasterSeg")
+REFERENCE_ROOT = os.environ.get("FASTERSEG_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/search") else _LOCAL_COPY)
 _SCRATCH = None
 _REF_MODULE_NAMES = (
     "operations", "slimmable_ops", "seg_oprs", "model_seg", "model_search", "genotypes",

@@ -22,12 +22,22 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "fasterseg_student_fps_1024x2048" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" when the reference tree (or build()'s verbatim copy under oracle/_ref) is importable, the oracle port otherwise
+    from oracle import ref_harness
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_harness.reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "1x3x1024x2048" in d["config"]["workload"]
     sys.path.insert(0, ROOT)
     import bench
     assert d["config"]["workload"] == bench.WORKLOAD          # same workload string as our arm
+
+
+def test_reference_arm_falls_back_to_the_port_without_a_reference_tree():
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1"], env={"FASTERSEG_REFERENCE": "/nonexistent"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1 and json.loads(lines[0])["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -95,3 +95,43 @@ def test_flat_path_falls_back_when_gradients_are_not_the_released_views():
     assert opt.flat_steps == 0
     for a, b in zip(lin.parameters(), ref.parameters()):
         assert torch.equal(a, b)
+
+
+def test_momentum_follows_when_leaving_the_flat_path():
+    """one flat step, then a step whose gradients no longer qualify (here: the release is marked stale): torch's per-parameter SGD
+    takes over and must continue from the momentum the flat kernel accumulated"""
+    from fasterseg_b200 import graphed
+    from fasterseg_b200 import optim as FO
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 128, 256, device="cuda")
+    t = torch.randint(0, 19, (2, 16, 32), device="cuda")
+    np.random.seed(21)
+    torch.manual_seed(22)
+    m = _build()
+    ps = _weights(m)
+    lr, mom, wd = 0.05, 0.9, 5e-4
+    opt = FO.FlatSGD(ps, lr=lr, momentum=mom, weight_decay=wd)
+    opt.zero_grad()
+    m._loss(x, t, True).backward()
+    opt.step()
+    assert opt.flat_steps == 1
+    mb = {id(p): opt.momentum_buffer(p).clone() for p in ps}
+    assert sum(float(v.abs().sum()) > 0 for v in mb.values()) > 100
+    opt.zero_grad()
+    m._loss(x, t, True).backward()
+    graphed.FLAT_BY_PARAM[id(ps[0])].fresh_release = False
+    g0 = {id(p): p.grad.detach().clone() for p in ps if p.grad is not None}
+    p0 = {id(p): p.detach().clone() for p in ps}
+    opt.step()
+    torch.cuda.synchronize()
+    assert opt.flat_steps == 1, "the stale release must not take the flat path"
+    checked = 0
+    for p in ps:
+        if id(p) not in g0:
+            assert torch.equal(p.detach(), p0[id(p)])
+            continue
+        buf = mom * mb[id(p)] + g0[id(p)] + wd * p0[id(p)]
+        want = p0[id(p)] - lr * buf
+        assert float((p.detach() - want).abs().max()) <= 2e-6 * (float(p0[id(p)].abs().max()) + 1e-12)
+        checked += 1
+    assert checked > 100

@@ -14,9 +14,15 @@ META = H.load_json("supernet_meta.json")
 CASE = META["case"]
 
 
+_SD_CACHE = {}
+
+
 def make_sd(requires_grad=False):
-    shapes = {k: tuple(v) for k, v in META["shapes"].items()}
-    sd = orc.random_state_dict(shapes, seed=CASE["seed"])
+    """the case's synthetic weights; drawing ~10^8 MT19937 gaussians takes ~10 s, so the draw is done once per process and cloned"""
+    if not _SD_CACHE:
+        shapes = {k: tuple(v) for k, v in META["shapes"].items()}
+        _SD_CACHE.update(orc.random_state_dict(shapes, seed=CASE["seed"]))
+    sd = {k: v.clone() for k, v in _SD_CACHE.items()}
     if requires_grad:
         for k, v in sd.items():
             if "running" not in k:
