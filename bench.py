@@ -323,6 +323,25 @@ def best_cpu_threads(model_state_cpu):
     return best[1]
 
 
+def student_cpu_baseline(sd_cpu, seconds=12.0):
+    """`cpu_baseline` of the default run: the student frame on the host cores, ~`seconds` of CPU work -- through the UNMODIFIED reference
+    network where its tree is available (kind "reference"), else through the oracle port (kind "port"); same weights as the GPU model."""
+    ref = reference_student_cpu()
+    if ref is not None:
+        ref.load_state_dict(sd_cpu)
+        threads, probe_fps = best_reference_threads(ref)
+        frames = int(min(200, max(10, seconds * probe_fps)))
+        fps, dt = reference_fps(ref, frames, threads)
+        return {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": "%d frames of 1x3x%dx%d through the UNMODIFIED reference network (train/model_seg.py, same weights) on CPU, "
+                          "torch fp32, %.1f s" % (frames, H, W, dt)}
+    frames = 10
+    threads = best_cpu_threads(sd_cpu)
+    fps, dt = cpu_port_fps(sd_cpu, frames, threads)
+    return {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d frames of 1x3x%dx%d through the CPU oracle port (torch CPU fp32), %.1f s" % (frames, H, W, dt)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -667,21 +686,10 @@ def main():
     if distill_metric is not None:
         line["distill_step"] = distill_metric
     if sd_cpu is not None:
-        frames = 10
-        ref = reference_student_cpu()
-        if ref is not None:
-            ref.load_state_dict(sd_cpu)
-            threads, probe_fps = best_reference_threads(ref)
-            frames = int(min(200, max(10, 12.0 * probe_fps)))      # ~12 s of CPU work
-            fps, dt = reference_fps(ref, frames, threads)
-            line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "reference",
-                                    "sample": "%d frames of 1x3x1024x2048 through the UNMODIFIED reference network (train/model_seg.py, same "
-                                              "weights) on CPU, torch fp32, %.1f s" % (frames, dt)}
-        else:
-            threads = best_cpu_threads(sd_cpu)
-            fps, dt = cpu_port_fps(sd_cpu, frames, threads)
-            line["cpu_baseline"] = {"value": round(fps, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d frames of 1x3x1024x2048 through the CPU oracle port (torch CPU fp32), %.1f s" % (frames, dt)}
+        try:
+            line["cpu_baseline"] = student_cpu_baseline(sd_cpu)
+        except Exception as e:  # noqa: BLE001 -- the baseline leg must never cost the measured line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s: %s" % (type(e).__name__, e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         try:

@@ -51,3 +51,43 @@ def test_our_arm_refuses_to_run_without_a_gpu():
         return
     r = _run(["--steps", "3", "--warmup", "3"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_default_run_cpu_baseline_leg(monkeypatch):
+    """`cpu_baseline` of our arm's line (bench.student_cpu_baseline): OUR model's state_dict loads into the unmodified reference network
+    key for key (kind "reference"; the oracle port where no reference tree exists), thread count probed, sample bounded.  Small frame
+    so that the leg runs in seconds here; the bench itself uses 1024x2048."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from fasterseg_b200 import zoo
+    from oracle import ref_harness
+    monkeypatch.setattr(bench, "H", 64)
+    monkeypatch.setattr(bench, "W", 128)
+    model = zoo.build_network(1)
+    bench.synth_weights_(model)
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    threads = torch.get_num_threads()
+    try:
+        out = bench.student_cpu_baseline(sd, seconds=0.05)
+    finally:
+        torch.set_num_threads(threads)
+    assert out["kind"] == ("reference" if ref_harness.reference_available() else "port")
+    assert out["value"] > 0 and out["cores"] >= 1 and out["unit"] == "frames/s" and "1x3x64x128" in out["sample"]
+
+
+def test_numa_binding_is_best_effort_and_keeps_a_subset():
+    sys.path.insert(0, ROOT)
+    import bench
+    before = os.sched_getaffinity(0)
+    try:
+        n = bench.bind_to_one_numa_node()
+        after = os.sched_getaffinity(0)
+        assert after <= before and len(after) >= 1
+        assert n in (0, len(after))
+    finally:
+        for tid in os.listdir("/proc/self/task"):
+            try:
+                os.sched_setaffinity(int(tid), before)
+            except OSError:
+                pass
