@@ -128,3 +128,31 @@ def test_graph_mode_second_step_sees_updated_weights_and_keeps_untouched_grads_n
     worst = max(float((p0[k] - p1[k]).norm() / (p0[k].norm() + 1e-12)) for k in p0)
     assert worst < 2e-3, worst   # one fp16 rounding flip of a weight after the optimizer step moves a tensor by ~1e-4
     assert {k for k, p in p0.items() if p.grad is None} == {k for k, p in p1.items() if p.grad is None}
+
+
+def test_flat_buffers_and_registry_entries_go_away_with_the_model():
+    """graphed.FLAT_BY_PARAM / FLAT_BY_MODEL are what the flat step tail (optim.py) looks gradients up in.  They must not keep a model
+    alive: a process that builds several supernets (the reference's search script builds two, the test suite dozens) would otherwise
+    accumulate 2 x 4 bytes per parameter of flat buffers per model -- and an id() of a dead parameter could be recycled."""
+    import gc
+    import weakref
+    from fasterseg_b200 import graphed
+    model = _build_supernet(3).train(True)
+    model.__dict__["_fsb_graph_mode"] = True
+    x = orc.random_input((2, 3, 64, 128), seed=3)
+    tgt = torch.randint(0, 19, (2, 8, 16))
+    np.random.seed(1)
+    torch.manual_seed(2)
+    model._loss(x, tgt, True).backward()
+    flat = graphed.FLAT_BY_MODEL.get(id(model))
+    assert flat is not None and flat.model_ref() is model
+    some = next(p for p, live in zip(flat.params, flat.live_flags) if live)      # a weight whose gradient the passes staged
+    assert graphed.FLAT_BY_PARAM.get(id(some)) is flat
+    assert some.grad is not None and some.grad.data_ptr() == flat.gview(some).data_ptr()
+    n_before = len(graphed.FLAT_BY_PARAM)
+    mid, pid, fref = id(model), id(some), weakref.ref(flat)
+    del flat, some, model
+    gc.collect()
+    assert fref() is None, "the FlatGrads (and with it ~8 bytes per parameter) outlived its model"
+    assert mid not in graphed.FLAT_BY_MODEL and pid not in graphed.FLAT_BY_PARAM
+    assert len(graphed.FLAT_BY_PARAM) < n_before
