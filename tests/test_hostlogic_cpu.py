@@ -262,3 +262,70 @@ def test_uint8_frame_path_matches_normalised_fp32_path_and_gpu_free_metrics():
     assert np.array_equal(hist, want) and labeled == int(k.sum()) and correct == int((p[k] == t[k]).sum())
     iu, miou, _, acc = metric.compute_score(hist, correct, labeled)
     assert 0 <= acc <= 1 and iu.shape == (19,)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# evaluator path (N4) pinned to the reference's own metric / normalisation code (tests/golden/metric.json, oracle/make_golden_metric.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _same_or_both_nan(a, b, tol=1e-12):
+    if b is None:
+        return a is None or (isinstance(a, float) and np.isnan(a))
+    return abs(float(a) - float(b)) <= tol * max(1.0, abs(float(b)))
+
+
+@pytest.mark.parametrize("name", sorted(H.load_json("metric.json")["metric"]))
+def test_device_confusion_matrix_and_scores_match_the_reference_goldens(name):
+    """fasterseg_b200/metric.py against tools/seg_opr/metric.py:7-27 run unmodified (goldens): the confusion matrix, labeled / correct
+    counts (ignore label 255 and negative labels), per-class IoU with absent classes (nan), mean IoU with / without class 0, pixel
+    accuracy -- one image at a time through `ConfusionMatrix.update`, as the evaluator accumulates them."""
+    from fasterseg_b200 import metric
+    from oracle import make_golden_metric as mk
+    want = H.load_json("metric.json")["metric"][name]
+    n_cl, pred, gt = mk.metric_inputs(name)
+    hist, labeled, correct = metric.hist_info(n_cl, torch.from_numpy(pred), torch.from_numpy(gt))
+    assert hist.dtype == np.int64 and hist.tolist() == want["hist"] and labeled == want["labeled"] and correct == want["correct"]
+    cm = metric.ConfusionMatrix(n_cl, device="cpu")
+    for i in range(pred.shape[0]):
+        cm.update(torch.from_numpy(pred[i]), torch.from_numpy(gt[i]))
+    h2, l2, c2 = cm.result()
+    assert h2.tolist() == want["hist"] and (l2, c2) == (labeled, correct)
+    iu, miou, miou_nb, acc = metric.compute_score(hist, correct, labeled)
+    assert len(iu) == n_cl and all(_same_or_both_nan(float(a), b) for a, b in zip(iu, want["iu"]))
+    assert _same_or_both_nan(float(miou), want["mean_IU"]) and _same_or_both_nan(float(miou_nb), want["mean_IU_no_back"])
+    assert _same_or_both_nan(float(acc), want["mean_pixel_acc"])
+
+
+@pytest.mark.parametrize("name", sorted(H.load_json("metric.json")["normalize"]))
+def test_normalisation_table_matches_the_reference_normalize(name):
+    """the 3 x 256 table the stem kernel gathers through (functional.normalization_lut) holds, for every byte value, the fp16 rounding
+    of what tools/utils/img_utils.py:179-185 makes of that byte (goldens: sum / head / tail of the reference's normalised frames)"""
+    from fasterseg_b200 import functional as F_
+    from oracle import make_golden_metric as mk
+    want = H.load_json("metric.json")["normalize"][name]
+    img, mean, std = mk.normalize_inputs(name)
+    lut = F_.normalization_lut(mean, std, "cpu")
+    assert lut.dtype == torch.float16 and tuple(lut.shape) == (3, 256)
+    exact = np.stack([((np.arange(256, dtype=np.uint8).astype(np.float32) / 255.0) - mean[c]) / std[c] for c in range(3)]).astype(np.float32)
+    assert torch.equal(lut, torch.from_numpy(exact).half())
+    frame = np.stack([exact[c][img[..., c]] for c in range(3)], axis=-1)          # gather, like the kernel; HWC fp32 before the fp16 rounding
+    assert abs(float(frame.astype(np.float64).sum()) - want["sum"]) <= 1e-6 * max(1.0, abs(want["sum"]))
+    np.testing.assert_allclose(frame.reshape(-1)[:12], np.array(want["first"], dtype=np.float32), rtol=0, atol=0)
+    np.testing.assert_allclose(frame.reshape(-1)[-12:], np.array(want["last"], dtype=np.float32), rtol=0, atol=0)
+
+
+def test_metric_goldens_are_what_the_live_reference_computes():
+    from oracle import make_golden_metric as mk
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted")
+    metric, normalize = mk.reference_modules()
+    gold = H.load_json("metric.json")
+    for name in mk.CASES:
+        n_cl, pred, gt = mk.metric_inputs(name)
+        hist, labeled, correct = metric.hist_info(n_cl, pred, gt)
+        assert hist.tolist() == gold["metric"][name]["hist"] and int(labeled) == gold["metric"][name]["labeled"]
+        assert int(correct) == gold["metric"][name]["correct"]
+    for name in mk.NORMALIZE_CASES:
+        img, mean, std = mk.normalize_inputs(name)
+        got = np.stack([normalize(im, mean, std) for im in img]).astype(np.float32)
+        assert got.reshape(-1)[:12].tolist() == gold["normalize"][name]["first"]

@@ -200,6 +200,20 @@ def test_uint8_frame_path_and_device_confusion_matrix():
         assert np.array_equal(hist, want) and labeled == int(k.sum()) and correct == int((p[k] == gt[k]).sum())
 
 
+@pytest.mark.parametrize("name", sorted(H.load_json("metric.json")["metric"]))
+def test_confusion_kernel_matches_the_reference_metric_goldens(name):
+    """csrc confusion_kernel against tools/seg_opr/metric.py:7-15 run unmodified (tests/golden/metric.json): ignore label 255, negative
+    labels, absent classes, n_cl = 5; int64 ground truth, and int32 / uint8 where the labels fit"""
+    from fasterseg_b200 import metric
+    from oracle import make_golden_metric as mk
+    want = H.load_json("metric.json")["metric"][name]
+    n_cl, pred, gt = mk.metric_inputs(name)
+    dtypes = [torch.int64, torch.int32] + ([torch.uint8] if gt.min() >= 0 else [])
+    for dtype in dtypes:
+        hist, labeled, correct = metric.hist_info(n_cl, torch.from_numpy(pred).cuda(), torch.from_numpy(gt).to(dtype).cuda())
+        assert hist.tolist() == want["hist"] and labeled == want["labeled"] and correct == want["correct"], (name, dtype)
+
+
 @pytest.mark.parametrize("seed,lasts", [(1003, [0, 1, 2]), (1010, [2, 0]), (1031, [1, 0]), (1045, [2, 1]), (1052, [0, 1, 2]), (1059, [2, 1])])
 def test_multi_stream_branches_are_bit_identical_to_serial_on_random_structures(seed, lasts):
     """branch cells run on side streams and read tensors allocated on the main stream; a feature that loses its last
