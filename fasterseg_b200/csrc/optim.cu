@@ -1,7 +1,7 @@
 // optim.cu -- the step's tail on the flat gradient buffer: clip_grad_norm_ + SGD(momentum, weight decay) over ~5 000 parameter tensors.
 //
 // The captured supernet passes leave every weight gradient in ONE flat fp32 buffer (graphed.FlatGrads); the drivers then call
-// nn.utils.clip_grad_norm_(model.parameters(), 5) and optimizer.step() (search/train_search.py:246-250), whose torch
+// nn.utils.clip_grad_norm_(model.parameters(), 5) and optimizer.step() (search/train_search.py:249-250), whose torch
 // implementations walk all ~5 000 Parameter objects in Python every step: 17 + 42 ms of host time per 165 ms step with the GPU
 // idle (profiles/r2_step_census_pretrain.log).  Here the same arithmetic runs as three table-driven kernels over the flat buffer:
 //   sqnorm : per-block sum of squares of the LIVE segments (parameters that received a gradient this step), fixed-order final sum

@@ -361,7 +361,7 @@ int fsb_loss_kl_bwd(int N, int C, int Hs, int Ws, int Ht, int Wt, int Ho, int Wo
                     int accumulate, void* stream);
 
 /* Step tail on the flat gradient buffer of the captured passes: nn.utils.clip_grad_norm_ + torch.optim.SGD(momentum, weight_decay)
- * (search/train_search.py:246-250, train/train.py:262-270) as table-driven kernels instead of a Python walk over ~5 000 tensors.
+ * (search/train_search.py:249-250, train/train.py:269) as table-driven kernels instead of a Python walk over ~5 000 tensors.
  * segs: array of {float* param, uint32 offset into G / M, uint32 numel} (16 bytes each); map: int32 pairs {segment, chunk} for every
  * fsb_flat_chunk()-element chunk of every segment; live: one byte per segment (parameters without a gradient this step are skipped,
  * like torch skips `grad is None`).  fsb_flat_grad_norm: out2 = {total 2-norm of the live gradients (+ sqrt-folded *extra_sq),
