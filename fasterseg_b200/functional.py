@@ -241,6 +241,31 @@ def confusion_matrix(pred_u8, gt, n_cl, out=None):
     return out
 
 
+# ---- flat step tail (csrc/optim.cu): tables are built by optim.FlatTables ---------------------------------------------------------
+def flat_chunk() -> int:
+    """elements of one block of the flat kernels' block map"""
+    return int(_lib.lib().fsb_flat_chunk())
+
+
+def flat_grad_norm(block_map, nblocks, segs, live, G, partial, extra_sq, max_norm, out2):
+    """out2[0] = 2-norm over the live segments of the flat gradient buffer G (+ extra_sq[0], gradients living elsewhere),
+    out2[1] = min(1, max_norm / (norm + 1e-6)) -- nn.utils.clip_grad_norm_'s total norm and clip coefficient, on the device"""
+    check(_lib.lib().fsb_flat_grad_norm(_ptr(block_map), int(nblocks), _ptr(segs), _ptr(live), _ptr(G), _ptr(partial), _ptr(extra_sq),
+                                        float(max_norm), _ptr(out2), _stream()), "fsb_flat_grad_norm")
+
+
+def flat_scale(block_map, nblocks, segs, live, G, coef):
+    """G[live segments] *= coef[0]"""
+    check(_lib.lib().fsb_flat_scale(_ptr(block_map), int(nblocks), _ptr(segs), _ptr(live), _ptr(G), _ptr(coef), _stream()), "fsb_flat_scale")
+
+
+def flat_sgd(block_map, nblocks, segs, live, G, M, lr, momentum, weight_decay):
+    """torch.optim.SGD arithmetic over the live segments: d = g + wd * p; m = momentum * m + d; p -= lr * m (p through the segment
+    table's storage pointers, g / m in the flat buffers)"""
+    check(_lib.lib().fsb_flat_sgd(_ptr(block_map), int(nblocks), _ptr(segs), _ptr(live), _ptr(G), _ptr(M), float(lr), float(momentum),
+                                  float(weight_decay), _stream()), "fsb_flat_sgd")
+
+
 def bilinear(x, size, relu=False, out=None):
     N, Cc, Hi, Wi, xcs = nhwc_info(x)
     Ho, Wo = int(size[0]), int(size[1])

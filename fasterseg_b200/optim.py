@@ -25,7 +25,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib, engine
+from . import engine
 from . import functional as F_
 
 _TORCH_SGD = torch.optim.SGD
@@ -37,7 +37,7 @@ class FlatTables:
 
     def __init__(self, flat):
         self.flat = flat
-        chunk = _lib.lib().fsb_flat_chunk()
+        chunk = F_.flat_chunk()
         n = len(flat.params)
         seg = np.zeros(n, dtype=[("p", "<u8"), ("off", "<u4"), ("n", "<u4")])
         blocks = []
@@ -141,11 +141,8 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=Fals
     extra_sq = None
     if extra:
         extra_sq = torch.stack([g.detach().float().pow(2).sum() for g in extra]).sum().reshape(1).contiguous()
-    lib = _lib.lib()
-    _lib.check(lib.fsb_flat_grad_norm(F_._ptr(t.map), t.nblocks, F_._ptr(t.segs), F_._ptr(t.live), F_._ptr(flat.G), F_._ptr(t.partial),
-                                      F_._ptr(extra_sq), float(max_norm), F_._ptr(t.norm), F_._stream()), "fsb_flat_grad_norm")
-    _lib.check(lib.fsb_flat_scale(F_._ptr(t.map), t.nblocks, F_._ptr(t.segs), F_._ptr(t.live), F_._ptr(flat.G), F_._ptr(t.norm[1:]),
-                                  F_._stream()), "fsb_flat_scale")
+    F_.flat_grad_norm(t.map, t.nblocks, t.segs, t.live, flat.G, t.partial, extra_sq, max_norm, t.norm)
+    F_.flat_scale(t.map, t.nblocks, t.segs, t.live, flat.G, t.norm[1:])
     for g in extra:
         g.mul_(t.norm[1])
     return t.norm[0].clone()
@@ -193,9 +190,7 @@ class FlatSGD(torch.optim.Optimizer):
         live = flat.live_flags & self._member
         # every gradient this optimizer owns must be one of the released views (otherwise torch's per-tensor path is the safe one)
         t.set_live(live)
-        _lib.check(_lib.lib().fsb_flat_sgd(F_._ptr(t.map), t.nblocks, F_._ptr(t.segs), F_._ptr(t.live), F_._ptr(flat.G), F_._ptr(self._M),
-                                           float(group["lr"]), float(group["momentum"]), float(group["weight_decay"]), F_._stream()),
-                   "fsb_flat_sgd")
+        F_.flat_sgd(t.map, t.nblocks, t.segs, t.live, flat.G, self._M, group["lr"], group["momentum"], group["weight_decay"])
         engine.bump_weights_epoch()
         self.flat_steps += 1
         return loss

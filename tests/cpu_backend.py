@@ -11,6 +11,8 @@ fp16, i.e. the storage semantics documented in include/fsb200.h.  Nothing here i
 import contextlib
 import types
 
+import numpy as np
+
 import torch
 import torch.nn.functional as TF
 
@@ -468,7 +470,67 @@ _PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold
             "upsample_logits", "upsample_argmax", "copy_channels", "bn_stats", "bn_finalize", "affine_act", "bn_bwd_sums", "bn_bwd_apply", "relu_bwd",
             "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
             "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd",
-            "stem_conv_u8hwc", "confusion_matrix", "bn_finalize_sel", "affine_act_sel", "bn_bwd_sel", "conv_bn_act_train_fwd_sel", "conv_bn_act_train_bwd_sel")
+            "stem_conv_u8hwc", "confusion_matrix", "bn_finalize_sel", "affine_act_sel", "bn_bwd_sel", "conv_bn_act_train_fwd_sel", "conv_bn_act_train_bwd_sel",
+            "flat_chunk", "flat_grad_norm", "flat_scale", "flat_sgd")
+
+
+# ---- flat step tail (csrc/optim.cu) on host memory: the segment table holds raw storage pointers, exactly as on the device ------------
+FLAT_CHUNK = 4096
+
+
+def flat_chunk():
+    return FLAT_CHUNK
+
+
+def _flat_tables(block_map, nblocks, segs, live):
+    """decode the tables optim.FlatTables built and check their invariants (what the kernels rely on without checking)"""
+    import ctypes
+    seg = np.frombuffer(segs.numpy().tobytes(), dtype=[("p", "<u8"), ("off", "<u4"), ("n", "<u4")])
+    bm = block_map.numpy().reshape(-1, 2)
+    assert bm.shape[0] == nblocks and block_map.dtype == torch.int32 and live.dtype == torch.uint8 and live.numel() == len(seg)
+    want = np.concatenate([np.stack([np.full((int(n) + FLAT_CHUNK - 1) // FLAT_CHUNK, i), np.arange((int(n) + FLAT_CHUNK - 1) // FLAT_CHUNK)], axis=1)
+                           for i, n in enumerate(seg["n"])])
+    assert np.array_equal(bm, want), "block map does not cover every segment chunk by chunk"
+    ends = seg["off"].astype(np.int64) + seg["n"]
+    assert np.all(seg["off"] % 4 == 0) and np.all(seg["off"][1:] >= ends[:-1]), "segments overlap or are misaligned"
+
+    def param(i):
+        n = int(seg["n"][i])
+        return np.ctypeslib.as_array((ctypes.c_float * n).from_address(int(seg["p"][i])))
+    return seg, live.numpy(), param
+
+
+def flat_grad_norm(block_map, nblocks, segs, live, G, partial, extra_sq, max_norm, out2):
+    seg, lv, _ = _flat_tables(block_map, nblocks, segs, live)
+    g = G.numpy()
+    sq = 0.0
+    for i in np.nonzero(lv)[0]:
+        v = g[int(seg["off"][i]):int(seg["off"][i]) + int(seg["n"][i])].astype(np.float64)
+        sq += float((v * v).sum())
+    if extra_sq is not None:
+        sq += float(extra_sq[0])
+    norm = np.float32(np.sqrt(sq))
+    out2[0] = float(norm)
+    out2[1] = float(min(np.float32(1.0), np.float32(max_norm) / (norm + np.float32(1e-6))))
+
+
+def flat_scale(block_map, nblocks, segs, live, G, coef):
+    seg, lv, _ = _flat_tables(block_map, nblocks, segs, live)
+    g = G.numpy()
+    c = np.float32(float(coef[0]))
+    for i in np.nonzero(lv)[0]:
+        g[int(seg["off"][i]):int(seg["off"][i]) + int(seg["n"][i])] *= c
+
+
+def flat_sgd(block_map, nblocks, segs, live, G, M, lr, momentum, weight_decay):
+    seg, lv, param = _flat_tables(block_map, nblocks, segs, live)
+    g, m = G.numpy(), M.numpy()
+    lr, momentum, wd = np.float32(lr), np.float32(momentum), np.float32(weight_decay)
+    for i in np.nonzero(lv)[0]:
+        lo, hi = int(seg["off"][i]), int(seg["off"][i]) + int(seg["n"][i])
+        p = param(i)
+        m[lo:hi] = momentum * m[lo:hi] + (g[lo:hi] + wd * p)
+        p -= lr * m[lo:hi]
 
 
 @contextlib.contextmanager

@@ -110,3 +110,132 @@ def test_whole_model_generator_is_recognised_without_being_consumed():
         graphed.FLAT_BY_MODEL.pop(id(other))
     finally:
         graphed.FLAT_BY_MODEL.pop(id(m), None)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the flat path itself on the CPU stand-in backend (tests/cpu_backend.py implements fsb_flat_* over the same tables: raw storage
+# pointers, block map, live flags), driven by the gradients of a captured-style `_loss` of a small supernet
+# ---------------------------------------------------------------------------------------------------------------------------
+from tests import cpu_backend  # noqa: E402
+from tests.test_boundary_cpu import _build_supernet  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def flat_case():
+    with cpu_backend.installed():
+        torch.manual_seed(0)
+        model = _build_supernet(3).train(True)
+        model.__dict__["_fsb_graph_mode"] = True
+        with torch.no_grad():
+            g = torch.Generator().manual_seed(5)
+            for ps in model._arch_parameters:
+                for p in ps:
+                    p.add_(torch.randn(p.shape, generator=g) * 0.3)
+        x = torch.randn(2, 3, 64, 128, generator=torch.Generator().manual_seed(1))
+        tgt = torch.randint(0, 19, (2, 8, 16), generator=torch.Generator().manual_seed(2))
+        yield model, x, tgt
+
+
+def _weights(model):
+    return [p for n, p in model.named_parameters() if not n.startswith(("alpha", "beta", "ratio"))]
+
+
+def _backward(model, x, tgt, seed, pretrain=True):
+    np.random.seed(seed)
+    torch.manual_seed(seed + 1)
+    model._loss(x, tgt, pretrain).backward()
+
+
+def test_flat_clip_and_sgd_equal_torch_arithmetic_on_the_stand_in(flat_case):
+    model, x, tgt = flat_case
+    ps = _weights(model)
+    lr, mom, wd, max_norm = 0.05, 0.9, 5e-4, 0.5
+    opt = FO.FlatSGD(ps, lr=lr, momentum=mom, weight_decay=wd)
+    named = dict(model.named_parameters())
+    mine = {id(p) for p in ps}
+    momentum = {k: torch.zeros_like(p) for k, p in named.items()}
+    for step in range(2):
+        model.zero_grad(set_to_none=True)
+        _backward(model, x, tgt, 10 + step, pretrain=(True if step == 0 else "search"))      # step 1: architecture parameters get gradients too
+        g0 = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in named.items()}
+        p0 = {k: p.detach().clone() for k, p in named.items()}
+        total = torch.sqrt(sum(g.double().pow(2).sum() for g in g0.values() if g is not None)).float()
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        got = FO.clip_grad_norm_(model.parameters(), max_norm)           # the drivers' call shape: the whole-model generator
+        assert float(got) == pytest.approx(float(total), rel=1e-6)
+        for k, p in named.items():
+            if g0[k] is not None:
+                assert torch.allclose(p.grad, g0[k] * coef, rtol=1e-6, atol=1e-12), k
+        opt.step()
+        moved = 0
+        for k, p in named.items():
+            if g0[k] is None or id(p) not in mine:
+                assert torch.equal(p.detach(), p0[k]), "%s has no gradient (or is not this optimizer's) but moved" % k
+                continue
+            momentum[k] = mom * momentum[k] + (g0[k] * coef + wd * p0[k])
+            want = p0[k] - lr * momentum[k]
+            assert float((p.detach() - want).abs().max()) <= 1e-6 * (float(p0[k].abs().max()) + 1e-12), (k, step)
+            mb = opt.momentum_buffer(p)
+            assert float((mb - momentum[k]).abs().max()) <= 1e-6 * (float(momentum[k].abs().max()) + 1e-12), (k, step)
+            momentum[k] = mb.clone()
+            moved += 1
+        assert moved > 50
+        if step == 1:
+            assert any(g0[k] is not None for k in named if k.startswith(("alpha", "beta", "ratio"))), "the search step gave no arch gradient"
+    assert opt.flat_steps == 2
+
+
+def test_clipping_a_subset_of_the_model_takes_torchs_path(flat_case):
+    model, x, tgt = flat_case
+    model.zero_grad(set_to_none=True)
+    _backward(model, x, tgt, 30)
+    some = [p for p in _weights(model) if p.grad is not None][:7]
+    g0 = [p.grad.detach().clone() for p in some]
+    want = torch.sqrt(sum(g.double().pow(2).sum() for g in g0)).float()
+    got = FO.clip_grad_norm_(some, 1e-3)
+    assert float(got) == pytest.approx(float(want), rel=1e-5)
+    coef = 1e-3 / (float(want) + 1e-6)
+    for p, g in zip(some, g0):
+        assert torch.allclose(p.grad, g * coef, rtol=1e-5, atol=1e-12)
+    others = [p for p in _weights(model) if p.grad is not None][7:9]
+    assert all(float(p.grad.abs().max()) > 0 for p in others)
+
+
+def test_momentum_is_handed_to_torch_when_a_step_leaves_the_flat_path(flat_case):
+    from fasterseg_b200 import graphed
+    model, x, tgt = flat_case
+    ps = _weights(model)
+    lr, mom, wd, max_norm = 0.05, 0.9, 5e-4, 0.5
+    opt = FO.FlatSGD(ps, lr=lr, momentum=mom, weight_decay=wd)
+    model.zero_grad(set_to_none=True)
+    _backward(model, x, tgt, 40)
+    FO.clip_grad_norm_(model.parameters(), max_norm)
+    opt.step()
+    assert opt.flat_steps == 1
+    mb = {id(p): opt.momentum_buffer(p).clone() for p in ps}
+    assert sum(float(v.abs().sum()) > 0 for v in mb.values()) > 50
+    model.zero_grad(set_to_none=True)
+    _backward(model, x, tgt, 41)
+    FO.clip_grad_norm_(model.parameters(), max_norm)
+    graphed.FLAT_BY_PARAM[id(ps[0])].fresh_release = False          # e.g. gradients accumulated over two backward passes
+    g0 = {id(p): p.grad.detach().clone() for p in ps if p.grad is not None}
+    p0 = {id(p): p.detach().clone() for p in ps}
+    opt.step()
+    assert opt.flat_steps == 1, "the stale release must not take the flat path"
+    checked = 0
+    for p in ps:
+        if id(p) not in g0:
+            assert torch.equal(p.detach(), p0[id(p)])
+            continue
+        buf = mom * mb[id(p)] + (g0[id(p)] + wd * p0[id(p)])
+        want = p0[id(p)] - lr * buf
+        scale = float(p0[id(p)].abs().max()) + lr * float(buf.abs().max()) + 1e-12
+        assert float((p.detach() - want).abs().max()) <= 2e-6 * scale
+        assert torch.allclose(opt.momentum_buffer(p), buf, rtol=1e-5, atol=1e-9)
+        checked += 1
+    assert checked > 50
+    # and it stays on torch's path (its state now holds the momentum), still stepping correctly
+    model.zero_grad(set_to_none=True)
+    _backward(model, x, tgt, 42)
+    opt.step()
+    assert opt.flat_steps == 1
