@@ -239,3 +239,90 @@ def test_weight_packing_and_stem_marshalling(fake):
         F_.nhwc_info(torch.empty(2, 8, 4, 4, dtype=torch.float16))          # NCHW-contiguous: not NHWC-addressable
     with pytest.raises(C.ArgumentError):
         fake.fsb_conv_fwd(None, torch.empty(1), None, None, None, None, None, None)   # a tensor is not a pointer
+
+
+def test_fused_criteria_marshalling(fake):
+    """N1 wrappers (csrc/loss.cu): shapes, channel strides, label geometry, flags and scalar types as include/fsb200.h declares them"""
+    fake.fsb_kth_workspace_bytes = C.CFUNCTYPE(C.c_size_t)(lambda: 4096)
+    fake.fsb_loss_rows = C.CFUNCTYPE(C.c_int)(lambda: 7)
+    x = act(2, 19, 8, 16)                      # low-resolution logits, channel stride 24
+    xt = act(2, 19, 4, 8, wide=8)              # teacher at another resolution inside a wider buffer (stride 32)
+    tgt = torch.zeros(2, 64, 128, dtype=torch.int64)
+    logp, lse = F_.loss_logp_fwd(x, tgt, (64, 128), 255)
+    a = fake.last("fsb_loss_logp_fwd")
+    assert a[:6] == [2, 19, 8, 16, 64, 128] and a[6] == x.data_ptr() and a[7] == 24 and a[8] == tgt.data_ptr() and a[9] == 255
+    assert a[10] == logp.data_ptr() and a[11] == lse.data_ptr() and logp.dtype == lse.dtype == torch.float32
+    assert tuple(logp.shape) == tuple(lse.shape) == (2, 64, 128)
+    with pytest.raises(AssertionError):
+        F_.loss_logp_fwd(x, tgt.int(), (64, 128), 255)          # labels must be int64, like the reference's target.long()
+    k = F_.kth_smallest(logp.reshape(-1), 100)
+    a = fake.last("fsb_kth_smallest_f32")
+    assert a[0] == logp.data_ptr() and a[1:3] == [2 * 64 * 128, 100] and a[3] == k.data_ptr() and k.dim() == 0
+    with pytest.raises(AssertionError):
+        F_.kth_smallest(logp.reshape(-1), 0)
+    red = F_.ohem_reduce(logp, tgt, 255, 19, thr=k)
+    a = fake.last("fsb_ohem_reduce")
+    assert a[0] == logp.data_ptr() and a[1] == tgt.data_ptr() and a[2:5] == [2 * 64 * 128, 255, 19] and a[5] == k.data_ptr()
+    assert a[7] == red.data_ptr() and red.numel() == 2
+    F_.ohem_reduce(logp, tgt, 255, 19)
+    assert fake.last("fsb_ohem_reduce")[5] is None              # no threshold: every valid pixel is kept
+    coef = torch.empty(())
+    dx = F_.loss_ce_bwd(x, tgt, (64, 128), 255, lse, logp, k, coef, 1024.0)
+    a = fake.last("fsb_loss_ce_bwd")
+    assert a[:6] == [2, 19, 8, 16, 64, 128] and a[7] == 24 and a[9] == 255 and a[10] == lse.data_ptr() and a[11] == logp.data_ptr()
+    assert a[12] == k.data_ptr() and a[13] == coef.data_ptr() and a[14] == dx.data_ptr() and a[15] == 24 and a[16] == 1024.0 and a[17] == 0
+    F_.loss_ce_bwd(x, tgt, (64, 128), 255, lse, logp, None, coef, 1024.0, out=dx)
+    a = fake.last("fsb_loss_ce_bwd")
+    assert a[12] is None and a[14] == dx.data_ptr() and a[17] == 1           # accumulate into the given gradient buffer
+    total, lse_s, lse_t = F_.loss_kl_fwd(x, xt, (64, 128))
+    a = fake.last("fsb_loss_kl_fwd")
+    assert a[:8] == [2, 19, 8, 16, 4, 8, 64, 128] and a[8] == x.data_ptr() and a[9] == 24 and a[10] == xt.data_ptr() and a[11] == 32
+    assert a[12] == lse_s.data_ptr() and a[13] == lse_t.data_ptr() and total.dim() == 0
+    dxs = F_.loss_kl_bwd(x, xt, (64, 128), lse_s, lse_t, coef, 1024.0)
+    a = fake.last("fsb_loss_kl_bwd")
+    assert a[:8] == [2, 19, 8, 16, 4, 8, 64, 128] and a[9] == 24 and a[11] == 32 and a[14] == coef.data_ptr() and a[15] == dxs.data_ptr()
+    assert a[16] == 24 and a[17] == 1024.0 and a[18] == 0 and tuple(dxs.shape) == (2, 19, 8, 16)
+
+
+def test_flat_step_tail_marshalling(fake):
+    """csrc/optim.cu through functional.flat_* with the tables optim.FlatTables builds for a (stand-in) flat gradient buffer"""
+    import numpy as np
+    from fasterseg_b200 import optim as FO
+    fake.fsb_flat_chunk = C.CFUNCTYPE(C.c_int)(lambda: 4096)
+
+    class Flat:      # the part of graphed.FlatGrads the tables need
+        def __init__(self, params):
+            self.params, self.offsets, total = params, {}, 0
+            for p in params:
+                self.offsets[id(p)] = total
+                total += (p.numel() + 3) // 4 * 4
+            self.G = torch.zeros(total)
+
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 4096, 4097, 10000)]
+    flat = Flat(params)
+    t = FO.FlatTables(flat)
+    assert t.nblocks == 1 + 1 + 2 + 3 and t.map.dtype == torch.int32 and tuple(t.map.shape) == (7, 2)
+    assert t.map.tolist() == [[0, 0], [1, 0], [2, 0], [2, 1], [3, 0], [3, 1], [3, 2]]
+    seg = np.frombuffer(t.segs.numpy().tobytes(), dtype=[("p", "<u8"), ("off", "<u4"), ("n", "<u4")])
+    assert seg["p"].tolist() == [p.data_ptr() for p in params] and seg["n"].tolist() == [5, 4096, 4097, 10000]
+    assert seg["off"].tolist() == [0, 8, 8 + 4096, 8 + 4096 + 4100] and t.segs.numel() == 4 * 16        # struct FlatSeg is 16 bytes
+    assert t.pointers_valid()
+    t.set_live(np.array([1, 0, 1, 1], dtype=np.uint8))
+    assert t.live.tolist() == [1, 0, 1, 1]
+    extra = torch.empty(1)
+    F_.flat_grad_norm(t.map, t.nblocks, t.segs, t.live, flat.G, t.partial, extra, 5, t.norm)
+    a = fake.last("fsb_flat_grad_norm")
+    assert a[0] == t.map.data_ptr() and a[1] == 7 and a[2] == t.segs.data_ptr() and a[3] == t.live.data_ptr() and a[4] == flat.G.data_ptr()
+    assert a[5] == t.partial.data_ptr() and a[6] == extra.data_ptr() and a[7] == 5.0 and a[8] == t.norm.data_ptr() and t.partial.numel() == 7
+    F_.flat_grad_norm(t.map, t.nblocks, t.segs, t.live, flat.G, t.partial, None, 5.0, t.norm)
+    assert fake.last("fsb_flat_grad_norm")[6] is None
+    F_.flat_scale(t.map, t.nblocks, t.segs, t.live, flat.G, t.norm[1:])
+    a = fake.last("fsb_flat_scale")
+    assert a[1] == 7 and a[4] == flat.G.data_ptr() and a[5] == t.norm.data_ptr() + 4            # the clip coefficient is norm[1]
+    M = torch.zeros_like(flat.G)
+    F_.flat_sgd(t.map, t.nblocks, t.segs, t.live, flat.G, M, 0.05, 0.9, 5e-4)
+    a = fake.last("fsb_flat_sgd")
+    assert a[4] == flat.G.data_ptr() and a[5] == M.data_ptr() and a[6] == pytest.approx(0.05) and a[7] == pytest.approx(0.9)
+    assert a[8] == pytest.approx(5e-4)
+    params[3].data = torch.zeros(10000)              # storage re-allocated behind the table's back (the guard samples first / 97th / last)
+    assert not t.pointers_valid()
