@@ -58,10 +58,10 @@ class FlatTables:
         self.norm = torch.zeros(2, device=dev, dtype=torch.float32)       # [total norm, clip coefficient]
 
     def pointers_valid(self):
-        """cheap guard against a caller that re-allocated parameter storage (p.data = ...): first, last and every 97th pointer"""
-        ps = self.flat.params
-        idx = list(range(0, len(ps), 97)) + [len(ps) - 1]
-        return all(ps[i].data_ptr() == int(self.ptrs[i]) for i in idx)
+        """guard against a caller that re-allocated parameter storage (p.data = ..., model.to(...)): the kernels write the weights through
+        the pointers of the segment table, so EVERY pointer is compared on every use (~0.4 ms for 5 000 parameters, < 1 % of a step)"""
+        cur = np.fromiter(map(torch.Tensor.data_ptr, self.flat.params), dtype=np.uint64, count=len(self.flat.params))
+        return bool(np.array_equal(cur, self.ptrs))
 
     def set_live(self, flags: np.ndarray):
         self.live_host.numpy()[:] = flags

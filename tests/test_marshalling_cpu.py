@@ -324,5 +324,7 @@ def test_flat_step_tail_marshalling(fake):
     a = fake.last("fsb_flat_sgd")
     assert a[4] == flat.G.data_ptr() and a[5] == M.data_ptr() and a[6] == pytest.approx(0.05) and a[7] == pytest.approx(0.9)
     assert a[8] == pytest.approx(5e-4)
-    params[3].data = torch.zeros(10000)              # storage re-allocated behind the table's back (the guard samples first / 97th / last)
+    params[2].data = torch.zeros(4097)               # storage re-allocated behind the table's back: every pointer is compared
     assert not t.pointers_valid()
+    t2 = FO._tables(flat)                            # ... and the tables are rebuilt for the new storage
+    assert t2 is not t and t2.pointers_valid() and int(t2.ptrs[2]) == params[2].data_ptr()
