@@ -22,6 +22,8 @@ Momentum lives in a flat buffer too (zero-initialised: arithmetically identical 
 """
 from __future__ import annotations
 
+from itertools import compress
+
 import numpy as np
 import torch
 
@@ -85,12 +87,11 @@ def _flat_of(params):
             continue
         if flat.fresh_release is not True:
             return None
-        # sampled guard: the live parameters must still carry the released views (not zero_grad()-ed, replaced or re-accumulated since)
-        live = np.nonzero(flat.live_flags)[0]
-        for i in live[:: max(1, len(live) // 16)]:
-            q = flat.params[i]
-            if q.grad is None or q.grad.data_ptr() != flat.gview(q).data_ptr():
-                return None
+        # every live parameter must still carry the view the release handed out (not zero_grad()-ed, replaced or re-accumulated since):
+        # the kernels read the flat buffer, not param.grad.  Identity of the cached view objects: ~0.8 ms for 5 000 parameters.
+        views = flat._gviews
+        if not all(q.grad is views.get(id(q)) for q in compress(flat.params, flat.live_flags.tolist())):
+            return None
         return flat
     return None
 

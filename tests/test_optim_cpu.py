@@ -239,3 +239,29 @@ def test_momentum_is_handed_to_torch_when_a_step_leaves_the_flat_path(flat_case)
     _backward(model, x, tgt, 42)
     opt.step()
     assert opt.flat_steps == 1
+
+
+def test_a_replaced_gradient_anywhere_in_the_model_takes_torchs_path(flat_case):
+    """the flat kernels read the flat buffer, not param.grad: if ANY live parameter no longer carries the released view (here: a caller
+    swapped in a hand-made gradient for one tensor deep inside the model) both calls must fall back to torch, which honours it"""
+    model, x, tgt = flat_case
+    ps = _weights(model)
+    opt = FO.FlatSGD(ps, lr=0.1, momentum=0.0, weight_decay=0.0)
+    model.zero_grad(set_to_none=True)
+    _backward(model, x, tgt, 50)
+    live = [p for p in ps if p.grad is not None]
+    victim = live[len(live) // 2 + 3]
+    victim.grad = torch.full_like(victim, 0.25)
+    p0 = victim.detach().clone()
+    others = {id(p): (p.detach().clone(), p.grad.detach().clone()) for p in live if p is not victim}
+    assert FO._flat_of(ps) is None
+    total = FO.clip_grad_norm_(model.parameters(), 1e9)      # no clipping, but the norm must include the hand-made gradient
+    want = torch.sqrt(sum(p.grad.double().pow(2).sum() for p in model.parameters() if p.grad is not None)).float()
+    assert float(total) == pytest.approx(float(want), rel=1e-5)
+    opt.step()
+    assert opt.flat_steps == 0
+    assert torch.allclose(victim.detach(), p0 - 0.1 * 0.25)
+    for p in live:
+        if p is not victim:
+            w0, g0 = others[id(p)]
+            assert torch.allclose(p.detach(), w0 - 0.1 * g0, rtol=1e-6, atol=1e-9)
