@@ -67,3 +67,18 @@ def test_native_dp_api_is_inert_until_initialised():
     ident = (ctypes.c_char * 128)()
     if lib.fsb_dp_unique_id(ident) == 0:      # needs libnccl.so.2 (bundled with torch); no GPU required for the id
         assert any(bytes(ident))
+
+
+def test_every_entry_point_is_documented_for_the_reference_maintainer():
+    """INTEGRATION.md section 3 maps each export (or its fwd/bwd family) to the reference call site it replaces; the header itself
+    cites reference file:line in the comment block above each family"""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    undocumented = []
+    for s in _header_symbols():
+        stem = re.sub(r"_(fwd|bwd|apply|reduce|sel|f16|f32|nchw|bytes|rows)$", "", s)
+        if s not in doc and stem not in doc:
+            undocumented.append(s)
+    assert not undocumented, undocumented
+    header = open(os.path.join(ROOT, "include", "fsb200.h")).read()
+    cites = re.findall(r"[a-z_/]+\.py:\d+", header)
+    assert len(cites) >= 30, "the header must cite the reference lines its entry points replace"
