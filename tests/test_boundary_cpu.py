@@ -145,3 +145,16 @@ def test_launcher_shadows_reference_module_names():
                 sys.modules.pop(n, None)
             else:
                 sys.modules[n] = m
+
+
+def test_reference_citations_point_into_the_reference_tree():
+    """docstrings, the header and the docs cite the reference as `dir/file.py:LINE[-LINE]`; every one must name an existing reference
+    file and lines inside it (tools/check_citations.py) -- a stale citation sends the parity reviewer to the wrong place"""
+    import sys
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import check_citations
+    bad, total = check_citations.stale(ref_harness.REFERENCE_ROOT)
+    assert total > 300 and not bad, bad[:10]
