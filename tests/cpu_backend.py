@@ -471,7 +471,85 @@ _PATCHED = ("nhwc_info", "to_nhwc_half", "to_nchw", "pack_conv_weight", "bn_fold
             "pack_conv_weight_dgrad", "conv_dgrad", "conv_wgrad", "bilinear_bwd", "upsample_logits_bwd", "nchw_grad_to_nhwc",
             "wsum_fwd", "wsum_bwd", "add_inplace", "conv_bn_act_train_fwd", "conv_bn_act_train_bwd",
             "stem_conv_u8hwc", "confusion_matrix", "bn_finalize_sel", "affine_act_sel", "bn_bwd_sel", "conv_bn_act_train_fwd_sel", "conv_bn_act_train_bwd_sel",
-            "flat_chunk", "flat_grad_norm", "flat_scale", "flat_sgd")
+            "flat_chunk", "flat_grad_norm", "flat_scale", "flat_sgd",
+            "loss_logp_fwd", "kth_smallest", "ohem_reduce", "loss_ce_bwd", "loss_kl_fwd", "loss_kl_bwd")
+
+
+# ---- fused criteria (csrc/loss.cu): same contracts, arithmetic by torch autograd through F.interpolate -----------------------------
+def _valid_labels(target, ignore_label, Cc):
+    return (target != ignore_label) & (target >= 0) & (target < Cc)
+
+
+def _logp_true(up, target, valid):
+    t = torch.where(valid, target, torch.zeros_like(target))
+    return up.gather(1, t.unsqueeze(1)).squeeze(1) - torch.logsumexp(up, dim=1)
+
+
+def loss_logp_fwd(x, target, size, ignore_label):
+    N, Cc, _, _, _ = nhwc_info(x)
+    up = _interp(x.float(), size)
+    valid = _valid_labels(target, ignore_label, Cc)
+    logp = torch.where(valid, _logp_true(up, target, valid), torch.zeros((), dtype=torch.float32))      # ignored pixels: probability 1
+    return logp.contiguous(), torch.logsumexp(up, dim=1).contiguous()
+
+
+def kth_smallest(x, k):
+    assert x.dtype == torch.float32 and x.is_contiguous() and 1 <= k <= x.numel()
+    return torch.kthvalue(x.reshape(-1), int(k)).values.clone()
+
+
+def _kept(logp_t, target, ignore_label, Cc, thr):
+    kept = _valid_labels(target, ignore_label, Cc)
+    if thr is not None:
+        kept = kept & (logp_t.reshape(target.shape) <= thr)
+    return kept
+
+
+def ohem_reduce(logp_t, target, ignore_label, num_classes, thr=None):
+    kept = _kept(logp_t, target, ignore_label, num_classes, thr).reshape(-1)
+    lp = logp_t.reshape(-1)
+    return torch.stack([-(lp[kept].double().sum()).float(), kept.sum().float()])
+
+
+def _to_grad_buffer(g32, gscale, like, out):
+    g = (g32 * gscale).half()
+    if out is None:
+        out = F_.empty_nhwc(*like.shape, like.device)
+        out.copy_(g)
+    else:
+        out.copy_((out.float() + g.float()).half())
+    return out
+
+
+def loss_ce_bwd(x, target, size, ignore_label, lse, logp_t, thr, coef, gscale, out=None):
+    N, Cc, _, _, _ = nhwc_info(x)
+    with torch.enable_grad():
+        xr = x.detach().float().requires_grad_(True)
+        up = _interp(xr, size)
+        valid = _valid_labels(target, ignore_label, Cc)
+        kept = _kept(logp_t, target, ignore_label, Cc, thr)       # the FORWARD's log-probabilities decide, as in the kernel
+        loss = -(torch.where(kept, _logp_true(up, target, valid), torch.zeros((), dtype=torch.float32))).sum() * coef.reshape(())
+        g, = torch.autograd.grad(loss, xr)
+    return _to_grad_buffer(g, gscale, x, out)
+
+
+def _kl_sum(us, ut):
+    logp = torch.log_softmax(us, dim=1)
+    logq = torch.log_softmax(ut, dim=1)
+    return (logq.exp() * (logq - logp)).sum()
+
+
+def loss_kl_fwd(xs, xt, size):
+    us, ut = _interp(xs.float(), size), _interp(xt.float(), size)
+    return _kl_sum(us.double(), ut.double()).float(), torch.logsumexp(us, dim=1).contiguous(), torch.logsumexp(ut, dim=1).contiguous()
+
+
+def loss_kl_bwd(xs, xt, size, lse_s, lse_t, coef, gscale, out=None):
+    with torch.enable_grad():
+        xr = xs.detach().float().requires_grad_(True)
+        loss = _kl_sum(_interp(xr, size), _interp(xt.detach().float(), size)) * coef.reshape(())
+        g, = torch.autograd.grad(loss, xr)
+    return _to_grad_buffer(g, gscale, xs, out)
 
 
 # ---- flat step tail (csrc/optim.cu) on host memory: the segment table holds raw storage pointers, exactly as on the device ------------
