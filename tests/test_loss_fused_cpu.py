@@ -109,3 +109,40 @@ def test_all_terms_of_the_distillation_loss_accumulate_into_one_low_resolution_g
     loss.backward()
     assert float(loss) == pytest.approx(float(want), rel=1e-5)
     _grad_close(x.grad.float() / AG.GRAD_SCALE, dense_in.grad, "ohem + kl")
+
+
+def test_distillation_step_with_lazy_logits_matches_the_materialised_path():
+    """the whole wiring of train/train.py:243-269 on the CPU stand-in: teacher in eval, student in train mode, `lazy_logits` on both ->
+    the heads hand out LazyLogits, the three OHEM terms and the KL term take the fused path, gradients reach every student parameter;
+    same loss and gradients as with materialised logits (two roundings of the same mathematics, amplified by the BatchNorm chains --
+    DESIGN section 4 -- hence the loose gate on the median)"""
+    from bench import synth_weights_
+    from tests.test_boundary_cpu import _build_student
+    g = torch.Generator().manual_seed(0)
+    B, Hh, Ww = 2, 64, 128
+    x = torch.randn(B, 3, Hh, Ww, generator=g)
+    t = torch.randint(0, 19, (B, Hh, Ww), generator=g)
+    t[torch.rand(t.shape, generator=g) < 0.05] = 255
+    crit = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=B * Hh * Ww // 16)
+    results = []
+    for lazy in (False, True):
+        teacher, _ = _build_student(0)
+        synth_weights_(teacher, 1)
+        student, _ = _build_student(1, training=True)
+        synth_weights_(student, 2)
+        teacher.lazy_logits = lazy
+        student.lazy_logits = lazy
+        with torch.no_grad():
+            tl = teacher.eval()(x)
+        l8, l16, l32 = student(x)
+        assert isinstance(l8, LazyLogits) == lazy and isinstance(tl, LazyLogits) == lazy
+        loss = crit(l8, t) + 0.2 * crit(l16, t) + 0.2 * crit(l32, t) + distillation_kl(l8, tl)
+        loss.backward()
+        grads = {k: p.grad.detach().float().clone() for k, p in student.named_parameters() if p.grad is not None}
+        missing = [k for k, p in student.named_parameters() if p.grad is None]
+        results.append((float(loss.detach()), grads, missing))
+    (l0, g0, m0), (l1, g1, m1) = results
+    assert l1 == pytest.approx(l0, rel=2e-3), (l0, l1)
+    assert set(g0) == set(g1) and m0 == m1 and len(g0) > 100
+    rel = sorted(float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-12)) for k in g0)
+    assert rel[len(rel) // 2] < 2e-2, "median relative gradient difference %.3e" % rel[len(rel) // 2]
