@@ -265,3 +265,57 @@ def test_a_replaced_gradient_anywhere_in_the_model_takes_torchs_path(flat_case):
         if p is not victim:
             w0, g0 = others[id(p)]
             assert torch.allclose(p.detach(), w0 - 0.1 * g0, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("graph_mode", [True, False])
+def test_weights_written_through_raw_pointers_invalidate_every_cache(flat_case, graph_mode, monkeypatch):
+    """the flat SGD kernel writes the parameters through their storage pointers: no tensor version counter moves.  The packed-weight /
+    folded-BatchNorm caches of the eager path and the weight snapshot of the captured passes key on engine.WEIGHTS_EPOCH instead; after
+    a flat step the next forward -- captured or eager -- must see the NEW weights: same loss as a freshly built model holding them"""
+    model, x, tgt = flat_case
+    ps = _weights(model)
+    opt = FO.FlatSGD(ps, lr=0.5, momentum=0.0, weight_decay=0.0)
+
+    def loss_of(m, mode):
+        m.__dict__["_fsb_graph_mode"] = mode
+        np.random.seed(77)
+        torch.manual_seed(78)
+        return m._loss(x, tgt, True)
+
+    try:
+        model.zero_grad(set_to_none=True)
+        before = loss_of(model, True)                 # gradients come from the captured-style pass (that is what fills the flat buffer)
+        before.backward()
+        if not graph_mode:
+            with torch.no_grad():
+                loss_of(model, False)                 # warm the EAGER path's caches with the old weights
+        FO.clip_grad_norm_(model.parameters(), 0.5)
+        # the captured passes keep their own packed copies of the weights and refresh them (the `pack` graph on a GPU) when the
+        # (WEIGHTS_EPOCH, tensor versions) snapshot changed; count the refreshes as well as comparing the loss
+        repacks = []
+        contexts = list(model.__dict__["_fsb_graph_runner"].contexts.values())
+        for c in contexts:
+            monkeypatch.setattr(c, "_repack", lambda c=c, real=c._repack: (real(), repacks.append(c)))
+        opt.step()
+        assert opt.flat_steps == 1 and not repacks
+        model.zero_grad(set_to_none=True)
+        if graph_mode:                  # graph mode needs grad mode (model_search.py `_loss`); no backward: the staged gradients are dropped
+            after = float(loss_of(model, True).detach())
+            assert repacks and {id(c) for c in repacks} == {id(c) for c in contexts}, "a captured pass kept its stale packed weights"
+            repacks.clear()
+            loss_of(model, True)
+            assert not repacks, "weights unchanged: no refresh expected"
+        else:
+            with torch.no_grad():
+                after = float(loss_of(model, False))
+        fresh = _build_supernet(3).train(True)
+        fresh.load_state_dict(model.state_dict())
+        if graph_mode:
+            want = float(loss_of(fresh, True).detach())
+        else:
+            with torch.no_grad():
+                want = float(loss_of(fresh, False))
+        assert abs(after - float(before.detach())) > 1e-4 * abs(want), "the step did not change the loss at all?"
+        assert after == pytest.approx(want, rel=1e-5), "a cache still holds the weights from before the flat step"
+    finally:
+        model.__dict__["_fsb_graph_mode"] = True
